@@ -1,0 +1,197 @@
+"""Generate the golden fixtures under tests/golden/ by running the REAL reference code in this
+container (it cannot travel to the GPU box, the fixtures can).
+
+    python tests/golden/make_golden.py            # needs /root/reference
+
+What is real and what is oracle:
+  * ``riemannian_optimizer.py`` is imported unmodified -> ``torus.npz`` is 100% reference output.
+  * ``agent_riemannian.RiemannianAgent.train_and_update``, ``main.predict_quantum_gp``,
+    ``main.k_fold_cross_validation_consensus`` and ``main.main`` run unmodified, with ``import squlearn``
+    satisfied by ``oracle.fake_squlearn``: every line of the reference's own arithmetic (central
+    differences, LAPACK sequence, gradient, rounding, ADMM, prediction, NLPD) is the reference's; only
+    the quantum-kernel values behind ``q_kernel.evaluate`` come from the oracle (parity unpinned there).
+  * scikit-learn 1.9.0's RBF / Matern / ExpSineSquared classes produce ``outer_kernels.npz``.
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from oracle import fake_squlearn  # noqa: E402
+
+fake_squlearn.install()
+import agent_riemannian as AR  # noqa: E402  (the real reference modules)
+import main as M  # noqa: E402
+import riemannian_optimizer as RO  # noqa: E402
+
+from oracle import circuits, driver, statevector  # noqa: E402
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def torus_golden():
+    rng = np.random.RandomState(11)
+    out = {}
+    for case, (a, p, rho) in enumerate([(4, 12, 100.0), (8, 48, 100.0), (3, 5, 1.0), (16, 120, 37.5)]):
+        theta = np.round(rng.rand(a, p) * 4 - 0.5, 4)
+        psi = np.round(rng.randn(a, p) * 30, 4)
+        grad = np.round(rng.randn(p) * 50, 4)
+        man, _, admm = RO.create_riemannian_framework(p, rho=rho)
+        z = admm.update_z(theta, psi)
+        zr = np.round(z, 4)
+        th = admm.update_theta(man.wrap_to_manifold(zr), grad, psi[0], 100.0, None)
+        ps = admm.update_psi(psi[0], th, man.wrap_to_manifold(zr))
+        out.update({f"c{case}_theta": theta, f"c{case}_psi": psi, f"c{case}_grad": grad, f"c{case}_rho": rho,
+                    f"c{case}_z": z, f"c{case}_theta_new": th, f"c{case}_psi_new": ps,
+                    f"c{case}_circmean": RO.circular_mean(theta), f"c{case}_wrap": man.wrap_to_manifold(theta[0] * 3 - 2),
+                    f"c{case}_logmap": man.log_map(theta[0], theta[1]),
+                    f"c{case}_dist": man.distance(theta[0], theta[1])})
+    np.savez_compressed(os.path.join(HERE, "torus.npz"), **out)
+
+
+AGENT_CASES = [
+    # name, encoding, kernel_type, outer, q, layers, d, n
+    ("cheb_proj_matern_q3", "chebyshev", "projected", "matern", 3, 1, 2, 48),
+    ("cheb_proj_gauss_q4", "chebyshev", "projected", "gaussian", 4, 3, 2, 40),
+    ("hub_fid_q5", "hubregtsen", "fidelity", "gaussian", 5, 2, 2, 56),
+    ("hub_proj_ess_q3", "hubregtsen", "projected", "expsinesquared", 3, 2, 4, 33),
+    ("yzcx_proj_gauss_q4", "yz_cx", "projected", "gaussian", 4, 3, 4, 64),
+    ("yzcx_fid_q2", "yz_cx", "fidelity", "gaussian", 2, 2, 1, 30),
+    ("kyr_proj_matern_q4", "kyriienko", "projected", "matern", 4, 2, 6, 37),
+    ("kyr_fid_q3", "kyriienko", "fidelity", "gaussian", 3, 1, 3, 29),
+]
+
+
+def agent_golden():
+    rng = np.random.RandomState(5)
+    for name, enc, ktype, outer, q, layers, d, n in AGENT_CASES:
+        x, y = driver.synthetic_dataset(n, d, enc, seed=abs(hash(name)) % 1000 if False else len(name))
+        qk = quiet(M.create_quantum_kernel, q, d, layers, True, enc, ktype, "XYZ", outer, None, None)
+        p = qk.encoding_circuit.num_parameters
+        z = np.round(rng.rand(p) * 3.5 - 0.2, 4)        # some entries outside [0, pi) to exercise the wrap
+        psi = np.round(rng.rand(p), 4)
+        agent = AR.RiemannianAgent("g", x, y, q, 0.1, 100.0, 100.0, q_kernel=qk, use_parameter_shift=True,
+                                   num_workers=2, shift_value=np.pi / 8, num_layers=layers, encoding_type=enc,
+                                   kernel_type=ktype, measurement="XYZ", outer_kernel=outer)
+        theta_i, psi_i, nll, cond, comp = quiet(agent.train_and_update, z, psi)
+        # also the reference's own K / dK for the same call (method of the real agent)
+        k, dk = quiet(agent._parallel_parameter_shift_kernel_and_derivatives_riemannian, x, np.mod(z, np.pi))
+        # base-set features / states from the oracle, for kernel-level GPU parity
+        gates = circuits.build_circuit(enc, q, d, layers)
+        states = statevector.simulate(gates, q, x, np.mod(z, np.pi))
+        feats = statevector.pauli_features(states, q)
+        # prediction path through the real main.predict_quantum_gp (honours `outer`)
+        xt, yt = driver.synthetic_dataset(17, d, enc, seed=99)
+        mean, var, k_tt, k_st, k_ss = quiet(M.predict_quantum_gp, x, y, xt, np.mod(z, np.pi), q, layers, 0.1, True, enc,
+                                            ktype, "XYZ", outer, None, None)
+        np.savez_compressed(
+            os.path.join(HERE, f"agent_step_{name}.npz"),
+            encoding=enc, kernel_type=ktype, outer_kernel=outer, q=q, layers=layers, d=d,
+            X=x, Y=y, z=z, psi=psi, noise_std=0.1, rho=100.0, L=100.0, h=np.pi / 8,
+            theta_out=theta_i, psi_out=psi_i, nll=nll, cond=cond,
+            log_det_term=comp["log_det_term"], quadratic_term=comp["quadratic_term"],
+            constant_term=comp["constant_term"], K=k,
+            dK_frob=np.array([np.sum(dk[i] ** 2) for i in range(p)]), dK_first=dk[0],
+            states_re=states.real, states_im=states.imag, features=feats,
+            X_test=xt, Y_test=yt, pred_mean=mean, pred_var=var, K_test_train=k_st)
+        print("agent golden", name, "P =", p, "nll =", nll)
+
+
+def outer_kernel_golden():
+    from sklearn.gaussian_process.kernels import RBF, ExpSineSquared, Matern
+    rng = np.random.RandomState(3)
+    f = rng.uniform(-1, 1, (23, 12))
+    g = np.vstack([rng.uniform(-1, 1, (18, 12)), f[:3]])          # three exact duplicates
+    np.savez_compressed(os.path.join(HERE, "outer_kernels.npz"), F=f, G=g,
+                        gaussian=RBF(length_scale=1.0 / np.sqrt(2.0))(f, g),
+                        matern=Matern(length_scale=1.0, nu=1.5)(f, g),
+                        expsinesquared=ExpSineSquared(length_scale=1.0, periodicity=1.0)(f, g))
+
+
+def trajectory_golden(max_iter=4):
+    """BASELINE.json configs[0] through the real main.main(), recording what crosses its process pool."""
+    record = {"iterations": []}
+    real_pool = M.ProcessPoolExecutor
+
+    class RecordingPool(real_pool):
+        def map(self, fn, *iterables, **kw):
+            args = [list(it) for it in iterables]
+            results = list(super().map(fn, *args, **kw))
+            if getattr(fn, "__name__", "") == "process_agent_training":
+                record["iterations"].append({
+                    "z": np.asarray(args[0][0][7]).tolist(),
+                    "psi_in": [np.asarray(a[8]).tolist() for a in args[0]],
+                    "theta_out": [np.asarray(r[0]).tolist() for r in results],
+                    "psi_out": [np.asarray(r[1]).tolist() for r in results],
+                    "nll": [float(r[2]) for r in results],
+                    "cond": [float(r[3]) for r in results],
+                })
+                if "shards" not in record:
+                    record["shards"] = [(np.asarray(a[1]), np.asarray(a[2])) for a in args[0]]
+            return iter(results)
+
+    real_cv = M.k_fold_cross_validation_consensus
+
+    def recording_cv(*a, **k):
+        out = real_cv(*a, **k)
+        record.setdefault("cv", []).append({"mean_nlpd": float(out["mean_nlpd"]),
+                                            "fold_nlpds": [float(v) for v in out["fold_nlpds"]],
+                                            "params": np.asarray(k.get("consensus_params", a[2] if len(a) > 2 else None)).tolist(),
+                                            "random_seed": int(k.get("random_seed", 42))})
+        if "train" not in record:
+            record["train"] = (np.asarray(k["X_train"]), np.asarray(k["Y_train"]))
+        return out
+
+    M.ProcessPoolExecutor = RecordingPool
+    M.k_fold_cross_validation_consensus = recording_cv
+    # matplotlib is a stub here: make the three plotting helpers no-ops (they do not touch the numerics)
+    for fn in ("plot_quantum_gp_data", "plot_agent_data_distribution", "plot_predictions"):
+        setattr(M, fn, lambda *a, **k: None)
+    argv = ("main.py --input-dim 2 --n-dataset 1000 --encoding chebyshev --kernel-type projected --num-layers 1 "
+            "--num-qubits 3 --outer-kernel matern --rho 100 --L 100 --n-agents 4 --no-plot --seed 42 --data-seed 7 "
+            f"--max-iter {max_iter}").split()
+    old = sys.argv
+    sys.argv = argv
+    log = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(log):
+            M.main()
+    except Exception as e:  # post-training reporting may trip over the matplotlib stub; ADMM is recorded by then
+        print("main() stopped after the ADMM loop with:", repr(e)[:200])
+    finally:
+        sys.argv = old
+        M.ProcessPoolExecutor = real_pool
+        M.k_fold_cross_validation_consensus = real_cv
+    shards = record.pop("shards")
+    xtr, ytr = record.pop("train")
+    arrays = {"X_train": xtr, "Y_train": ytr}
+    for a, (xa, ya) in enumerate(shards):
+        arrays[f"X_{a}"] = xa
+        arrays[f"Y_{a}"] = ya
+    np.savez_compressed(os.path.join(HERE, "trajectory_cfg1_data.npz"), **arrays)
+    record["argv"] = " ".join(argv)
+    record["n_agents"] = len(shards)
+    with open(os.path.join(HERE, "trajectory_cfg1.json"), "w") as f:
+        json.dump(record, f, indent=1)
+    print("trajectory golden:", len(record["iterations"]), "iterations; shard sizes", [s[0].shape[0] for s in shards])
+    return log.getvalue()
+
+
+if __name__ == "__main__":
+    torus_golden()
+    outer_kernel_golden()
+    agent_golden()
+    log = trajectory_golden()
+    with open("/tmp/main_cfg1.log", "w") as f:
+        f.write(log)
