@@ -1,0 +1,126 @@
+"""``RiemannianAgent`` and ``process_agent_training`` with the reference's constructor / call signatures
+(``agent_riemannian.py:126-491``, ``main.py:1311-1362``), executing the whole step on the GPU.
+
+Host arrays in, host arrays out: every call copies the agent's shard, z and psi_i to the device (the
+reference pickles the same data to its worker processes every iteration) and reads back
+``(theta_i, psi_i, nll_loss, condition_number, nll_components)``.  Both process pools of the reference
+(agents x shifted-parameter jobs) collapse into one stream of kernels.
+
+Reference behaviours kept: only the (2P+1)-evaluation central-difference path exists (Q3/Q4); training
+Grams use the Gaussian outer kernel whatever ``outer_kernel`` says (Q1) unless
+``training_ignores_outer_kernel=False``; gradient, theta_i and psi_i are rounded to 4 decimals (Q5);
+``riemannian_*`` arguments are accepted and inert (Q8).  Deviation, documented: ``condition_number`` is NaN
+unless ``compute_condition_number=True`` (the reference's ``np.linalg.cond`` is an O(n^3) SVD used only in
+prints, main.py:2629-2642).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import AgentEngine
+from .kernels import dev_f64
+from .riemannian import create_riemannian_framework
+
+_ENGINE_CACHE = {}     # per-process, like the reference's per-process kernel cache (main.py:147-159)
+
+
+def _engine_for(key, factory):
+    eng = _ENGINE_CACHE.get(key)
+    if eng is None:
+        if len(_ENGINE_CACHE) >= 64:
+            _ENGINE_CACHE.clear()
+        eng = _ENGINE_CACHE[key] = factory()
+    return eng
+
+
+class RiemannianAgent:
+    def __init__(self, agent_id, X_sub, Y_sub, num_qubits, noise_std, rho, L, q_kernel=None, use_parameter_shift=False,
+                 num_workers=None, shift_value=np.pi / 8, num_layers=2, combined_computation=True, encoding_type="yz_cx",
+                 kernel_type="fidelity", measurement="XYZ", outer_kernel="gaussian", outer_kernel_params=None,
+                 regularization=None, riemannian_lr=0.01, riemannian_method="gradient_descent", riemannian_beta=0.9,
+                 training_ignores_outer_kernel=True, compute_condition_number=False):
+        self.agent_id = agent_id
+        self.X_sub = np.asarray(X_sub, dtype=np.float64)
+        if self.X_sub.ndim == 1:
+            self.X_sub = self.X_sub.reshape(-1, 1)
+        self.Y_sub = np.asarray(Y_sub, dtype=np.float64).reshape(-1)
+        self.num_qubits, self.noise_std, self.rho, self.L = num_qubits, noise_std, rho, L
+        self.q_kernel, self.use_parameter_shift, self.num_workers = q_kernel, use_parameter_shift, num_workers
+        self.shift_value, self.num_layers, self.combined_computation = shift_value, num_layers, combined_computation
+        self.encoding_type, self.kernel_type, self.measurement = encoding_type, kernel_type, measurement
+        self.outer_kernel, self.outer_kernel_params, self.regularization = outer_kernel, outer_kernel_params, regularization
+        self.riemannian_lr, self.riemannian_method, self.riemannian_beta = riemannian_lr, riemannian_method, riemannian_beta
+        self.training_ignores_outer_kernel = training_ignores_outer_kernel
+        self.compute_condition_number = compute_condition_number
+        self.manifold = self.riemannian_optimizer = self.riemannian_admm = None
+        if measurement != "XYZ":
+            raise NotImplementedError("only measurement='XYZ' is on the hot path")
+        if regularization is not None:
+            raise NotImplementedError("regularization is outside the hot path (SURVEY §2 #13)")
+        self.last_gradient = None       # unrounded dL/dtheta of the last call (diagnostics / tests)
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def _setup_riemannian_framework(self, num_parameters):
+        if self.manifold is None:
+            self.manifold, self.riemannian_optimizer, self.riemannian_admm = create_riemannian_framework(
+                num_parameters=num_parameters, learning_rate=self.riemannian_lr, rho=self.rho, method=self.riemannian_method)
+
+    def _engine(self):
+        n, d = self.X_sub.shape
+        key = (n, d, self.encoding_type, self.kernel_type, self.num_qubits, self.num_layers, self.outer_kernel,
+               float(self.noise_std), float(self.rho), float(self.L), float(self.shift_value), self.training_ignores_outer_kernel)
+        return _engine_for(key, lambda: AgentEngine(
+            self.X_sub, self.Y_sub, encoding_type=self.encoding_type, kernel_type=self.kernel_type, num_qubits=self.num_qubits,
+            num_layers=self.num_layers, noise_std=self.noise_std, rho=self.rho, L=self.L, outer_kernel=self.outer_kernel,
+            shift_value=self.shift_value, training_ignores_outer_kernel=self.training_ignores_outer_kernel))
+
+    def train_and_update(self, z, psi_i):
+        """-> (theta_i, psi_i, nll_loss, condition_number, nll_components), as agent_riemannian.py:491."""
+        eng = self._engine()
+        z = np.asarray(z, dtype=np.float64).reshape(-1)
+        psi_i = np.asarray(psi_i, dtype=np.float64).reshape(-1)
+        if z.size != eng.P or psi_i.size != eng.P:
+            raise ValueError(f"expected {eng.P} parameters, got z {z.size}, psi {psi_i.size}")
+        self._setup_riemannian_framework(eng.P)
+        eng.load_data(self.X_sub, self.Y_sub)
+        d_in = dev_f64(np.stack([z, psi_i]))
+        d_out = torch.empty((2, eng.P), dtype=torch.float64, device=d_in.device)
+        eng.step(d_in[0], d_in[1], d_out[0], d_out[1])
+        packed = torch.cat([d_out.reshape(-1), eng.d_nll, eng.d_grad, eng.d_info.to(torch.float64)]).cpu().numpy()   # one D2H
+        self.h2d_bytes = self.X_sub.nbytes + self.Y_sub.nbytes + z.nbytes + psi_i.nbytes
+        self.d2h_bytes = packed.nbytes
+        p = eng.P
+        theta_i, psi_new = packed[:p].copy(), packed[p:2 * p].copy()
+        terms = packed[2 * p:2 * p + 4]
+        self.last_gradient = packed[2 * p + 4:3 * p + 4].copy()
+        info = int(packed[-1])
+        if info != 0:
+            # the reference falls back to LU and then pinv here (agent_riemannian.py:419-428); this engine has
+            # no CPU path by design, so the failure is surfaced instead.
+            raise np.linalg.LinAlgError(f"Agent {self.agent_id}: Cholesky failed at pivot {info} (K + sigma^2 I not SPD)")
+        cond = float("nan")
+        if self.compute_condition_number:
+            k = eng.solver.matrix()    # holds L after the step; recompute the Gram for the diagnostic
+            eng.simulate(d_in[0]); eng.gram()
+            k = torch.tril(eng.solver.matrix()); k = k + k.T - torch.diag(torch.diagonal(k))
+            k = k - (self.noise_std ** 2) * torch.eye(eng.n, dtype=torch.float64, device=k.device)
+            sv = torch.linalg.svdvals(k)
+            cond = float((sv[0] / sv[-1]).item())
+        comps = {"log_det_term": float(terms[0]), "quadratic_term": float(terms[1]), "constant_term": float(terms[2]),
+                 "total": float(terms[3])}
+        return theta_i, psi_new, float(terms[3]), cond, comps
+
+
+def process_agent_training(agent_data):
+    """Same 23-tuple in / 5-tuple out as ``main.process_agent_training`` (main.py:1311-1362)."""
+    (agent_id, X_sub, Y_sub, num_qubits, noise_std, rho, L, z, psi_i, use_parameter_shift, num_features, num_layers,
+     num_workers, shift_value, encoding_type, kernel_type, measurement, riemannian_lr, riemannian_method, riemannian_beta,
+     outer_kernel, outer_kernel_params, regularization) = agent_data
+    agent = RiemannianAgent(agent_id=agent_id, X_sub=X_sub, Y_sub=Y_sub, num_qubits=num_qubits, noise_std=noise_std, rho=rho,
+                            L=L, q_kernel=None, use_parameter_shift=use_parameter_shift, num_workers=num_workers,
+                            shift_value=shift_value, num_layers=num_layers, encoding_type=encoding_type,
+                            kernel_type=kernel_type, measurement=measurement, outer_kernel=outer_kernel,
+                            outer_kernel_params=outer_kernel_params, regularization=regularization,
+                            riemannian_lr=riemannian_lr, riemannian_method=riemannian_method, riemannian_beta=riemannian_beta)
+    return agent.train_and_update(z, psi_i)

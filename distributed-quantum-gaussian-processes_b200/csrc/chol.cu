@@ -1,0 +1,333 @@
+// Blocked fp64 Cholesky + explicit SPD inverse + solve on one GPU (sm_100a).
+// Replaces the LAPACK sequence of RiemannianAgent.train_and_update (reference agent_riemannian.py:410-418:
+// cholesky, 4x general solve incl. an explicit inverse against eye(n); :442 slogdet) with
+//   potrf   right-looking, nb = 128: [leaf: factor + invert the diagonal block] -> [panel = panel * inv(Lkk)^T]
+//           -> [trailing -= panel panel^T]           (trailing update on DMMA, n^3/3 flops)
+//   trtri   W = L^-1 by recursive halving: W21 = -W22 (L21 W11), all products of one level in ONE grouped
+//           launch (2 launches per level, log2(n/128) levels, n^3/3 flops on DMMA)
+//   lauum   A^-1 = W^T W, lower tiles only, contraction range clipped to the triangular support (n^3/3)
+//   solve   alpha = W^T (W y);  logdet = 2 sum log Lii (accumulated by the leaves)
+// The matrix is padded to a multiple of 128 with an identity block, so no kernel has edge cases.
+#include <cmath>
+#include "gemm64.cuh"
+
+namespace dqgp {
+constexpr int NB = 128;
+constexpr int LEAF_PITCH = NB + 1;
+constexpr size_t LEAF_SMEM = sizeof(double) * NB * LEAF_PITCH;
+}  // namespace dqgp
+
+struct dqgp_solver {
+    int n, np, ld, nblk, device;
+    double *A, *W, *T;            // factor (in place), L^-1, scratch / A^-1
+    double *y_pad, *w, *partial;  // padded rhs, W y, column partial sums
+    double *strip, *V;            // prediction: padded 128-row strip of K(test,train), V = W strip^T
+    dqgp::GemmTask* d_tasks;
+    // launch groups: [first task, task count, tiles]
+    struct Group { int first, count, tiles; };
+    std::vector<Group> trsm, syrk;         // per potrf step
+    std::vector<Group> tri_t, tri_w;       // per trtri level
+    Group lauum, quad;
+    size_t bytes;
+};
+
+namespace dqgp {
+
+// ---- leaf: Cholesky of a 128x128 diagonal block in shared memory, then its inverse in place -------------
+__global__ void __launch_bounds__(256, 1) potrf_leaf_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int blk,
+                                                            double* logdet, int* info, int n_real) {
+    extern __shared__ double S[];
+    __shared__ double s_red[8];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x;
+    double* Ablk = A + (size_t)blk * NB * ld + (size_t)blk * NB;
+    double* Wblk = W + (size_t)blk * NB * ld + (size_t)blk * NB;
+    if (tid == 0) s_bad = 0;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        S[r * LEAF_PITCH + c] = (c <= r) ? Ablk[(size_t)r * ld + c] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < NB; ++j) {
+        const double piv = S[j * LEAF_PITCH + j];
+        if (!(piv > 0.0) && tid == 0 && s_bad == 0) s_bad = j + 1;
+        const double d = sqrt(piv);
+        const double inv = 1.0 / d;
+        __syncthreads();
+        if (tid == 0) S[j * LEAF_PITCH + j] = d;
+        for (int i = j + 1 + tid; i < NB; i += 256) S[i * LEAF_PITCH + j] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: two threads per row, interleaved columns
+        const int i = j + 1 + (tid >> 1);
+        if (i < NB) {
+            const double lij = S[i * LEAF_PITCH + j];
+            for (int k = j + 1 + (tid & 1); k <= i; k += 2) S[i * LEAF_PITCH + k] = fma(-lij, S[k * LEAF_PITCH + j], S[i * LEAF_PITCH + k]);
+        }
+        __syncthreads();
+    }
+    // write L (upper part of the block zeroed), accumulate log-determinant
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        Ablk[(size_t)r * ld + c] = S[r * LEAF_PITCH + c];
+    }
+    {
+        double v = (tid < NB) ? log(S[tid * LEAF_PITCH + tid]) : 0.0;
+        v = warp_sum(v);
+        if ((tid & 31) == 0) s_red[tid >> 5] = v;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < 8; ++w) tot += s_red[w];
+            *logdet += 2.0 * tot;
+            if (s_bad && *info == 0 && blk * NB + s_bad <= n_real) *info = blk * NB + s_bad;
+        }
+    }
+    __syncthreads();
+    // in-place inverse of the lower-triangular block, last column first (LAPACK dtrti2 order)
+    for (int j = NB - 1; j >= 0; --j) {
+        const double wjj = 1.0 / S[j * LEAF_PITCH + j];
+        double acc = 0.0;
+        const int i = j + 1 + tid;
+        if (i < NB) {
+            for (int k = j + 1; k <= i; ++k) acc = fma(S[i * LEAF_PITCH + k], S[k * LEAF_PITCH + j], acc);
+        }
+        __syncthreads();
+        if (i < NB) S[i * LEAF_PITCH + j] = -acc * wjj;
+        if (tid == 0) S[j * LEAF_PITCH + j] = wjj;
+        __syncthreads();
+    }
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        Wblk[(size_t)r * ld + c] = S[r * LEAF_PITCH + c];
+    }
+}
+
+// ---- padding: rows/cols >= n become the identity ---------------------------------------------------------
+__global__ void pad_identity_kernel(double* A, int n, int np, int ld) {
+    const int r = blockIdx.x;   // np rows
+    for (int c = threadIdx.x; c < np; c += blockDim.x) {
+        if (r >= n || c >= n) A[(size_t)r * ld + c] = (r == c) ? 1.0 : 0.0;
+    }
+}
+__global__ void pad_vector_kernel(const double* y, int n, int np, double* out, double* logdet, int* info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) out[i] = (i < n) ? y[i] : 0.0;
+    if (i == 0) { *logdet = 0.0; *info = 0; }
+}
+
+// ---- w = W y (lower-triangular, one warp per row) --------------------------------------------------------
+__global__ void trmv_lower_kernel(const double* __restrict__ W, int np, int ld, const double* __restrict__ y, double* __restrict__ w) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= np) return;
+    double acc = 0.0;
+    for (int k = lane; k <= row; k += 32) acc = fma(W[(size_t)row * ld + k], y[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) w[row] = acc;
+}
+// ---- alpha = W^T w: per (row block, column block) partial sums, then a fixed-order reduction --------------
+__global__ void trmv_lower_T_partial_kernel(const double* __restrict__ W, int ld, const double* __restrict__ w, double* __restrict__ partial, int np) {
+    const int rb = blockIdx.y, cb = blockIdx.x;
+    const int col = cb * NB + threadIdx.x;
+    double acc = 0.0;
+    if (rb >= cb) {
+        const int r0 = rb * NB;
+        for (int r = 0; r < NB; ++r) acc = fma(W[(size_t)(r0 + r) * ld + col], w[r0 + r], acc);   // zero above the diagonal
+    }
+    partial[(size_t)rb * np + col] = acc;
+}
+__global__ void reduce_partial_kernel(const double* __restrict__ partial, int nblk, int np, int n, double* __restrict__ out) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n) return;
+    double acc = 0.0;
+    for (int rb = 0; rb < nblk; ++rb) acc += partial[(size_t)rb * np + col];
+    out[col] = acc;
+}
+// ---- mirror the lower triangle of a padded square into the upper one (tiled transpose through smem) --------
+__global__ void symmetrize_lower_kernel(double* A, int ld) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = A[(size_t)(bi * 32 + r) * ld + bj * 32 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int gr = bj * 32 + r, gc = bi * 32 + tx;
+        if (bi != bj || gc > gr) A[(size_t)gr * ld + gc] = tile[tx][r];
+    }
+}
+__global__ void colsumsq_kernel(const double* __restrict__ V, int rows, int ld, int ncols, double* __restrict__ out) {
+    // out[c] = sum_r V[r][c]^2, fixed order; one thread per column, coalesced across threads
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double acc = 0.0;
+    for (int r = 0; r < rows; ++r) { const double v = V[(size_t)r * ld + c]; acc = fma(v, v, acc); }
+    out[c] = acc;
+}
+__global__ void copy_pad_rows_kernel(const double* __restrict__ B, int nb, int n, int ldb, double* __restrict__ out, int nbp, int np, int ldo) {
+    const int r = blockIdx.x;
+    for (int c = threadIdx.x; c < np; c += blockDim.x) out[(size_t)r * ldo + c] = (r < nb && c < n) ? B[(size_t)r * ldb + c] : 0.0;
+}
+
+static GemmTask make_task(const double* A, const double* B, double* C, int M, int N, int K, int ld, int a_k, int b_k, int lower,
+                          int krule, double alpha, double beta) {
+    GemmTask t;
+    t.A = A; t.B = B; t.C = C; t.M = M; t.N = N; t.K = K; t.lda = t.ldb = t.ldc = ld;
+    t.a_k_contig = a_k; t.b_k_contig = b_k; t.lower_tiles = lower; t.krule = krule; t.alpha = alpha; t.beta = beta;
+    t.tile_begin = 0; t.tiles = gemm_task_tiles(t);
+    return t;
+}
+
+}  // namespace dqgp
+
+extern "C" {
+
+int dqgp_solver_create(int n, dqgp_solver** out) {
+    using namespace dqgp;
+    DQGP_REQUIRE(out != nullptr, "dqgp_solver_create: out is NULL");
+    *out = nullptr;
+    DQGP_REQUIRE(n >= 1 && n <= (1 << 17), "dqgp_solver_create: n = %d outside [1, 131072]", n);
+    dqgp_solver* s = new dqgp_solver();
+    s->n = n;
+    s->nblk = (n + NB - 1) / NB;
+    s->np = s->nblk * NB;
+    s->ld = s->np;
+    s->A = s->W = s->T = s->y_pad = s->w = s->partial = s->strip = s->V = nullptr;
+    s->d_tasks = nullptr;
+    cudaError_t e = cudaGetDevice(&s->device);
+    const size_t mat = sizeof(double) * (size_t)s->np * s->ld;
+    s->bytes = 3 * mat;
+    if (e == cudaSuccess) e = cudaMalloc(&s->A, mat);
+    if (e == cudaSuccess) e = cudaMalloc(&s->W, mat);
+    if (e == cudaSuccess) e = cudaMalloc(&s->T, mat);
+    if (e == cudaSuccess) e = cudaMalloc(&s->y_pad, sizeof(double) * s->np);
+    if (e == cudaSuccess) e = cudaMalloc(&s->w, sizeof(double) * s->np);
+    if (e == cudaSuccess) e = cudaMalloc(&s->partial, sizeof(double) * (size_t)s->nblk * s->np);
+    if (e == cudaSuccess) e = cudaMalloc(&s->strip, sizeof(double) * (size_t)NB * s->ld);
+    if (e == cudaSuccess) e = cudaMalloc(&s->V, sizeof(double) * (size_t)s->np * NB);
+    if (e != cudaSuccess) { dqgp_solver_destroy(s); return cuda_fail(e, "dqgp_solver_create (allocation; this library has no CPU fallback)"); }
+
+    std::vector<GemmTask> tasks;
+    auto push_group = [&](std::vector<GemmTask>& grp) {
+        dqgp_solver::Group g;
+        g.first = (int)tasks.size(); g.count = (int)grp.size(); g.tiles = 0;
+        for (auto& t : grp) { t.tile_begin = g.tiles; g.tiles += t.tiles; tasks.push_back(t); }
+        grp.clear();
+        return g;
+    };
+    const int ld = s->ld, np = s->np, nblk = s->nblk;
+    auto at = [&](double* base, int rb, int cb) { return base + (size_t)rb * NB * ld + (size_t)cb * NB; };
+    std::vector<GemmTask> grp;
+    // potrf steps
+    for (int k = 0; k + 1 < nblk; ++k) {
+        const int rest = np - (k + 1) * NB;
+        grp.push_back(make_task(at(s->A, k + 1, k), at(s->W, k, k), at(s->A, k + 1, k), rest, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
+        s->trsm.push_back(push_group(grp));
+        grp.push_back(make_task(at(s->A, k + 1, k), at(s->A, k + 1, k), at(s->A, k + 1, k + 1), rest, rest, NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
+        s->syrk.push_back(push_group(grp));
+    }
+    // trtri levels: spans of `span` blocks are already inverted; join neighbours pairwise
+    for (int span = 1; span < nblk; span *= 2) {
+        std::vector<GemmTask> gt, gw;
+        for (int o = 0; o + span < nblk; o += 2 * span) {
+            const int h1 = span, h2 = std::min(span, nblk - (o + span));
+            // T21 = L21 * W11   (W11 lower-triangular as the K x N operand)
+            gt.push_back(make_task(at(s->A, o + h1, o), at(s->W, o, o), at(s->T, o + h1, o), h2 * NB, h1 * NB, h1 * NB, ld, 1, 0, 0, GM_KRULE_B_LOWER, 1.0, 0.0));
+            // W21 = -W22 * T21  (W22 lower-triangular as the M x K operand)
+            gw.push_back(make_task(at(s->W, o + h1, o + h1), at(s->T, o + h1, o), at(s->W, o + h1, o), h2 * NB, h1 * NB, h2 * NB, ld, 1, 0, 0, GM_KRULE_A_LOWER, -1.0, 0.0));
+        }
+        s->tri_t.push_back(push_group(gt));
+        s->tri_w.push_back(push_group(gw));
+    }
+    // lauum: Ainv = W^T W  (both operands row-contiguous: A[k][m] = W[k][m])
+    grp.push_back(make_task(s->W, s->W, s->T, np, np, np, ld, 0, 0, 1, GM_KRULE_LAUUM, 1.0, 0.0));
+    s->lauum = push_group(grp);
+    // prediction: V[m][c] = sum_k W[m][k] strip[c][k]  (W lower-triangular, both operands k-contiguous)
+    {
+        GemmTask t = make_task(s->W, s->strip, s->V, np, NB, np, ld, 1, 1, 0, GM_KRULE_A_LOWER, 1.0, 0.0);
+        t.ldc = NB;
+        grp.push_back(t);
+        s->quad = push_group(grp);
+    }
+
+    e = cudaMalloc(&s->d_tasks, sizeof(GemmTask) * tasks.size());
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_tasks, tasks.data(), sizeof(GemmTask) * tasks.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM);
+    if (e != cudaSuccess) { dqgp_solver_destroy(s); return cuda_fail(e, "dqgp_solver_create (task table)"); }
+    int rc = gemm_init();
+    if (rc) { dqgp_solver_destroy(s); return rc; }
+    *out = s;
+    return 0;
+}
+
+void dqgp_solver_destroy(dqgp_solver* s) {
+    if (!s) return;
+    cudaFree(s->A); cudaFree(s->W); cudaFree(s->T); cudaFree(s->y_pad); cudaFree(s->w); cudaFree(s->partial); cudaFree(s->strip); cudaFree(s->V); cudaFree(s->d_tasks);
+    delete s;
+}
+int dqgp_solver_n(const dqgp_solver* s) { return s ? s->n : -1; }
+int dqgp_solver_ld(const dqgp_solver* s) { return s ? s->ld : -1; }
+double* dqgp_solver_matrix(dqgp_solver* s) { return s ? s->A : nullptr; }
+double* dqgp_solver_inverse(dqgp_solver* s) { return s ? s->T : nullptr; }
+double* dqgp_solver_factor(dqgp_solver* s) { return s ? s->A : nullptr; }
+size_t dqgp_solver_bytes(const dqgp_solver* s) { return s ? s->bytes : 0; }
+
+int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, double* d_logdet, int* d_info, int want_inverse,
+                         void* stream) {
+    using namespace dqgp;
+    DQGP_REQUIRE(s && d_y && d_alpha && d_logdet && d_info, "dqgp_potrf_solve_inv: NULL argument");
+    cudaStream_t st = as_stream(stream);
+    const int np = s->np, ld = s->ld, nblk = s->nblk;
+    pad_vector_kernel<<<(np + 255) / 256, 256, 0, st>>>(d_y, s->n, np, s->y_pad, d_logdet, d_info);
+    if (np != s->n) pad_identity_kernel<<<np, 256, 0, st>>>(s->A, s->n, np, ld);
+    DQGP_LAUNCH_CHECK("pad kernels");
+    for (int k = 0; k < nblk; ++k) {
+        potrf_leaf_kernel<<<1, 256, LEAF_SMEM, st>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
+        DQGP_LAUNCH_CHECK("potrf_leaf_kernel");
+        if (k + 1 < nblk) {
+            int rc = launch_gemm_group(s->d_tasks + s->trsm[k].first, s->trsm[k].count, s->trsm[k].tiles, st);
+            if (rc) return rc;
+            rc = launch_gemm_group(s->d_tasks + s->syrk[k].first, s->syrk[k].count, s->syrk[k].tiles, st);
+            if (rc) return rc;
+        }
+    }
+    for (size_t l = 0; l < s->tri_t.size(); ++l) {
+        int rc = launch_gemm_group(s->d_tasks + s->tri_t[l].first, s->tri_t[l].count, s->tri_t[l].tiles, st);
+        if (rc) return rc;
+        rc = launch_gemm_group(s->d_tasks + s->tri_w[l].first, s->tri_w[l].count, s->tri_w[l].tiles, st);
+        if (rc) return rc;
+    }
+    // alpha = W^T (W y)
+    trmv_lower_kernel<<<(np + 7) / 8, 256, 0, st>>>(s->W, np, ld, s->y_pad, s->w);
+    trmv_lower_T_partial_kernel<<<dim3(nblk, nblk), NB, 0, st>>>(s->W, ld, s->w, s->partial, np);
+    reduce_partial_kernel<<<(s->n + 255) / 256, 256, 0, st>>>(s->partial, nblk, np, s->n, d_alpha);
+    DQGP_LAUNCH_CHECK("solve kernels");
+    if (want_inverse) {
+        int rc = launch_gemm_group(s->d_tasks + s->lauum.first, s->lauum.count, s->lauum.tiles, st);
+        if (rc) return rc;
+        if (want_inverse > 1) {
+            symmetrize_lower_kernel<<<dim3(np / 32, np / 32), 256, 0, st>>>(s->T, ld);
+            DQGP_LAUNCH_CHECK("symmetrize_lower_kernel");
+        }
+    }
+    return 0;
+}
+
+int dqgp_solver_quadform_rows(dqgp_solver* s, const double* d_B, int nb, int ldb, double* d_out, void* stream) {
+    // d_out[i] = || L^-1 b_i ||^2 for every row b_i of B (nb, n): V = W B^T in strips of 128 rows of B on the
+    // DMMA GEMM, then fixed-order column sums of squares (main.py:1462-1463).
+    using namespace dqgp;
+    DQGP_REQUIRE(s && d_B && d_out && nb >= 0 && ldb >= s->n, "dqgp_solver_quadform_rows: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    for (int r0 = 0; r0 < nb; r0 += NB) {
+        const int cnt = std::min(NB, nb - r0);
+        copy_pad_rows_kernel<<<NB, 256, 0, st>>>(d_B + (size_t)r0 * ldb, cnt, s->n, ldb, s->strip, NB, s->np, s->ld);
+        int rc = launch_gemm_group(s->d_tasks + s->quad.first, s->quad.count, s->quad.tiles, st);
+        if (rc) return rc;
+        colsumsq_kernel<<<1, NB, 0, st>>>(s->V, s->n, NB, cnt, d_out + r0);
+        DQGP_LAUNCH_CHECK("quadform kernels");
+    }
+    return 0;
+}
+
+}  // extern "C"

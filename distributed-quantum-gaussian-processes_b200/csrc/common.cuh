@@ -1,0 +1,68 @@
+// Shared internals of libdqgp (sm_100a).  Not part of the public ABI (see include/dqgp.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+#include "../../include/dqgp.h"
+
+struct dqgp_circuit;
+
+namespace dqgp {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define DQGP_CUDA(call)                                                     \
+    do {                                                                    \
+        cudaError_t e__ = (call);                                           \
+        if (e__ != cudaSuccess) return ::dqgp::cuda_fail(e__, #call);       \
+    } while (0)
+#define DQGP_LAUNCH_CHECK(name)                                             \
+    do {                                                                    \
+        cudaError_t e__ = cudaGetLastError();                               \
+        if (e__ != cudaSuccess) return ::dqgp::cuda_fail(e__, name);        \
+    } while (0)
+#define DQGP_REQUIRE(cond, ...)                                             \
+    do {                                                                    \
+        if (!(cond)) { ::dqgp::set_error(__VA_ARGS__); return -1; }         \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+int sm_count();
+int circuit_on_device(const dqgp_circuit* c);  // uploads the gate program on first use
+
+constexpr int MAX_QUBITS = 12;
+
+// fp64 mma.sync m8n8k4: A 8x4 (row), B 4x8 (col), C 8x8.  Fragment ownership (lane = 4*g + t):
+//   a = A[g][t], b = B[t][g], c0 = C[g][2t], c1 = C[g][2t+1].   SASS: DMMA.8x8x4
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace dqgp
+
+struct dqgp_circuit {
+    int encoding, q, d, layers, P;
+    bool uses_acos;
+    std::vector<dqgp_gate> gates;  // host copy
+    dqgp_gate* d_gates;            // device copy
+    int device;
+};

@@ -1,0 +1,166 @@
+// Gram-matrix kernels: projected kernel (outer kernel on Pauli features) and fidelity kernel.
+// Replace ProjectedQuantumKernel.evaluate / FidelityKernel.evaluate (reference main.py:118-137, call
+// sites main.py:245,1420-1430, agent_riemannian.py:118).  One 64x64 tile of K per CTA; the only HBM
+// traffic besides the (tiny) feature tiles is the 8 B/entry store of K, issued as 128-bit stores.
+#include "pairwise.cuh"
+
+namespace dqgp {
+
+template <int OUTER>
+__global__ void __launch_bounds__(PW_THREADS) gram_projected_kernel(const double* __restrict__ F1, int n1,
+                                                                    const double* __restrict__ F2, int n2, int m,
+                                                                    OuterHyp hyp, double* __restrict__ K, int ldk) {
+    __shared__ __align__(16) double FrT[PW_MAX_M * PW_PITCH];
+    __shared__ __align__(16) double FcT[PW_MAX_M * PW_PITCH];
+    const int row0 = blockIdx.y * PW_TILE, col0 = blockIdx.x * PW_TILE;
+    stage_features_T(FrT, F1, row0, n1, m);
+    stage_features_T(FcT, F2, col0, n2, m);
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double d2[4][4];
+    micro_sqdist(FrT, FcT, m, ty, tx, d2);
+    const bool vec_ok = ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = row0 + ty + 16 * i;
+        if (r >= n1) continue;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int c = col0 + 2 * tx + 32 * jj;
+            const double v0 = outer_eval<OUTER>(d2[i][2 * jj], hyp);
+            const double v1 = outer_eval<OUTER>(d2[i][2 * jj + 1], hyp);
+            double* dst = K + (size_t)r * ldk + c;
+            if (vec_ok && c + 1 < n2) {
+                *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            } else {
+                if (c < n2) dst[0] = v0;
+                if (c + 1 < n2) dst[1] = v1;
+            }
+        }
+    }
+}
+
+// Fidelity Gram: K[j][k] = |sum_i conj(psi2_k[i]) psi1_j[i]|^2, complex tile contraction over the 2^q
+// amplitudes in chunks of FID_KC, 4x4 complex accumulators per thread.
+constexpr int FID_KC = 16;
+constexpr int FID_PITCH = 65;   // double2 units
+
+__device__ __forceinline__ void stage_states_T(double2* dst, const double2* __restrict__ Psi, int row0, int n, int dim, int k0) {
+    // dst[kk*FID_PITCH + r] = Psi[(row0+r)*dim + k0+kk]
+    const int valid = min(PW_TILE, n - row0);
+    for (int e = threadIdx.x; e < PW_TILE * FID_KC; e += PW_THREADS) {
+        const int r = e / FID_KC, kk = e % FID_KC;
+        double2 v = make_double2(0.0, 0.0);
+        if (r < valid && k0 + kk < dim) v = Psi[(size_t)(row0 + r) * dim + k0 + kk];
+        dst[kk * FID_PITCH + r] = v;
+    }
+}
+
+__device__ __forceinline__ void micro_overlap(const double2* __restrict__ ArT, const double2* __restrict__ AcT, int ty, int tx,
+                                              double (&re)[4][4], double (&im)[4][4]) {
+#pragma unroll 4
+    for (int kk = 0; kk < FID_KC; ++kk) {
+        double2 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = ArT[kk * FID_PITCH + ty + 16 * i];
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            b[2 * jj] = AcT[kk * FID_PITCH + 2 * tx + 32 * jj];
+            b[2 * jj + 1] = AcT[kk * FID_PITCH + 2 * tx + 32 * jj + 1];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                re[i][j] = fma(a[i].x, b[j].x, re[i][j]);
+                re[i][j] = fma(a[i].y, b[j].y, re[i][j]);
+                im[i][j] = fma(a[i].y, b[j].x, im[i][j]);
+                im[i][j] = fma(-a[i].x, b[j].y, im[i][j]);
+            }
+    }
+}
+
+__global__ void __launch_bounds__(PW_THREADS) gram_fidelity_kernel(const double2* __restrict__ Psi1, int n1,
+                                                                   const double2* __restrict__ Psi2, int n2, int dim,
+                                                                   double* __restrict__ K, int ldk) {
+    __shared__ __align__(16) double2 ArT[FID_KC * FID_PITCH];
+    __shared__ __align__(16) double2 AcT[FID_KC * FID_PITCH];
+    const int row0 = blockIdx.y * PW_TILE, col0 = blockIdx.x * PW_TILE;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double re[4][4], im[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) re[i][j] = im[i][j] = 0.0;
+    for (int k0 = 0; k0 < dim; k0 += FID_KC) {
+        __syncthreads();
+        stage_states_T(ArT, Psi1, row0, n1, dim, k0);
+        stage_states_T(AcT, Psi2, col0, n2, dim, k0);
+        __syncthreads();
+        micro_overlap(ArT, AcT, ty, tx, re, im);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = row0 + ty + 16 * i;
+        if (r >= n1) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = col0 + 2 * tx + 32 * (j >> 1) + (j & 1);
+            if (c < n2) K[(size_t)r * ldk + c] = re[i][j] * re[i][j] + im[i][j] * im[i][j];
+        }
+    }
+}
+
+__global__ void add_diagonal_kernel(double* A, int n, int lda, double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(size_t)i * lda + i] += v;
+}
+
+}  // namespace dqgp
+
+extern "C" {
+
+int dqgp_gram_projected(int outer, const double* h_hyp, const double* d_F1, int n1, const double* d_F2, int n2, int m,
+                        double* d_K, int ldk, int same, void* stream) {
+    using namespace dqgp;
+    (void)same;  // direct differences already give exact zeros on identical operands
+    DQGP_REQUIRE(d_F1 && d_F2 && d_K, "dqgp_gram_projected: NULL argument");
+    DQGP_REQUIRE(m >= 1 && m <= PW_MAX_M, "dqgp_gram_projected: feature count %d outside [1,%d]", m, PW_MAX_M);
+    DQGP_REQUIRE(n1 >= 0 && n2 >= 0 && ldk >= n2, "dqgp_gram_projected: bad shape (%d,%d) ld %d", n1, n2, ldk);
+    OuterHyp hyp;
+    if (make_outer_hyp(outer, h_hyp, &hyp)) return -1;
+    if (n1 == 0 || n2 == 0) return 0;
+    dim3 grid((n2 + PW_TILE - 1) / PW_TILE, (n1 + PW_TILE - 1) / PW_TILE);
+    cudaStream_t st = as_stream(stream);
+    switch (outer) {
+        case DQGP_OUTER_GAUSSIAN: gram_projected_kernel<DQGP_OUTER_GAUSSIAN><<<grid, PW_THREADS, 0, st>>>(d_F1, n1, d_F2, n2, m, hyp, d_K, ldk); break;
+        case DQGP_OUTER_MATERN15: gram_projected_kernel<DQGP_OUTER_MATERN15><<<grid, PW_THREADS, 0, st>>>(d_F1, n1, d_F2, n2, m, hyp, d_K, ldk); break;
+        default: gram_projected_kernel<DQGP_OUTER_EXPSINE2><<<grid, PW_THREADS, 0, st>>>(d_F1, n1, d_F2, n2, m, hyp, d_K, ldk); break;
+    }
+    DQGP_LAUNCH_CHECK("gram_projected_kernel");
+    return 0;
+}
+
+int dqgp_gram_fidelity(const double* d_Psi1, int n1, const double* d_Psi2, int n2, int dim, double* d_K, int ldk, int same,
+                       void* stream) {
+    using namespace dqgp;
+    (void)same;
+    DQGP_REQUIRE(d_Psi1 && d_Psi2 && d_K, "dqgp_gram_fidelity: NULL argument");
+    DQGP_REQUIRE(dim >= 1 && n1 >= 0 && n2 >= 0 && ldk >= n2, "dqgp_gram_fidelity: bad shape");
+    if (n1 == 0 || n2 == 0) return 0;
+    dim3 grid((n2 + PW_TILE - 1) / PW_TILE, (n1 + PW_TILE - 1) / PW_TILE);
+    gram_fidelity_kernel<<<grid, PW_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const double2*>(d_Psi1), n1,
+                                                                    reinterpret_cast<const double2*>(d_Psi2), n2, dim, d_K, ldk);
+    DQGP_LAUNCH_CHECK("gram_fidelity_kernel");
+    return 0;
+}
+
+int dqgp_add_diagonal(double* d_A, int n, int lda, double value, void* stream) {
+    using namespace dqgp;
+    DQGP_REQUIRE(d_A && n >= 0 && lda >= n, "dqgp_add_diagonal: bad arguments");
+    if (n == 0) return 0;
+    add_diagonal_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(d_A, n, lda, value);
+    DQGP_LAUNCH_CHECK("add_diagonal_kernel");
+    return 0;
+}
+}

@@ -1,0 +1,99 @@
+// Pairwise tile machinery shared by the Gram kernels (gram.cu) and the fused gradient kernels (grad.cu).
+//
+// A CTA of 256 threads owns a 64x64 tile of (row sample j, column sample k) pairs.  Thread (ty,tx) =
+// (tid>>4, tid&15) owns the 4x4 micro-tile rows {ty+16i} x cols {2tx+32jj+e}: a warp then touches two
+// tile rows and 64 contiguous columns, so K / A^-1 accesses are full 128-byte-line, 128-bit per lane.
+// Feature tiles live in shared memory transposed ([feature][sample], pitch 66) so a lane's two adjacent
+// columns are one LDS.128 and the row operand is a broadcast.
+#pragma once
+#include "common.cuh"
+
+namespace dqgp {
+
+constexpr int PW_TILE = 64;
+constexpr int PW_PITCH = 66;      // doubles; even (16-byte LDS.128 alignment), != multiple of 32
+constexpr int PW_THREADS = 256;
+constexpr int PW_MAX_M = 3 * MAX_QUBITS;
+
+struct OuterHyp {
+    double a;   // gaussian: gamma        | matern: 1/length_scale | expsine2: 1/length_scale
+    double b;   //                                                  | expsine2: pi/periodicity
+};
+
+// Outer kernels with scikit-learn's formulas (sklearn/gaussian_process/kernels.py RBF / Matern(nu=1.5) /
+// ExpSineSquared, as used by squlearn's ProjectedQuantumKernel; reference main.py:130-137).
+template <int OUTER>
+__device__ __forceinline__ double outer_eval(double d2, const OuterHyp& h) {
+    if (OUTER == DQGP_OUTER_GAUSSIAN) {
+        return exp(-h.a * d2);
+    } else if (OUTER == DQGP_OUTER_MATERN15) {
+        const double k = sqrt(d2) * h.a * 1.7320508075688772;   // sqrt(3) * d / l
+        return (1.0 + k) * exp(-k);
+    } else {
+        const double s = sin(sqrt(d2) * h.b) * h.a;             // sin(pi d / p) / l
+        return exp(-2.0 * (s * s));
+    }
+}
+
+static inline int make_outer_hyp(int outer, const double* h_hyp, OuterHyp* out) {
+    const double pi = 3.14159265358979323846;
+    switch (outer) {
+        case DQGP_OUTER_GAUSSIAN:
+            out->a = h_hyp ? h_hyp[0] : 1.0; out->b = 0.0;
+            DQGP_REQUIRE(out->a > 0, "gaussian outer kernel: gamma must be > 0");
+            return 0;
+        case DQGP_OUTER_MATERN15: {
+            const double l = h_hyp ? h_hyp[0] : 1.0;
+            DQGP_REQUIRE(l > 0, "matern outer kernel: length_scale must be > 0");
+            out->a = 1.0 / l; out->b = 0.0;
+            return 0;
+        }
+        case DQGP_OUTER_EXPSINE2: {
+            const double l = h_hyp ? h_hyp[0] : 1.0, per = h_hyp ? h_hyp[1] : 1.0;
+            DQGP_REQUIRE(l > 0 && per > 0, "expsinesquared outer kernel: length_scale and periodicity must be > 0");
+            out->a = 1.0 / l; out->b = pi / per;
+            return 0;
+        }
+    }
+    set_error("unknown outer kernel id %d (hot path covers gaussian, matern, expsinesquared)", outer);
+    return -1;
+}
+
+// Stage a (<=64 rows) x m feature tile into shared memory, transposed: dst[k*PW_PITCH + r] = F[(row0+r)*m + k].
+// Rows past n are zero-filled.  Global reads are fully coalesced (the tile is one contiguous span).
+__device__ __forceinline__ void stage_features_T(double* dst, const double* __restrict__ F, int row0, int n, int m) {
+    const int valid = min(PW_TILE, n - row0);
+    const double* src = F + (size_t)row0 * m;
+    for (int e = threadIdx.x; e < PW_TILE * m; e += PW_THREADS) {
+        const int r = e / m, k = e - r * m;
+        dst[k * PW_PITCH + r] = (r < valid) ? src[e] : 0.0;
+    }
+}
+
+// squared distances of the thread's 4x4 micro-tile by direct differences (what SciPy cdist does; exact 0
+// on identical inputs, no cancellation for near-duplicates — SURVEY §7.3.3)
+__device__ __forceinline__ void micro_sqdist(const double* __restrict__ FrT, const double* __restrict__ FcT, int m, int ty,
+                                             int tx, double (&d2)[4][4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d2[i][j] = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < m; ++k) {
+        double a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = FrT[k * PW_PITCH + ty + 16 * i];
+        const double2 b0 = *reinterpret_cast<const double2*>(&FcT[k * PW_PITCH + 2 * tx]);
+        const double2 b1 = *reinterpret_cast<const double2*>(&FcT[k * PW_PITCH + 2 * tx + 32]);
+        const double b[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double df = a[i] - b[j];
+                d2[i][j] = fma(df, df, d2[i][j]);
+            }
+    }
+}
+
+}  // namespace dqgp

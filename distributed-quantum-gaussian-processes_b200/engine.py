@@ -1,0 +1,233 @@
+"""Device-resident engines: one agent's step (``AgentEngine``) and the multi-agent ADMM iteration over the
+GPUs of a node (``AdmmEngine``).
+
+``AgentEngine.step`` is the GPU equivalent of ``RiemannianAgent.train_and_update``
+(``agent_riemannian.py:314-491``): 2P+1 parameter sets -> statevector features/states for all sets ->
+unshifted Gram written straight into the solver's padded matrix -> + sigma^2 I -> blocked Cholesky, alpha,
+explicit inverse, logdet -> fused central-difference gradient (no shifted Gram is materialised) -> NLL terms
+-> local ADMM update.  Everything is enqueued on the current CUDA stream; nothing syncs with the host.
+
+``AdmmEngine.iteration`` is the body of the driver loop (``main.py:2507-2555``) minus CV and printing:
+consensus z from all agents' (theta, psi), then every local agent's step; with several ranks
+(``torch.distributed``, one process per GPU) the only exchange is an all-gather of the (A, P) theta/psi
+rows — a few KB over NVLink.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import OUTER_KERNELS, DqgpError, check
+from .kernels import EncodingCircuit, _require_cuda, dev_f64, outer_hyp, stream_ptr
+
+PERIOD = float(np.pi)
+
+
+class _DeviceMatrix:
+    """Zero-copy view of library-owned device memory as a torch tensor (tests / diagnostics)."""
+
+    def __init__(self, ptr, shape, strides_bytes):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": strides_bytes}
+
+
+class Solver:
+    """``dqgp_solver`` handle: padded fp64 workspace + task tables for Cholesky / inverse / solve."""
+
+    def __init__(self, n):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        check(self._lib.dqgp_solver_create(int(n), C.byref(h)), "dqgp_solver_create")
+        self.handle, self.n = h, int(n)
+        self.ld = self._lib.dqgp_solver_ld(h)
+        self.matrix_ptr = self._lib.dqgp_solver_matrix(h)
+        self.inverse_ptr = self._lib.dqgp_solver_inverse(h)
+
+    def _view(self, ptr):
+        return torch.as_tensor(_DeviceMatrix(ptr, (self.n, self.n), (self.ld * 8, 8)), device="cuda")
+
+    def matrix(self):
+        return self._view(self.matrix_ptr)
+
+    def inverse(self):
+        return self._view(self.inverse_ptr)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self._lib.dqgp_solver_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class AgentEngine:
+    def __init__(self, X, Y, *, encoding_type, kernel_type, num_qubits, num_layers, noise_std, rho, L,
+                 outer_kernel="gaussian", shift_value=np.pi / 8, training_ignores_outer_kernel=True):
+        _require_cuda()
+        self._lib = _lib.load()
+        X = np.asarray(X, dtype=np.float64)
+        X = X.reshape(-1, 1) if X.ndim == 1 else X
+        self.n, self.d = X.shape
+        if kernel_type not in ("fidelity", "projected"):
+            raise ValueError(f"Unknown kernel type: {kernel_type}")
+        self.kernel_type = kernel_type
+        self.circuit = EncodingCircuit(encoding_type, num_qubits, self.d, num_layers)
+        self.q, self.P = int(num_qubits), self.circuit.num_parameters
+        self.S = 2 * self.P + 1
+        # Q1: the reference's shifted-kernel workers never receive the outer kernel, so training Grams are
+        # always Gaussian(gamma=1); training_ignores_outer_kernel=False honours `outer_kernel` instead.
+        self.outer_kernel = "gaussian" if training_ignores_outer_kernel else outer_kernel
+        self._outer_id = OUTER_KERNELS[self.outer_kernel] if kernel_type == "projected" else 0
+        self._hyp = _lib.hyp_array(outer_hyp(self.outer_kernel)) if kernel_type == "projected" else None
+        self.noise_std, self.rho, self.L, self.h = float(noise_std), float(rho), float(L), float(shift_value)
+        self.d_X = dev_f64(X)
+        self.d_Y = dev_f64(np.asarray(Y, dtype=np.float64).reshape(-1))
+        dev = self.d_X.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.m = 3 * self.q if kernel_type == "projected" else 2 * (1 << self.q)   # doubles per sample per set
+        self.d_Pm = torch.empty((self.S, self.P), **f64)
+        self.d_feat = torch.empty((self.S, self.n, self.m), **f64)
+        self.solver = Solver(self.n)
+        self.d_alpha = torch.empty(self.n, **f64)
+        self.d_logdet = torch.zeros(1, **f64)
+        self.d_info = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.d_grad = torch.empty(self.P, **f64)
+        self.d_nll = torch.empty(4, **f64)
+        self.d_work = torch.empty(max(1, self._lib.dqgp_grad_workspace_bytes(self.n, self.P) // 8), **f64)
+        self.entries_per_step = self.S * self.n * self.n    # full squares, all 2P+1 sets
+
+    def load_data(self, X, Y):
+        """Refresh the resident shard from host arrays (the e2e path does this every call, like the
+        reference re-pickles X_i, Y_i to its workers every iteration, main.py:2530-2542)."""
+        self.d_X.copy_(torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64).reshape(self.n, self.d)).pin_memory(),
+                       non_blocking=True)
+        self.d_Y.copy_(torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)).pin_memory(), non_blocking=True)
+
+    # -- phases (each enqueues on the current stream) ----------------------------------------------------------
+    def simulate(self, d_z):
+        lib, st = self._lib, stream_ptr()
+        check(lib.dqgp_shift_parameter_sets(d_z.data_ptr(), self.P, self.h, PERIOD, self.d_Pm.data_ptr(), st), "shift sets")
+        fn = lib.dqgp_features if self.kernel_type == "projected" else lib.dqgp_states
+        check(fn(self.circuit.handle, self.d_X.data_ptr(), self.n, self.d_Pm.data_ptr(), self.S, self.d_feat.data_ptr(), st),
+              "statevector")
+
+    def gram(self):
+        lib, st, s = self._lib, stream_ptr(), self.solver
+        base = self.d_feat.data_ptr()          # set 0 = unshifted parameters
+        if self.kernel_type == "projected":
+            check(lib.dqgp_gram_projected(self._outer_id, self._hyp, base, self.n, base, self.n, self.m, s.matrix_ptr, s.ld, 1, st),
+                  "gram projected")
+        else:
+            check(lib.dqgp_gram_fidelity(base, self.n, base, self.n, 1 << self.q, s.matrix_ptr, s.ld, 1, st), "gram fidelity")
+        check(lib.dqgp_add_diagonal(s.matrix_ptr, self.n, s.ld, self.noise_std ** 2, st), "add diagonal")
+
+    def factor(self):
+        check(self._lib.dqgp_potrf_solve_inv(self.solver.handle, self.d_Y.data_ptr(), self.d_alpha.data_ptr(),
+                                             self.d_logdet.data_ptr(), self.d_info.data_ptr(), 1, stream_ptr()), "potrf")
+
+    def gradient(self):
+        lib, st, s = self._lib, stream_ptr(), self.solver
+        if self.kernel_type == "projected":
+            check(lib.dqgp_grad_projected(self._outer_id, self._hyp, s.inverse_ptr, s.ld, self.d_alpha.data_ptr(),
+                                          self.d_feat.data_ptr(), self.n, self.m, self.P, self.h, self.d_grad.data_ptr(),
+                                          self.d_work.data_ptr(), st), "grad projected")
+        else:
+            check(lib.dqgp_grad_fidelity(s.inverse_ptr, s.ld, self.d_alpha.data_ptr(), self.d_feat.data_ptr(), self.n,
+                                         1 << self.q, self.P, self.h, self.d_grad.data_ptr(), self.d_work.data_ptr(), st),
+                  "grad fidelity")
+        check(lib.dqgp_nll_terms(self.d_logdet.data_ptr(), self.d_Y.data_ptr(), self.d_alpha.data_ptr(), self.n,
+                                 self.d_nll.data_ptr(), st), "nll")
+
+    def update(self, d_psi, d_theta_out, d_psi_out):
+        # z wrapped to the manifold = row 0 of the parameter-set table (agent_riemannian.py:378)
+        check(self._lib.dqgp_admm_local(self.d_Pm.data_ptr(), self.d_grad.data_ptr(), d_psi.data_ptr(), self.P, self.rho, self.L,
+                                        PERIOD, d_theta_out.data_ptr(), d_psi_out.data_ptr(), stream_ptr()), "admm local")
+
+    def step(self, d_z, d_psi, d_theta_out, d_psi_out):
+        self.simulate(d_z)
+        self.gram()
+        self.factor()
+        self.gradient()
+        self.update(d_psi, d_theta_out, d_psi_out)
+
+    def check_info(self):
+        """Host check of the Cholesky status (syncs).  >0 = index of the first non-positive pivot."""
+        info = int(self.d_info.item())
+        if info != 0:
+            raise np.linalg.LinAlgError(f"Cholesky failed at pivot {info}: K + sigma^2 I is not positive definite")
+
+
+def synthetic_dataset(n, d, encoding, seed=0):
+    """SURVEY §8(d) / BASELINE.md §4 synthetic inputs (identical to oracle.driver.synthetic_dataset)."""
+    rng = np.random.default_rng(seed)
+    lo, hi = (-0.99, 0.99) if encoding in ("chebyshev", "kyriienko") else (-2.0, 2.0)
+    x = rng.uniform(lo, hi, (n, d))
+    y = np.sin(x.sum(axis=1)) + 0.1 * rng.standard_normal(n)
+    return x, y
+
+
+class AdmmEngine:
+    """All agents of a run, sharded over ranks in contiguous blocks (agent a lives on rank a // (A/world))."""
+
+    def __init__(self, shards, theta0, psi0, *, rho, L, process_group=None, rank=0, world_size=1, streams=True, **agent_kw):
+        _require_cuda()
+        self._lib = _lib.load()
+        self.A_total = int(theta0.shape[0])
+        self.P = int(theta0.shape[1])
+        self.world, self.rank, self.pg = int(world_size), int(rank), process_group
+        if self.A_total % self.world:
+            raise ValueError(f"{self.A_total} agents do not split evenly over {self.world} ranks")
+        self.A_local = self.A_total // self.world
+        if len(shards) != self.A_local:
+            raise ValueError(f"rank {rank} expects {self.A_local} shards, got {len(shards)}")
+        self.first = self.rank * self.A_local
+        self.rho = float(rho)
+        lips = L if np.ndim(L) else [L] * self.A_total
+        self.agents = [AgentEngine(x, y, rho=rho, L=lips[self.first + i], **agent_kw) for i, (x, y) in enumerate(shards)]
+        if any(a.P != self.P for a in self.agents):
+            raise ValueError("theta0 does not match the circuit's parameter count")
+        self.theta = dev_f64(theta0)
+        self.psi = dev_f64(psi0)
+        self.z = torch.empty(self.P, dtype=torch.float64, device=self.theta.device)
+        self.local_theta = torch.empty((self.A_local, self.P), dtype=torch.float64, device=self.theta.device)
+        self.local_psi = torch.empty_like(self.local_theta)
+        self.streams = [torch.cuda.Stream() for _ in self.agents] if (streams and self.A_local > 1) else None
+        self.entries_per_iteration = sum(a.entries_per_step for a in self.agents)
+
+    def consensus(self):
+        check(self._lib.dqgp_admm_consensus(self.theta.data_ptr(), self.psi.data_ptr(), self.A_total, self.P, self.rho, PERIOD,
+                                            self.z.data_ptr(), stream_ptr()), "consensus")
+
+    def iteration(self):
+        self.consensus()
+        if self.streams is None:
+            for i, ag in enumerate(self.agents):
+                ag.step(self.z, self.psi[self.first + i], self.local_theta[i], self.local_psi[i])
+        else:
+            main = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for i, ag in enumerate(self.agents):
+                s = self.streams[i]
+                s.wait_event(ready)
+                with torch.cuda.stream(s):
+                    ag.step(self.z, self.psi[self.first + i], self.local_theta[i], self.local_psi[i])
+                done = torch.cuda.Event()
+                done.record(s)
+                main.wait_event(done)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.theta, self.local_theta, group=self.pg)
+            dist.all_gather_into_tensor(self.psi, self.local_psi, group=self.pg)
+        else:
+            self.theta.copy_(self.local_theta)
+            self.psi.copy_(self.local_psi)
+
+    def state(self):
+        """(z, theta, psi, per-agent NLL) on the host (synchronises)."""
+        nll = np.array([float(a.d_nll[3].item()) for a in self.agents])
+        return self.z.cpu().numpy(), self.theta.cpu().numpy(), self.psi.cpu().numpy(), nll

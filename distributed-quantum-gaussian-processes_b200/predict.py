@@ -1,0 +1,126 @@
+"""GP prediction, NLPD and k-fold CV on the consensus parameters with the reference's signatures
+(``main.predict_quantum_gp`` main.py:1364-1488, NLPD main.py:1546-1552, ``k_fold_cross_validation_consensus``
+main.py:1490-1596).  K(train,train) goes straight into the solver, K(test,train) is a rectangular Gram,
+the predictive variance uses v = L^-1 K(test,train)^T through the DMMA GEMM, and — unlike the reference,
+which evaluates the full K(test,test) and keeps its diagonal (main.py:1430,1463) — only the diagonal
+k(x*,x*) is evaluated.  KFold orchestration stays on the host (scikit-learn), as in the reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+from .engine import Solver
+from .kernels import create_quantum_kernel, dev_f64, stream_ptr
+
+
+def predict_quantum_gp(X_train, Y_train, X_test, quantum_kernel_params, num_qubits, num_layers, noise_std,
+                       use_parameter_shift=True, encoding_type="yz_cx", kernel_type="fidelity", measurement="XYZ",
+                       outer_kernel="gaussian", outer_kernel_params=None, regularization=None, return_kernels=False,
+                       Y_test=None):
+    """-> (mean, var, K_tt, K_st, K_ss); the three matrices are None unless ``return_kernels`` (they are only
+    used for plots in the reference).  With ``Y_test`` the mean NLPD is computed on the device and attached as
+    ``predict_quantum_gp.last_nlpd``."""
+    lib = _lib.load()
+    X_train = np.asarray(X_train, dtype=np.float64)
+    X_test = np.asarray(X_test, dtype=np.float64)
+    if X_train.ndim == 1:
+        X_train = X_train.reshape(-1, 1)
+    if X_test.ndim == 1:
+        X_test = X_test.reshape(-1, 1)
+    d = X_train.shape[1]
+    qk = create_quantum_kernel(num_qubits, d, num_layers, use_parameter_shift, encoding_type, kernel_type, measurement,
+                               outer_kernel, outer_kernel_params, regularization)
+    qk.assign_parameters(quantum_kernel_params)
+    n, nt = X_train.shape[0], X_test.shape[0]
+    d_xtr, d_xte = dev_f64(X_train), dev_f64(X_test)
+    d_p = dev_f64(np.asarray(quantum_kernel_params, dtype=np.float64).reshape(1, -1))
+    d_y = dev_f64(np.asarray(Y_train, dtype=np.float64).reshape(-1))
+    st = stream_ptr()
+    solver = Solver(n)
+    k_tt = solver.matrix()
+    qk.evaluate_device(d_xtr, d_xtr, d_p, same=True, out=k_tt, ld=solver.ld)
+    k_tt_host = k_tt.cpu().numpy() if return_kernels else None
+    # K + sigma^2 I, then + 1e-6 I as two separate additions (main.py:1434-1438)
+    check(lib.dqgp_add_diagonal(solver.matrix_ptr, n, solver.ld, float(noise_std) ** 2, st), "add diagonal")
+    check(lib.dqgp_add_diagonal(solver.matrix_ptr, n, solver.ld, 1e-6, st), "add diagonal")
+    f64 = dict(dtype=torch.float64, device=d_xtr.device)
+    alpha, logdet = torch.empty(n, **f64), torch.zeros(1, **f64)
+    info = torch.zeros(1, dtype=torch.int32, device=d_xtr.device)
+    check(lib.dqgp_potrf_solve_inv(solver.handle, d_y.data_ptr(), alpha.data_ptr(), logdet.data_ptr(), info.data_ptr(), 0, st),
+          "potrf")
+    k_st = qk.evaluate_device(d_xte, d_xtr, d_p, same=False)
+    quad = torch.empty(nt, **f64)
+    check(lib.dqgp_solver_quadform_rows(solver.handle, k_st.data_ptr(), nt, n, quad.data_ptr(), st), "quadform")
+    # diag K(test,test): each test point against itself (1 x 1 Grams batched as a diagonal extraction)
+    kss_diag = _self_kernel_diag(qk, d_xte, d_p)
+    mean, var = torch.empty(nt, **f64), torch.empty(nt, **f64)
+    nlpd_buf = torch.empty(1 + nt, **f64) if Y_test is not None else None
+    d_yt = dev_f64(np.asarray(Y_test, dtype=np.float64).reshape(-1)) if Y_test is not None else None
+    check(lib.dqgp_predict_finish(k_st.data_ptr(), nt, n, n, alpha.data_ptr(), kss_diag.data_ptr(), quad.data_ptr(),
+                                  d_yt.data_ptr() if d_yt is not None else None, mean.data_ptr(), var.data_ptr(),
+                                  nlpd_buf.data_ptr() if nlpd_buf is not None else None, st), "predict finish")
+    if int(info.item()) != 0:
+        raise RuntimeError("Cholesky failed: training kernel matrix is not positive definite "
+                           "(the reference's np.linalg.inv fallback, main.py:1479-1486, is not on the GPU path)")
+    predict_quantum_gp.last_nlpd = float(nlpd_buf[0].item()) if nlpd_buf is not None else None
+    k_ss = qk.evaluate_device(d_xte, d_xte, d_p, same=True).cpu().numpy() if return_kernels else None
+    return (mean.cpu().numpy(), var.cpu().numpy(), k_tt_host, k_st.cpu().numpy() if return_kernels else None, k_ss)
+
+
+predict_quantum_gp.last_nlpd = None
+
+
+def _self_kernel_diag(qk, d_x, d_p):
+    """k(x_i, x_i) for every row: exactly outer(0) = 1 for the projected kernels; |<psi|psi>|^2 for fidelity."""
+    nt = d_x.shape[0]
+    if hasattr(qk, "outer_kernel"):
+        return torch.ones(nt, dtype=torch.float64, device=d_x.device)
+    s = qk.encoding_circuit.states(d_x, d_p)[0]           # (nt, dim, 2)
+    nrm = (s * s).sum(dim=(1, 2))
+    return nrm * nrm
+
+
+def nlpd(Y_true, y_pred_mean, y_pred_var):
+    """Mean negative log predictive density, main.py:1546-1552 (host formula for host arrays)."""
+    var = np.maximum(np.asarray(y_pred_var, dtype=np.float64), 1e-10)
+    r = np.asarray(Y_true, dtype=np.float64) - np.asarray(y_pred_mean, dtype=np.float64)
+    return float(np.mean(0.5 * np.log(2 * np.pi) + 0.5 * np.log(var) + 0.5 * (r ** 2 / var)))
+
+
+def k_fold_cross_validation_consensus(X_train, Y_train, consensus_params, num_qubits, num_layers, noise_std, k_folds=5,
+                                      use_parameter_shift=True, encoding_type="yz_cx", kernel_type="fidelity",
+                                      measurement="XYZ", outer_kernel="gaussian", outer_kernel_params=None,
+                                      regularization=None, random_seed=42):
+    """Same result dict as main.py:1490-1596 (mean/std NLPD, R^2, RMSE over valid folds)."""
+    from sklearn.metrics import mean_squared_error, r2_score
+    from sklearn.model_selection import KFold
+
+    X_train = np.asarray(X_train, dtype=np.float64)
+    Y_train = np.asarray(Y_train, dtype=np.float64)
+    fold_nlpds, fold_r2s, fold_rmses = [], [], []
+    for tr, va in KFold(n_splits=k_folds, shuffle=True, random_state=random_seed).split(X_train):
+        try:
+            mean, var, _, _, _ = predict_quantum_gp(X_train[tr], Y_train[tr], X_train[va], consensus_params, num_qubits,
+                                                    num_layers, noise_std, use_parameter_shift, encoding_type, kernel_type,
+                                                    measurement, outer_kernel, outer_kernel_params, regularization)
+            fold_nlpds.append(nlpd(Y_train[va], mean, var))
+            fold_r2s.append(r2_score(Y_train[va], mean))
+            fold_rmses.append(float(np.sqrt(mean_squared_error(Y_train[va], mean))))
+        except Exception:
+            fold_nlpds.append(float("inf"))
+            fold_r2s.append(-float("inf"))
+            fold_rmses.append(float("inf"))
+    valid = [v for v in fold_nlpds if not np.isinf(v)]
+    if len(valid) >= k_folds // 2:
+        ok = [not np.isinf(v) for v in fold_nlpds]
+        out = {"mean_nlpd": float(np.mean(valid)), "std_nlpd": float(np.std(valid)),
+               "mean_r2": float(np.mean([r for r, o in zip(fold_r2s, ok) if o])),
+               "mean_rmse": float(np.mean([r for r, o in zip(fold_rmses, ok) if o]))}
+    else:
+        out = {"mean_nlpd": float("inf"), "std_nlpd": float("inf"), "mean_r2": -float("inf"), "mean_rmse": float("inf")}
+    out.update({"fold_nlpds": fold_nlpds, "fold_r2s": fold_r2s, "fold_rmses": fold_rmses, "valid_folds": len(valid),
+                "total_folds": k_folds})
+    return out

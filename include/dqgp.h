@@ -1,0 +1,139 @@
+/* dqgp.h — C-ABI of the B200-native engine for the distributed quantum-GP hot path.
+ *
+ * The reference (mpala-lab/distributed-quantum-gaussian-processes) has no FFI: its seams are Python
+ * duck-typed calls into squlearn and NumPy.  Each entry point below names the reference interface it
+ * replaces (file:line relative to the reference checkout).  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory on the current CUDA device, contiguous row-major fp64
+ *     (complex128 = interleaved re,im doubles); h_* is HOST memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all work is enqueued on it
+ *     and nothing synchronises unless stated;
+ *   - return value: 0 = ok, <0 = error (dqgp_last_error() gives a thread-local message); nothing throws;
+ *   - no global mutable state; handles are immutable after creation and may be shared by streams,
+ *     except dqgp_solver (owns scratch: one in-flight use at a time);
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef DQGP_H
+#define DQGP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DQGP_VERSION 100
+
+/* encoding circuits (reference ctor sites main.py:68-83, agent_riemannian.py:51-66) */
+enum { DQGP_CHEBYSHEV = 0, DQGP_HUBREGTSEN = 1, DQGP_YZ_CX = 2, DQGP_KYRIIENKO = 3 };
+/* outer kernels of the projected kernel (main.py:130-137; sklearn RBF / Matern(1.5) / ExpSineSquared) */
+enum { DQGP_OUTER_GAUSSIAN = 0, DQGP_OUTER_MATERN15 = 1, DQGP_OUTER_EXPSINE2 = 2 };
+/* gate kinds / angle forms of the gate program (dqgp_circuit_describe) */
+enum { DQGP_G_H = 0, DQGP_G_RX = 1, DQGP_G_RY = 2, DQGP_G_RZ = 3, DQGP_G_CX = 4, DQGP_G_CRZ = 5 };
+enum { DQGP_A_NONE = 0, DQGP_A_P = 1, DQGP_A_X = 2, DQGP_A_P_PLUS_CX = 3, DQGP_A_P_TIMES_ACOS = 4, DQGP_A_C_TIMES_ACOS = 5 };
+
+typedef struct dqgp_gate {
+    int32_t kind;  /* DQGP_G_*                                   */
+    int32_t q0;    /* target (1-qubit) or control (CX, CRZ)      */
+    int32_t q1;    /* target of CX / CRZ, else -1                */
+    int32_t form;  /* DQGP_A_*                                   */
+    int32_t pidx;  /* parameter index or -1                      */
+    int32_t fidx;  /* feature index or -1                        */
+    double coef;   /* c in p + c*x  /  c*acos(x)                 */
+} dqgp_gate;
+
+typedef struct dqgp_circuit dqgp_circuit; /* immutable gate program resident on one device */
+typedef struct dqgp_solver dqgp_solver;   /* workspace + task tables of the fp64 Cholesky / inverse */
+
+int dqgp_version(void);
+const char* dqgp_last_error(void);
+
+/* ---- circuits: replaces squlearn ChebyshevPQC / HubregtsenEncodingCircuit / YZ_CX_EncodingCircuit /
+ *      KyriienkoEncodingCircuit (num_qubits, num_features, num_layers); all other options at defaults. */
+int dqgp_circuit_create(int encoding, int num_qubits, int num_features, int num_layers, dqgp_circuit** out);
+void dqgp_circuit_destroy(dqgp_circuit* c);
+int dqgp_circuit_num_parameters(const dqgp_circuit* c); /* = encoding_circuit.num_parameters (main.py:199) */
+int dqgp_circuit_num_gates(const dqgp_circuit* c);
+int dqgp_circuit_describe(const dqgp_circuit* c, dqgp_gate* h_out, int capacity); /* host copy of the program */
+
+/* ---- statevector simulation (what q_kernel.evaluate does per sample, agent_riemannian.py:118):
+ *      d_X (n,d), d_Pm (S,P) parameter sets.  Features: d_F (S,n,3q) = [<X_k>],[<Y_k>],[<Z_k>];
+ *      states: d_Psi (S,n,2^q) complex128. */
+int dqgp_features(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int S, double* d_F, void* stream);
+int dqgp_states(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int S, double* d_Psi, void* stream);
+
+/* ---- Gram matrices.  d_K (n1,n2) with leading dimension ldk (>= n2).
+ *      projected: K = outer(f1_j, f2_k); hyp = {gamma} | {length_scale} | {length_scale, periodicity}
+ *      (ProjectedQuantumKernel.evaluate, main.py:130-137);  fidelity: K = |<psi2_k|psi1_j>|^2
+ *      (FidelityKernel.evaluate, main.py:118-124). `same` != 0 promises the two operands are the same
+ *      array so the diagonal is exactly outer(0) / the mirror is exact. */
+int dqgp_gram_projected(int outer, const double* h_hyp, const double* d_F1, int n1, const double* d_F2, int n2, int m,
+                        double* d_K, int ldk, int same, void* stream);
+int dqgp_gram_fidelity(const double* d_Psi1, int n1, const double* d_Psi2, int n2, int dim, double* d_K, int ldk,
+                       int same, void* stream);
+
+/* ---- fp64 Cholesky / solve / inverse (agent_riemannian.py:410-418, :442): for the SPD matrix
+ *      A = K + sigma^2 I held in the solver (dqgp_solver_matrix, leading dimension dqgp_solver_ld):
+ *      factor, alpha = A^-1 y, A^-1 (full symmetric, dqgp_solver_inverse), logdet(A).
+ *      *d_info = 0 ok, j>0 = first non-positive pivot (1-based) so the host can mirror the
+ *      reference's LU -> pinv ladder (agent_riemannian.py:419-428) or raise. */
+int dqgp_solver_create(int n, dqgp_solver** out);
+void dqgp_solver_destroy(dqgp_solver* s);
+int dqgp_solver_n(const dqgp_solver* s);
+int dqgp_solver_ld(const dqgp_solver* s);
+double* dqgp_solver_matrix(dqgp_solver* s);  /* (n, ld): write A here (lower triangle is what is read) */
+double* dqgp_solver_inverse(dqgp_solver* s); /* (n, ld): A^-1 after dqgp_potrf_solve_inv               */
+double* dqgp_solver_factor(dqgp_solver* s);  /* (n, ld): L (lower) after the call                      */
+size_t dqgp_solver_bytes(const dqgp_solver* s);
+int dqgp_add_diagonal(double* d_A, int n, int lda, double value, void* stream);
+int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, double* d_logdet, int* d_info,
+                         int want_inverse, void* stream);
+/* v = L^-1 B^T for B (nb, n): returns column sums of v^2 -> d_out[nb] (main.py:1462-1463) */
+int dqgp_solver_quadform_rows(dqgp_solver* s, const double* d_B, int nb, int ldb, double* d_out, void* stream);
+
+/* fp64 GEMM building block on the DMMA tensor path (used by the factorisation; exposed for tests):
+ * C(MxN) = alpha*A*B + beta*C; A is [m][k] if a_k_contig else [k][m]; B is [n][k] if b_k_contig else [k][n].
+ * M, N multiples of 128; K multiple of 16; even leading dimensions; 16-byte aligned pointers. */
+int dqgp_dgemm(int a_k_contig, int b_k_contig, int M, int N, int K, double alpha, const double* d_A, int lda,
+               const double* d_B, int ldb, double beta, double* d_C, int ldc, void* stream);
+
+/* ---- parameter sets of the central-difference ("parameter shift") rule
+ *      (agent_riemannian.py:219,245-256 and the worker's wrap :41): d_Pm (2P+1, P). */
+int dqgp_shift_parameter_sets(const double* d_z, int P, double h, double period, double* d_Pm, void* stream);
+
+/* ---- fused gradient: grad_i = 1/2 sum_jk (A^-1 - alpha alpha^T)_jk (K(p+h e_i) - K(p-h e_i))_kj / (2h)
+ *      (agent_riemannian.py:270-275 and :431-436) without materialising any shifted Gram.
+ *      d_F: (2P+1, n, m) features / d_Psi: (2P+1, n, dim) states of the sets in dqgp_shift_parameter_sets
+ *      order; d_Ainv (n, ld).  d_work: dqgp_grad_workspace_bytes(n, P) bytes.  d_grad[P] is UNROUNDED. */
+size_t dqgp_grad_workspace_bytes(int n, int P);
+int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, int ld, const double* d_alpha,
+                        const double* d_F, int n, int m, int P, double h, double* d_grad, void* d_work, void* stream);
+int dqgp_grad_fidelity(const double* d_Ainv, int ld, const double* d_alpha, const double* d_Psi, int n, int dim, int P,
+                       double h, double* d_grad, void* d_work, void* stream);
+
+/* ---- NLL terms (agent_riemannian.py:441-452): d_out[4] = {1/2 logdet, 1/2 y^T alpha, n/2 log 2pi, total} */
+int dqgp_nll_terms(const double* d_logdet, const double* d_y, const double* d_alpha, int n, double* d_out, void* stream);
+
+/* ---- local ADMM update (agent_riemannian.py:438,479-486; riemannian_optimizer.py:324-368):
+ *      g4 = round(grad,4); theta = (z - (g4+psi)/(rho+L)) mod period; psi' = psi + rho*((theta - z) mod period);
+ *      outputs rounded to 4 decimals (psi' from the UNROUNDED theta).  z must already be wrapped. */
+int dqgp_admm_local(const double* d_z, const double* d_grad, const double* d_psi, int P, double rho, double lipschitz,
+                    double period, double* d_theta_out, double* d_psi_out, void* stream);
+/* ---- consensus (riemannian_optimizer.py:302-322 -> :26-51; rounding main.py:2523):
+ *      z = round(circular_mean(theta + psi/rho), 4) over A agents, summed in agent order. */
+int dqgp_admm_consensus(const double* d_theta, const double* d_psi, int A, int P, double rho, double period,
+                        double* d_z_out, void* stream);
+
+/* ---- GP prediction pieces (main.py:1458-1466, 1546-1552): mean = Kst alpha; var = max(diag - q, 1e-10);
+ *      d_nlpd[0] = mean_i(0.5 log 2pi + 0.5 log var_i + 0.5 (y_i-mean_i)^2/var_i). */
+int dqgp_predict_finish(const double* d_Kst, int nt, int n, int ldk, const double* d_alpha, const double* d_kss_diag,
+                        const double* d_quad, const double* d_ytest, double* d_mean, double* d_var, double* d_nlpd,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQGP_H */

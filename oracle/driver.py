@@ -50,11 +50,20 @@ def predict(cfg, x_train, y_train, x_test, params, noise_std):
     k_ss = k.evaluate(x_test, x_test)
     a = k_tt + (noise_std ** 2) * np.eye(k_tt.shape[0])
     a += 1e-6 * np.eye(k_tt.shape[0])
-    chol = np.linalg.cholesky(a)
-    alpha = np.linalg.solve(chol.T, np.linalg.solve(chol, y_train))
-    mean = k_st @ alpha
-    v = np.linalg.solve(chol, k_st.T)
-    var = np.maximum(np.diag(k_ss) - np.sum(v ** 2, axis=0), 1e-10)
+    try:
+        chol = np.linalg.cholesky(a)
+        alpha = np.linalg.solve(chol, y_train)
+        alpha = np.linalg.solve(chol.T, alpha)
+        mean = k_st @ alpha
+        v = np.linalg.solve(chol, k_st.T)
+        var = np.maximum(np.diag(k_ss) - np.sum(v ** 2, axis=0), 1e-10)
+    except np.linalg.LinAlgError:
+        # main.py:1470-1486: direct inversion when the Cholesky fails (e.g. ExpSineSquared of a Euclidean
+        # distance is not positive semi-definite in more than one dimension)
+        a_inv = np.linalg.inv(a)
+        alpha = a_inv @ y_train
+        mean = k_st @ alpha
+        var = np.maximum(np.diag(k_ss - k_st @ a_inv @ k_st.T), 1e-10)
     return mean, var
 
 

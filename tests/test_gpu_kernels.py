@@ -1,0 +1,221 @@
+"""GPU parity, kernel level: every C-ABI compute entry point against the oracle on seeded inputs.
+Tolerances: 1e-10 relative on K entries (BASELINE.json north_star), 1e-12 on features/states."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import AGENT_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def d():
+    import dqgp_b200
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box")
+    return dqgp_b200
+
+
+def _sp():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+CIRCUITS = [("chebyshev", 3, 2, 1), ("chebyshev", 4, 2, 3), ("hubregtsen", 5, 2, 2), ("hubregtsen", 3, 5, 1),
+            ("yz_cx", 8, 4, 3), ("yz_cx", 2, 1, 2), ("yz_cx", 1, 1, 1), ("kyriienko", 10, 6, 2), ("kyriienko", 6, 3, 2),
+            ("hubregtsen", 7, 3, 1), ("chebyshev", 9, 4, 1), ("yz_cx", 11, 5, 1)]
+
+
+@pytest.mark.parametrize("enc,q,dd,layers", CIRCUITS)
+def test_features_and_states_match_oracle(d, enc, q, dd, layers):
+    from oracle import circuits, statevector
+    rng = np.random.default_rng(q * 100 + dd)
+    n, S = 37, 5
+    lo, hi = (-0.99, 0.99) if enc in ("chebyshev", "kyriienko") else (-2, 2)
+    x = rng.uniform(lo, hi, (n, dd))
+    P = circuits.num_parameters(enc, q, layers)
+    pm = rng.uniform(0, np.pi, (S, max(P, 1)))[:, :P]
+    ec = d.EncodingCircuit(enc, q, dd, layers)
+    assert ec.num_parameters == P
+    dx, dpm = d.kernels.dev_f64(x), d.kernels.dev_f64(pm)
+    F = ec.features(dx, dpm).cpu().numpy()
+    Psi = ec.states(dx, dpm).cpu().numpy()
+    gates = circuits.build_circuit(enc, q, dd, layers)
+    for s in range(S):
+        ref = statevector.simulate(gates, q, x, pm[s])
+        got = Psi[s, :, :, 0] + 1j * Psi[s, :, :, 1]
+        assert np.abs(got - ref).max() < 1e-12
+        assert np.abs(F[s] - statevector.pauli_features(ref, q)).max() < 1e-12
+
+
+def test_features_empty_and_single(d):
+    ec = d.EncodingCircuit("yz_cx", 3, 2, 1)
+    dx = d.kernels.dev_f64(np.zeros((0, 2)))
+    dpm = d.kernels.dev_f64(np.zeros((1, ec.num_parameters)))
+    assert ec.features(dx, dpm).shape == (1, 0, 9)
+    one = ec.features(d.kernels.dev_f64(np.zeros((1, 2))), dpm).cpu().numpy()
+    assert np.allclose(one[0, 0], [0, 0, 0, 0, 0, 0, 1, 1, 1])        # |000>: <Z>=1, <X>=<Y>=0
+
+
+@pytest.mark.parametrize("outer", ["gaussian", "matern", "expsinesquared"])
+def test_gram_projected_matches_sklearn_golden(d, outer):
+    g = load_golden("outer_kernels.npz")
+    F, G = g["F"], g["G"]
+    lib = d.load()
+    dF, dG = d.kernels.dev_f64(F), d.kernels.dev_f64(G)
+    K = torch.empty((F.shape[0], G.shape[0]), dtype=torch.float64, device="cuda")
+    from dqgp_b200 import _lib
+    hyp = _lib.hyp_array(d.kernels.outer_hyp(outer))
+    rc = lib.dqgp_gram_projected(_lib.OUTER_KERNELS[outer], hyp, dF.data_ptr(), F.shape[0], dG.data_ptr(), G.shape[0],
+                                 F.shape[1], K.data_ptr(), G.shape[0], 0, _sp())
+    assert rc == 0
+    K = K.cpu().numpy()
+    ref = g[outer]
+    assert np.max(np.abs(K - ref) / np.abs(ref)) < 1e-10
+    assert np.all(K[:3, -3:].diagonal() == 1.0)          # exact duplicates -> exactly outer(0) = 1
+
+
+@pytest.mark.parametrize("case", AGENT_CASES)
+def test_kernel_evaluate_matches_reference_K(d, case):
+    """q_kernel.evaluate(X, X) through the Python mirror == the K the real reference agent computed."""
+    g = load_golden(f"agent_step_{case}.npz")
+    qk = d.create_quantum_kernel(int(g["q"]), int(g["d"]), int(g["layers"]), True, str(g["encoding"]), str(g["kernel_type"]),
+                                 "XYZ", "gaussian")   # training Grams are Gaussian in the reference (Q1)
+    qk.assign_parameters(np.mod(g["z"], np.pi))
+    K = qk.evaluate(g["X"], g["X"])
+    ref = g["K"]
+    assert np.max(np.abs(K - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-10
+    assert np.allclose(K, K.T, rtol=0, atol=1e-14)
+    Kt = qk.evaluate(g["X_test"], g["X"])
+    if str(g["outer_kernel"]) == "gaussian" or str(g["kernel_type"]) == "fidelity":
+        assert np.max(np.abs(Kt - g["K_test_train"])) < 1e-12
+
+
+def test_gram_rectangular_ragged_shapes(d):
+    from oracle import qkernels
+    rng = np.random.default_rng(0)
+    for n1, n2 in [(1, 1), (63, 65), (64, 64), (129, 7), (5, 200)]:
+        F, G = rng.uniform(-1, 1, (n1, 9)), rng.uniform(-1, 1, (n2, 9))
+        ref = qkernels.outer_kernel_matrix("matern", F, G)
+        from dqgp_b200 import _lib
+        K = torch.full((n1, n2 + 3), -7.0, dtype=torch.float64, device="cuda")     # ld > n2, odd ld
+        rc = d.load().dqgp_gram_projected(1, _lib.hyp_array([1.0]), d.kernels.dev_f64(F).data_ptr(), n1,
+                                          d.kernels.dev_f64(G).data_ptr(), n2, 9, K.data_ptr(), n2 + 3, 0, _sp())
+        assert rc == 0
+        K = K.cpu().numpy()
+        assert np.max(np.abs(K[:, :n2] - ref)) < 1e-13
+        assert np.all(K[:, n2:] == -7.0)                  # nothing written past the logical width
+
+
+@pytest.mark.parametrize("akc,bkc", [(1, 1), (1, 0), (0, 0), (0, 1)])
+def test_dgemm_all_operand_layouts(d, akc, bkc):
+    rng = np.random.default_rng(akc * 2 + bkc)
+    M, N, K = 256, 384, 208
+    A = rng.standard_normal((M, K)); B = rng.standard_normal((K, N)); Cm = rng.standard_normal((M, N))
+    dA = d.kernels.dev_f64(A if akc else A.T.copy())
+    dB = d.kernels.dev_f64(B.T.copy() if bkc else B)
+    dC = d.kernels.dev_f64(Cm)
+    rc = d.load().dqgp_dgemm(akc, bkc, M, N, K, -0.5, dA.data_ptr(), dA.shape[1], dB.data_ptr(), dB.shape[1], 2.0,
+                             dC.data_ptr(), N, _sp())
+    assert rc == 0, d.load().dqgp_last_error()
+    ref = -0.5 * A @ B + 2.0 * Cm
+    assert np.max(np.abs(dC.cpu().numpy() - ref)) < 1e-11
+
+
+def test_dgemm_rejects_bad_shapes(d):
+    t = torch.zeros(16, dtype=torch.float64, device="cuda")
+    lib = d.load()
+    assert lib.dqgp_dgemm(1, 1, 100, 128, 16, 1.0, t.data_ptr(), 16, t.data_ptr(), 16, 0.0, t.data_ptr(), 128, _sp()) < 0
+    assert b"multiples" in lib.dqgp_last_error()
+
+
+@pytest.mark.parametrize("n", [1, 5, 127, 128, 129, 300, 640, 1100])
+def test_potrf_solve_inv_matches_lapack(d, n):
+    rng = np.random.default_rng(n)
+    F = rng.uniform(-1, 1, (n, 6))
+    from oracle import qkernels
+    A = qkernels.outer_kernel_matrix("gaussian", F, F) + 0.01 * np.eye(n)
+    y = rng.standard_normal(n)
+    s = d.engine.Solver(n)
+    s.matrix().copy_(torch.from_numpy(A).cuda())
+    f64 = dict(dtype=torch.float64, device="cuda")
+    alpha, logdet, info = torch.empty(n, **f64), torch.zeros(1, **f64), torch.zeros(1, dtype=torch.int32, device="cuda")
+    rc = d.load().dqgp_potrf_solve_inv(s.handle, d.kernels.dev_f64(y).data_ptr(), alpha.data_ptr(), logdet.data_ptr(),
+                                       info.data_ptr(), 2, _sp())
+    assert rc == 0 and int(info.item()) == 0
+    L = np.linalg.cholesky(A)
+    ref_alpha = np.linalg.solve(L.T, np.linalg.solve(L, y))
+    ref_inv = np.linalg.solve(L.T, np.linalg.solve(L, np.eye(n)))
+    sign, ref_logdet = np.linalg.slogdet(A)
+    assert abs(logdet.item() - ref_logdet) < 1e-9 * max(1.0, abs(ref_logdet))
+    scale = np.abs(ref_inv).max()
+    assert np.max(np.abs(s.inverse().cpu().numpy() - ref_inv)) < 1e-9 * scale
+    assert np.max(np.abs(alpha.cpu().numpy() - ref_alpha)) < 1e-9 * np.abs(ref_alpha).max()
+    assert np.max(np.abs(np.tril(s.matrix().cpu().numpy()) - L)) < 1e-11
+
+
+def test_potrf_reports_non_spd(d):
+    n = 200
+    A = np.eye(n); A[150, 150] = -1.0
+    s = d.engine.Solver(n)
+    s.matrix().copy_(torch.from_numpy(A).cuda())
+    f64 = dict(dtype=torch.float64, device="cuda")
+    alpha, logdet, info = torch.empty(n, **f64), torch.zeros(1, **f64), torch.zeros(1, dtype=torch.int32, device="cuda")
+    d.load().dqgp_potrf_solve_inv(s.handle, torch.zeros(n, **f64).data_ptr(), alpha.data_ptr(), logdet.data_ptr(), info.data_ptr(), 0, _sp())
+    assert int(info.item()) == 151
+
+
+@pytest.mark.parametrize("case", AGENT_CASES)
+def test_fused_gradient_matches_oracle(d, case):
+    """dqgp_grad_* on the oracle's A^-1 and alpha == 1/2 sum(B * dK_i^T) with materialised dK (agent_riemannian.py:431-436)."""
+    from oracle import agent_step
+    g = load_golden(f"agent_step_{case}.npz")
+    cfg = agent_step.KernelConfig(str(g["encoding"]), str(g["kernel_type"]), int(g["q"]), int(g["layers"]), str(g["outer_kernel"]))
+    X, Y, z = g["X"], g["Y"], np.mod(g["z"], np.pi)
+    K, dK = agent_step.kernel_and_derivatives(cfg, X, z, float(g["h"]))
+    grad_ref, comp, _, alpha, cinv = agent_step.gp_terms(K, dK, Y, 0.1, want_cond=False)
+    eng = d.AgentEngine(X, Y, encoding_type=cfg.encoding_type, kernel_type=cfg.kernel_type, num_qubits=cfg.num_qubits,
+                        num_layers=cfg.num_layers, noise_std=0.1, rho=100.0, L=100.0, outer_kernel=cfg.outer_kernel)
+    eng.simulate(d.kernels.dev_f64(g["z"]))
+    eng.gram(); eng.factor(); eng.gradient()
+    torch.cuda.synchronize()
+    assert np.max(np.abs(eng.d_alpha.cpu().numpy() - alpha)) < 1e-8 * np.abs(alpha).max()
+    got = eng.d_grad.cpu().numpy()
+    assert np.max(np.abs(got - grad_ref)) < 1e-8 * max(1.0, np.abs(grad_ref).max())
+    nll = eng.d_nll.cpu().numpy()
+    assert abs(nll[3] - float(g["nll"])) < 1e-8 * max(1.0, abs(float(g["nll"])))
+    assert abs(nll[0] - float(g["log_det_term"])) < 1e-8 * max(1.0, abs(float(g["log_det_term"])))
+    assert abs(nll[1] - float(g["quadratic_term"])) < 1e-8 * max(1.0, abs(float(g["quadratic_term"])))
+    assert nll[2] == pytest.approx(float(g["constant_term"]), rel=1e-15)
+
+
+def test_admm_kernels_match_reference_golden(d):
+    g = load_golden("torus.npz")
+    lib = d.load()
+    for c in range(4):
+        theta, psi, grad, rho = g[f"c{c}_theta"], g[f"c{c}_psi"], g[f"c{c}_grad"], float(g[f"c{c}_rho"])
+        A, P = theta.shape
+        dz = torch.empty(P, dtype=torch.float64, device="cuda")
+        assert lib.dqgp_admm_consensus(d.kernels.dev_f64(theta).data_ptr(), d.kernels.dev_f64(psi).data_ptr(), A, P, rho, np.pi,
+                                       dz.data_ptr(), _sp()) == 0
+        z_ref = np.round(g[f"c{c}_z"], 4)
+        assert np.max(np.abs(dz.cpu().numpy() - z_ref)) < 1e-12          # same 1e-4 grid point
+        th, ps = torch.empty(P, dtype=torch.float64, device="cuda"), torch.empty(P, dtype=torch.float64, device="cuda")
+        zw = np.mod(z_ref, np.pi)
+        assert lib.dqgp_admm_local(d.kernels.dev_f64(zw).data_ptr(), d.kernels.dev_f64(grad).data_ptr(),
+                                   d.kernels.dev_f64(psi[0]).data_ptr(), P, rho, 100.0, np.pi, th.data_ptr(), ps.data_ptr(), _sp()) == 0
+        assert np.array_equal(th.cpu().numpy(), np.round(g[f"c{c}_theta_new"], 4))      # bit-exact
+        assert np.array_equal(ps.cpu().numpy(), np.round(g[f"c{c}_psi_new"], 4))
+
+
+def test_shift_parameter_sets_bit_exact(d):
+    from oracle import agent_step
+    rng = np.random.default_rng(4)
+    z = np.round(rng.uniform(-1, 4, 17), 4)
+    ref = agent_step.shifted_parameter_sets(z, np.pi / 8)
+    out = torch.empty(ref.shape, dtype=torch.float64, device="cuda")
+    assert d.load().dqgp_shift_parameter_sets(d.kernels.dev_f64(z).data_ptr(), 17, np.pi / 8, np.pi, out.data_ptr(), _sp()) == 0
+    assert np.array_equal(out.cpu().numpy(), ref)

@@ -1,0 +1,115 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/dqgp.h declares (no compute
+calls), the library's gate programs equal the oracle's, the host mirror equals the reference's formulas,
+and the product fails loudly without a GPU instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+@pytest.fixture(scope="module")
+def d():
+    import __graft_entry__
+    __graft_entry__.build()
+    import dqgp_b200
+    return dqgp_b200
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dqgp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dqgp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(d):
+    names = _declared_symbols()
+    assert len(names) >= 30
+    lib = ctypes.CDLL(d._lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/dqgp.h but not exported by libdqgp.so"
+    assert sorted(d._lib.SIGNATURES) == names, "ctypes signature table and header drifted"
+    assert d.load().dqgp_version() == 100
+
+
+def test_library_is_sm100a_dmma_code(d):
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", d._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "DMMA.8x8x4" in sass            # fp64 tensor path in the factorisation
+    assert "LDGSTS" in sass                # async global->shared staging
+
+
+@pytest.mark.parametrize("enc,q,dd,layers", [("chebyshev", 3, 2, 1), ("chebyshev", 4, 2, 3), ("chebyshev", 2, 1, 2),
+                                            ("hubregtsen", 5, 2, 2), ("hubregtsen", 3, 7, 2), ("hubregtsen", 2, 2, 1),
+                                            ("yz_cx", 8, 4, 3), ("yz_cx", 5, 2, 4), ("yz_cx", 1, 1, 1),
+                                            ("kyriienko", 10, 6, 4), ("kyriienko", 3, 2, 1)])
+def test_library_gate_program_equals_oracle(d, enc, q, dd, layers):
+    from oracle import circuits
+    kinds = {"h": 0, "rx": 1, "ry": 2, "rz": 3, "cx": 4, "crz": 5}
+    forms = {"": 0, "p": 1, "x": 2, "p+cx": 3, "p*acos": 4, "c*acos": 5}
+    ec = d.EncodingCircuit(enc, q, dd, layers)       # host-side program; no device needed
+    got = ec.describe()
+    ref = circuits.build_circuit(enc, q, dd, layers)
+    assert ec.num_parameters == circuits.num_parameters(enc, q, layers)
+    assert len(got) == len(ref)
+    for (kind, q0, q1, form, pidx, fidx, coef), g in zip(got, ref):
+        assert (kind, q0, q1, form, pidx, fidx) == (kinds[g.name], g.q0, g.q1, forms[g.form], g.pidx, g.fidx)
+        if g.form in ("p+cx", "c*acos"):
+            assert coef == g.coef
+
+
+def test_circuit_argument_errors(d):
+    with pytest.raises(ValueError, match="Unknown encoding type"):
+        d.EncodingCircuit("layered", 3, 2, 1)
+    with pytest.raises(d.DqgpError):
+        d.EncodingCircuit("yz_cx", 40, 2, 1)
+
+
+def test_host_mirror_equals_reference_formulas(d):
+    g = load_golden("torus.npz")
+    for c in range(4):
+        theta, psi, grad, rho = g[f"c{c}_theta"], g[f"c{c}_psi"], g[f"c{c}_grad"], float(g[f"c{c}_rho"])
+        man, opt, admm = d.create_riemannian_framework(theta.shape[1], rho=rho)
+        assert np.array_equal(admm.update_z(theta, psi), g[f"c{c}_z"])
+        assert np.array_equal(d.circular_mean(theta), g[f"c{c}_circmean"])
+        zr = man.wrap_to_manifold(np.round(g[f"c{c}_z"], 4))
+        th = admm.update_theta(zr, grad, psi[0], 100.0, opt)
+        assert np.array_equal(th, g[f"c{c}_theta_new"])
+        assert np.array_equal(admm.update_psi(psi[0], th, zr), g[f"c{c}_psi_new"])
+        assert np.array_equal(man.log_map(theta[0], theta[1]), g[f"c{c}_logmap"])
+        assert man.distance(theta[0], theta[1]) == float(g[f"c{c}_dist"])
+    with pytest.raises(NotImplementedError):
+        opt.step(theta[0], grad)
+
+
+def test_no_cpu_fallback(d):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(d.DqgpError, match="no CPU fallback"):
+        d.create_quantum_kernel(3, 2, 1, True, "yz_cx", "projected")
+    x = np.zeros((4, 2))
+    with pytest.raises(d.DqgpError):
+        d.RiemannianAgent("a", x, np.zeros(4), 3, 0.1, 100, 100, encoding_type="yz_cx", kernel_type="projected",
+                          num_layers=1).train_and_update(np.zeros(6), np.zeros(6))
+    with pytest.raises(d.DqgpError):
+        d.predict_quantum_gp(x, np.zeros(4), x, np.zeros(6), 3, 1, 0.1, encoding_type="yz_cx", kernel_type="projected")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "distributed-quantum-gaussian-processes_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{fn} imports the oracle"
+
+
+def test_synthetic_dataset_identical_to_oracle(d):
+    from oracle import driver
+    for enc in ("yz_cx", "chebyshev"):
+        a, b = d.synthetic_dataset(50, 3, enc), driver.synthetic_dataset(50, 3, enc)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
