@@ -124,6 +124,7 @@ int dqgp_gram_projected(int outer, const double* h_hyp, const double* d_F1, int 
                         double* d_K, int ldk, int same, void* stream) {
     using namespace dqgp;
     (void)same;  // direct differences already give exact zeros on identical operands
+    if (n1 == 0 || n2 == 0) return 0;
     DQGP_REQUIRE(d_F1 && d_F2 && d_K, "dqgp_gram_projected: NULL argument");
     DQGP_REQUIRE(m >= 1 && m <= PW_MAX_M, "dqgp_gram_projected: feature count %d outside [1,%d]", m, PW_MAX_M);
     DQGP_REQUIRE(n1 >= 0 && n2 >= 0 && ldk >= n2, "dqgp_gram_projected: bad shape (%d,%d) ld %d", n1, n2, ldk);
@@ -145,6 +146,7 @@ int dqgp_gram_fidelity(const double* d_Psi1, int n1, const double* d_Psi2, int n
                        void* stream) {
     using namespace dqgp;
     (void)same;
+    if (n1 == 0 || n2 == 0) return 0;
     DQGP_REQUIRE(d_Psi1 && d_Psi2 && d_K, "dqgp_gram_fidelity: NULL argument");
     DQGP_REQUIRE(dim >= 1 && n1 >= 0 && n2 >= 0 && ldk >= n2, "dqgp_gram_fidelity: bad shape");
     if (n1 == 0 || n2 == 0) return 0;

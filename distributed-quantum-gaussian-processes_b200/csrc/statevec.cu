@@ -193,9 +193,9 @@ static int launch_sv(const dqgp_circuit* c, const double* X, int n, const double
 
 template <bool WANT_STATES>
 static int dispatch_sv(const dqgp_circuit* c, const double* X, int n, const double* Pm, int S, double* out, void* stream) {
-    DQGP_REQUIRE(c && X && Pm && out, "statevector: NULL argument");
     DQGP_REQUIRE(n >= 0 && S >= 0, "statevector: negative size");
-    if (n == 0 || S == 0) return 0;
+    if (n == 0 || S == 0) return 0;      // empty input: nothing to do (pointers may be NULL)
+    DQGP_REQUIRE(c && X && Pm && out, "statevector: NULL argument");
     int rc = circuit_on_device(c);
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);

@@ -102,8 +102,9 @@ def test_gram_rectangular_ragged_shapes(d):
         ref = qkernels.outer_kernel_matrix("matern", F, G)
         from dqgp_b200 import _lib
         K = torch.full((n1, n2 + 3), -7.0, dtype=torch.float64, device="cuda")     # ld > n2, odd ld
-        rc = d.load().dqgp_gram_projected(1, _lib.hyp_array([1.0]), d.kernels.dev_f64(F).data_ptr(), n1,
-                                          d.kernels.dev_f64(G).data_ptr(), n2, 9, K.data_ptr(), n2 + 3, 0, _sp())
+        dF, dG = d.kernels.dev_f64(F), d.kernels.dev_f64(G)
+        rc = d.load().dqgp_gram_projected(1, _lib.hyp_array([1.0]), dF.data_ptr(), n1, dG.data_ptr(), n2, 9, K.data_ptr(),
+                                          n2 + 3, 0, _sp())
         assert rc == 0
         K = K.cpu().numpy()
         assert np.max(np.abs(K[:, :n2] - ref)) < 1e-13
@@ -143,8 +144,8 @@ def test_potrf_solve_inv_matches_lapack(d, n):
     s.matrix().copy_(torch.from_numpy(A).cuda())
     f64 = dict(dtype=torch.float64, device="cuda")
     alpha, logdet, info = torch.empty(n, **f64), torch.zeros(1, **f64), torch.zeros(1, dtype=torch.int32, device="cuda")
-    rc = d.load().dqgp_potrf_solve_inv(s.handle, d.kernels.dev_f64(y).data_ptr(), alpha.data_ptr(), logdet.data_ptr(),
-                                       info.data_ptr(), 2, _sp())
+    dy = d.kernels.dev_f64(y)
+    rc = d.load().dqgp_potrf_solve_inv(s.handle, dy.data_ptr(), alpha.data_ptr(), logdet.data_ptr(), info.data_ptr(), 2, _sp())
     assert rc == 0 and int(info.item()) == 0
     L = np.linalg.cholesky(A)
     ref_alpha = np.linalg.solve(L.T, np.linalg.solve(L, y))
@@ -164,7 +165,8 @@ def test_potrf_reports_non_spd(d):
     s.matrix().copy_(torch.from_numpy(A).cuda())
     f64 = dict(dtype=torch.float64, device="cuda")
     alpha, logdet, info = torch.empty(n, **f64), torch.zeros(1, **f64), torch.zeros(1, dtype=torch.int32, device="cuda")
-    d.load().dqgp_potrf_solve_inv(s.handle, torch.zeros(n, **f64).data_ptr(), alpha.data_ptr(), logdet.data_ptr(), info.data_ptr(), 0, _sp())
+    dy = torch.zeros(n, **f64)
+    d.load().dqgp_potrf_solve_inv(s.handle, dy.data_ptr(), alpha.data_ptr(), logdet.data_ptr(), info.data_ptr(), 0, _sp())
     assert int(info.item()) == 151
 
 
@@ -199,14 +201,15 @@ def test_admm_kernels_match_reference_golden(d):
         theta, psi, grad, rho = g[f"c{c}_theta"], g[f"c{c}_psi"], g[f"c{c}_grad"], float(g[f"c{c}_rho"])
         A, P = theta.shape
         dz = torch.empty(P, dtype=torch.float64, device="cuda")
-        assert lib.dqgp_admm_consensus(d.kernels.dev_f64(theta).data_ptr(), d.kernels.dev_f64(psi).data_ptr(), A, P, rho, np.pi,
-                                       dz.data_ptr(), _sp()) == 0
+        dth, dps = d.kernels.dev_f64(theta), d.kernels.dev_f64(psi)
+        assert lib.dqgp_admm_consensus(dth.data_ptr(), dps.data_ptr(), A, P, rho, np.pi, dz.data_ptr(), _sp()) == 0
         z_ref = np.round(g[f"c{c}_z"], 4)
         assert np.max(np.abs(dz.cpu().numpy() - z_ref)) < 1e-12          # same 1e-4 grid point
         th, ps = torch.empty(P, dtype=torch.float64, device="cuda"), torch.empty(P, dtype=torch.float64, device="cuda")
         zw = np.mod(z_ref, np.pi)
-        assert lib.dqgp_admm_local(d.kernels.dev_f64(zw).data_ptr(), d.kernels.dev_f64(grad).data_ptr(),
-                                   d.kernels.dev_f64(psi[0]).data_ptr(), P, rho, 100.0, np.pi, th.data_ptr(), ps.data_ptr(), _sp()) == 0
+        dzw, dgr, dp0 = d.kernels.dev_f64(zw), d.kernels.dev_f64(grad), d.kernels.dev_f64(psi[0])
+        assert lib.dqgp_admm_local(dzw.data_ptr(), dgr.data_ptr(), dp0.data_ptr(), P, rho, 100.0, np.pi, th.data_ptr(),
+                                   ps.data_ptr(), _sp()) == 0
         assert np.array_equal(th.cpu().numpy(), np.round(g[f"c{c}_theta_new"], 4))      # bit-exact
         assert np.array_equal(ps.cpu().numpy(), np.round(g[f"c{c}_psi_new"], 4))
 
@@ -217,5 +220,6 @@ def test_shift_parameter_sets_bit_exact(d):
     z = np.round(rng.uniform(-1, 4, 17), 4)
     ref = agent_step.shifted_parameter_sets(z, np.pi / 8)
     out = torch.empty(ref.shape, dtype=torch.float64, device="cuda")
-    assert d.load().dqgp_shift_parameter_sets(d.kernels.dev_f64(z).data_ptr(), 17, np.pi / 8, np.pi, out.data_ptr(), _sp()) == 0
+    dz = d.kernels.dev_f64(z)
+    assert d.load().dqgp_shift_parameter_sets(dz.data_ptr(), 17, np.pi / 8, np.pi, out.data_ptr(), _sp()) == 0
     assert np.array_equal(out.cpu().numpy(), ref)
