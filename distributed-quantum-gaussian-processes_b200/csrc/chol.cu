@@ -13,8 +13,6 @@
 
 namespace dqgp {
 constexpr int NB = 128;
-constexpr int LEAF_PITCH = NB + 1;
-constexpr size_t LEAF_SMEM = sizeof(double) * NB * LEAF_PITCH;
 }  // namespace dqgp
 
 struct dqgp_solver {
@@ -33,72 +31,164 @@ struct dqgp_solver {
 
 namespace dqgp {
 
-// ---- leaf: Cholesky of a 128x128 diagonal block in shared memory, then its inverse in place -------------
-__global__ void __launch_bounds__(256, 1) potrf_leaf_kernel(double* __restrict__ A, int ld, double* __restrict__ W, int blk,
-                                                            double* logdet, int* info, int n_real) {
-    extern __shared__ double S[];
-    __shared__ double s_red[8];
+// ---- leaf: Cholesky of a 128x128 diagonal block and its triangular inverse, one CTA, 128 threads -----------
+// One shared 128x130 array M holds both results: the strict upper triangle keeps L transposed
+// (M[k][i] = L[i][k], k < i) and the strict lower triangle receives W = L^-1 (M[k][j] = W[k][j], j < k);
+// the diagonals live in s_diag / s_rdiag.  Phase 1 is a left-looking Cholesky in panels of 8 columns: thread
+// i owns row i, keeps its 8 panel entries in registers, and per k issues 1 conflict-free LDS + 4 broadcast
+// LDS.128 for 8 DFMA; the 8x8 diagonal block is factored inside one warp with shuffles.  Phase 2 inverts L
+// column by column (thread j owns column j of W) in panels of 8 rows with the same 5-loads-per-8-DFMA
+// pattern and no barrier at all.  (v1 was an unblocked right-looking loop: 281 us per leaf; ncu r01_v1_leaf.)
+constexpr int LEAF_THREADS = 128;
+constexpr int LP = 130;
+constexpr size_t LEAF_SMEM_V2 = sizeof(double) * (NB * LP + 2 * NB);
+
+__global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __restrict__ A, int ld, double* __restrict__ W,
+                                                                      int blk, double* logdet, int* info, int n_real) {
+    extern __shared__ __align__(16) double leaf_smem[];
+    double* M = leaf_smem;
+    double* s_diag = M + NB * LP;
+    double* s_rdiag = s_diag + NB;
+    __shared__ double s_red[LEAF_THREADS / 32];
     __shared__ int s_bad;
-    const int tid = threadIdx.x;
+    const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
     double* Ablk = A + (size_t)blk * NB * ld + (size_t)blk * NB;
     double* Wblk = W + (size_t)blk * NB * ld + (size_t)blk * NB;
-    if (tid == 0) s_bad = 0;
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e >> 7, c = e & 127;
-        S[r * LEAF_PITCH + c] = (c <= r) ? Ablk[(size_t)r * ld + c] : 0.0;
-    }
+    if (i == 0) s_bad = 0;
     __syncthreads();
-    for (int j = 0; j < NB; ++j) {
-        const double piv = S[j * LEAF_PITCH + j];
-        if (!(piv > 0.0) && tid == 0 && s_bad == 0) s_bad = j + 1;
-        const double d = sqrt(piv);
-        const double inv = 1.0 / d;
-        __syncthreads();
-        if (tid == 0) S[j * LEAF_PITCH + j] = d;
-        for (int i = j + 1 + tid; i < NB; i += 256) S[i * LEAF_PITCH + j] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: two threads per row, interleaved columns
-        const int i = j + 1 + (tid >> 1);
-        if (i < NB) {
-            const double lij = S[i * LEAF_PITCH + j];
-            for (int k = j + 1 + (tid & 1); k <= i; k += 2) S[i * LEAF_PITCH + k] = fma(-lij, S[k * LEAF_PITCH + j], S[i * LEAF_PITCH + k]);
+
+    // ---------------- phase 1: Cholesky ----------------
+    double a[8];
+    {
+        const double2* src = reinterpret_cast<const double2*>(Ablk + (size_t)i * ld);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const double2 v = src[c]; a[2 * c] = v.x; a[2 * c + 1] = v.y; }
+    }
+    for (int j0 = 0; j0 < NB; j0 += 8) {
+        double nxt[8];
+        if (j0 + 8 < NB && i >= j0 + 8) {   // prefetch the next panel's entries of this row (hidden behind the update)
+            const double2* src = reinterpret_cast<const double2*>(Ablk + (size_t)i * ld + j0 + 8);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const double2 v = src[c]; nxt[2 * c] = v.x; nxt[2 * c + 1] = v.y; }
+        }
+        if (i >= j0) {
+#pragma unroll 4
+            for (int k = 0; k < j0; ++k) {
+                const double lik = M[k * LP + i];
+                const double2* row = reinterpret_cast<const double2*>(&M[k * LP + j0]);
+                const double2 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+                a[0] = fma(-lik, v0.x, a[0]); a[1] = fma(-lik, v0.y, a[1]);
+                a[2] = fma(-lik, v1.x, a[2]); a[3] = fma(-lik, v1.y, a[3]);
+                a[4] = fma(-lik, v2.x, a[4]); a[5] = fma(-lik, v2.y, a[5]);
+                a[6] = fma(-lik, v3.x, a[6]); a[7] = fma(-lik, v3.y, a[7]);
+            }
+        }
+        if (warp == (j0 >> 5)) {
+            // the warp that owns rows j0..j0+7 factors the 8x8 block and finishes its own rows with shuffles
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int src_lane = (j0 + c) & 31;
+                const double piv = __shfl_sync(0xffffffffu, a[c], src_lane);
+                if (!(piv > 0.0) && lane == 0 && s_bad == 0) s_bad = j0 + c + 1;
+                const double d = sqrt(piv), rd = 1.0 / d;
+                if (i > j0 + c) a[c] *= rd;
+                else if (i == j0 + c) { a[c] = d; s_diag[i] = d; s_rdiag[i] = rd; }
+#pragma unroll
+                for (int c2 = c + 1; c2 < 8; ++c2) {
+                    const double lc = __shfl_sync(0xffffffffu, a[c], (j0 + c2) & 31);   // L[j0+c2][j0+c]
+                    if (i > j0 + c) a[c2] = fma(-a[c], lc, a[c2]);
+                }
+            }
+            if (i >= j0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (i > j0 + c) M[(j0 + c) * LP + i] = a[c];
+            }
         }
         __syncthreads();
-    }
-    // write L (upper part of the block zeroed), accumulate log-determinant
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e >> 7, c = e & 127;
-        Ablk[(size_t)r * ld + c] = S[r * LEAF_PITCH + c];
+        if (warp != (j0 >> 5) && i >= j0 + 8) {
+            // rows owned by the other warps: forward substitution against the 8x8 block now in shared memory
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double x = a[c];
+#pragma unroll
+                for (int k = 0; k < c; ++k) x = fma(-a[k], M[(j0 + k) * LP + j0 + c], x);
+                x *= s_rdiag[j0 + c];
+                a[c] = x;
+                M[(j0 + c) * LP + i] = x;
+            }
+        }
+        if (i >= j0) {
+            double2* dst = reinterpret_cast<double2*>(Ablk + (size_t)i * ld + j0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                dst[c] = make_double2((i >= j0 + 2 * c) ? a[2 * c] : 0.0, (i >= j0 + 2 * c + 1) ? a[2 * c + 1] : 0.0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[c] = nxt[c];
     }
     {
-        double v = (tid < NB) ? log(S[tid * LEAF_PITCH + tid]) : 0.0;
+        double v = log(s_diag[i]);
         v = warp_sum(v);
-        if ((tid & 31) == 0) s_red[tid >> 5] = v;
+        if (lane == 0) s_red[warp] = v;
         __syncthreads();
-        if (tid == 0) {
+        if (i == 0) {
             double tot = 0.0;
-            for (int w = 0; w < 8; ++w) tot += s_red[w];
+#pragma unroll
+            for (int w = 0; w < LEAF_THREADS / 32; ++w) tot += s_red[w];
             *logdet += 2.0 * tot;
             if (s_bad && *info == 0 && blk * NB + s_bad <= n_real) *info = blk * NB + s_bad;
         }
     }
-    __syncthreads();
-    // in-place inverse of the lower-triangular block, last column first (LAPACK dtrti2 order)
-    for (int j = NB - 1; j >= 0; --j) {
-        const double wjj = 1.0 / S[j * LEAF_PITCH + j];
-        double acc = 0.0;
-        const int i = j + 1 + tid;
-        if (i < NB) {
-            for (int k = j + 1; k <= i; ++k) acc = fma(S[i * LEAF_PITCH + k], S[k * LEAF_PITCH + j], acc);
+
+    // ---------------- phase 2: W = L^-1, thread j owns column j ----------------
+    const int j = i;
+    for (int i0 = 0; i0 < NB; i0 += 8) {
+        if (j > i0 + 7) continue;
+        double acc[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+        if (j < i0) {
+            {   // k = j: W[j][j] = 1 / L[j][j]
+                const double w = s_rdiag[j];
+                const double2* row = reinterpret_cast<const double2*>(&M[j * LP + i0]);
+                const double2 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+                acc[0] = w * v0.x; acc[1] = w * v0.y; acc[2] = w * v1.x; acc[3] = w * v1.y;
+                acc[4] = w * v2.x; acc[5] = w * v2.y; acc[6] = w * v3.x; acc[7] = w * v3.y;
+            }
+#pragma unroll 4
+            for (int k = j + 1; k < i0; ++k) {
+                const double w = M[k * LP + j];
+                const double2* row = reinterpret_cast<const double2*>(&M[k * LP + i0]);
+                const double2 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+                acc[0] = fma(w, v0.x, acc[0]); acc[1] = fma(w, v0.y, acc[1]);
+                acc[2] = fma(w, v1.x, acc[2]); acc[3] = fma(w, v1.y, acc[3]);
+                acc[4] = fma(w, v2.x, acc[4]); acc[5] = fma(w, v2.y, acc[5]);
+                acc[6] = fma(w, v3.x, acc[6]); acc[7] = fma(w, v3.y, acc[7]);
+            }
         }
-        __syncthreads();
-        if (i < NB) S[i * LEAF_PITCH + j] = -acc * wjj;
-        if (tid == 0) S[j * LEAF_PITCH + j] = wjj;
-        __syncthreads();
+        double wv[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int row = i0 + r;
+            double w = 0.0;
+            if (row == j) w = s_rdiag[j];
+            else if (row > j) {
+                double sres = acc[r];
+#pragma unroll
+                for (int r2 = 0; r2 < r; ++r2)
+                    if (i0 + r2 >= j) sres = fma(M[(i0 + r2) * LP + row], wv[r2], sres);
+                w = -sres * s_rdiag[row];
+                M[row * LP + j] = w;
+            }
+            wv[r] = w;
+        }
     }
-    for (int e = tid; e < NB * NB; e += 256) {
+    __syncthreads();
+    for (int e = i; e < NB * NB; e += LEAF_THREADS) {
         const int r = e >> 7, c = e & 127;
-        Wblk[(size_t)r * ld + c] = S[r * LEAF_PITCH + c];
+        Wblk[(size_t)r * ld + c] = (c < r) ? M[r * LP + c] : (c == r ? s_rdiag[r] : 0.0);
     }
 }
 
@@ -252,7 +342,7 @@ int dqgp_solver_create(int n, dqgp_solver** out) {
 
     e = cudaMalloc(&s->d_tasks, sizeof(GemmTask) * tasks.size());
     if (e == cudaSuccess) e = cudaMemcpy(s->d_tasks, tasks.data(), sizeof(GemmTask) * tasks.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM_V2);
     if (e != cudaSuccess) { dqgp_solver_destroy(s); return cuda_fail(e, "dqgp_solver_create (task table)"); }
     int rc = gemm_init();
     if (rc) { dqgp_solver_destroy(s); return rc; }
@@ -282,7 +372,7 @@ int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, dou
     if (np != s->n) pad_identity_kernel<<<np, 256, 0, st>>>(s->A, s->n, np, ld);
     DQGP_LAUNCH_CHECK("pad kernels");
     for (int k = 0; k < nblk; ++k) {
-        potrf_leaf_kernel<<<1, 256, LEAF_SMEM, st>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
+        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, st>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
         DQGP_LAUNCH_CHECK("potrf_leaf_kernel");
         if (k + 1 < nblk) {
             int rc = launch_gemm_group(s->d_tasks + s->trsm[k].first, s->trsm[k].count, s->trsm[k].tiles, st);

@@ -8,6 +8,8 @@
 // fixed order, so the result is bit-reproducible run to run (the reference rounds it to 4 decimals).
 // Bound: FP64 pipe (3m + outer-kernel flops per entry); HBM traffic is one read of A^-1.
 #include "pairwise.cuh"
+#include <cstdlib>
+#include "fastmath.cuh"
 
 namespace dqgp {
 
@@ -79,6 +81,173 @@ __global__ void __launch_bounds__(PW_THREADS) grad_projected_kernel(const double
         }
         block_commit(acc, s_red, partial + (size_t)blockIdx.x * P + i);
     }
+}
+
+// ---- v2: Gram-identity formulation on the DMMA pipe ---------------------------------------------------------------
+// -gamma*||f-g||^2 = 2*gamma*f.g - gamma*||f||^2 - gamma*||g||^2: the accumulator of an 8x8 DMMA block is
+// initialised with the (pre-scaled) norms, the row operand is scaled by 2*gamma at fragment load, and m/4
+// DMMA.8x8x4 steps leave -gamma*d^2 in the accumulator, which goes straight into fast_exp.  Per entry that
+// is 1 DADD + m MACs + 16 (exp) + 1 DFMA (contraction with B) on the FP64 pipe instead of 2m + 23 + 1 for the
+// direct-difference form (the absolute error of d^2 is ~1e-15, harmless for exp/Matern/ExpSine outer kernels;
+// the unshifted Gram that is *written* keeps direct differences).  CTA = 64x64 tile, 8 warps as 4x2, warp tile
+// 16x32 = 2x4 DMMA blocks; B stays in registers for all 2P sets; feature tiles double-buffered with cp.async.
+constexpr int G2_PITCH = 36;                       // doubles per staged sample row: = 4 (mod 16) -> conflict-free fragments
+constexpr int G2_STAGE_DOUBLES = 2 * PW_TILE * G2_PITCH + 2 * PW_TILE;
+constexpr size_t G2_SMEM = sizeof(double) * 2 * G2_STAGE_DOUBLES;
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+
+__device__ __forceinline__ void g2_stage(double* buf, const double* __restrict__ Fs, const double* __restrict__ Ns, int row0,
+                                         int col0, int n, int m) {
+    double* Fr = buf;
+    double* Fc = buf + PW_TILE * G2_PITCH;
+    double* nr = buf + 2 * PW_TILE * G2_PITCH;
+    for (int e = threadIdx.x; e < PW_TILE * m; e += PW_THREADS) {
+        const int r = e / m, k = e - r * m;
+        cp_async8(&Fr[r * G2_PITCH + k], &Fs[(size_t)min(row0 + r, n - 1) * m + k]);
+        cp_async8(&Fc[r * G2_PITCH + k], &Fs[(size_t)min(col0 + r, n - 1) * m + k]);
+    }
+    if (threadIdx.x < PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(row0 + threadIdx.x, n - 1)]);
+    else if (threadIdx.x < 2 * PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(col0 + threadIdx.x - PW_TILE, n - 1)]);
+}
+
+template <int OUTER>
+__device__ __forceinline__ double outer_from_neg_gd2(double v, const OuterHyp& h) {
+    // v = -gamma_eff * d^2 (gamma_eff = gamma for the Gaussian, 1 otherwise)
+    if (OUTER == DQGP_OUTER_GAUSSIAN) {
+        return fast_exp(fmax(v, -700.0));
+    } else if (OUTER == DQGP_OUTER_MATERN15) {
+        const double k = sqrt(fmax(-v, 0.0)) * h.a * 1.7320508075688772;
+        return (1.0 + k) * fast_exp(fmax(-k, -700.0));
+    } else {
+        const double sn = sin(sqrt(fmax(-v, 0.0)) * h.b) * h.a;
+        return fast_exp(fmax(-2.0 * (sn * sn), -700.0));
+    }
+}
+
+template <int OUTER>
+__global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(const double* __restrict__ Ainv, int ld,
+                                                                           const double* __restrict__ alpha,
+                                                                           const double* __restrict__ F,
+                                                                           const double* __restrict__ Nrm, int n, int m, int P,
+                                                                           OuterHyp hyp, double* __restrict__ partial) {
+    extern __shared__ __align__(16) double g2_smem[];
+    __shared__ double s_red[2][PW_THREADS / 32];
+    int bi, bj;
+    tile_from_index(blockIdx.x, bi, bj);
+    const int row0 = bi * PW_TILE, col0 = bj * PW_TILE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wr = warp >> 1, wc = warp & 1, g = lane >> 2, t = lane & 3;
+    const int ksteps = (m + 3) >> 2;
+    const double gam = (OUTER == DQGP_OUTER_GAUSSIAN) ? hyp.a : 1.0;
+    const double a_scale = 2.0 * gam;
+
+    // zero the k-padding columns of both stages once (cp.async never writes them)
+    for (int e = threadIdx.x; e < 2 * 2 * PW_TILE * (G2_PITCH - m); e += PW_THREADS) {
+        const int per = G2_PITCH - m;
+        const int row = e / per, k = m + (e - row * per);          // row in [0, 4*64): stage x operand x sample
+        const int stage = row / (2 * PW_TILE), rr = row - stage * 2 * PW_TILE;
+        g2_smem[stage * G2_STAGE_DOUBLES + rr * G2_PITCH + k] = 0.0;
+    }
+
+    // B = weight * (A^-1 - alpha alpha^T) for this lane's 16 entries; zero outside the matrix and on the diagonal
+    double br[2][4][2];
+    const double weight = (bi == bj) ? 1.0 : 2.0;
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) {
+        const int r = row0 + wr * 16 + rb * 8 + g;
+        const double ar = (r < n) ? alpha[r] : 0.0;
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            const int c = col0 + wc * 32 + cb * 8 + 2 * t;
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                br[rb][cb][e] = (r < n && c + e < n && r != c + e) ? weight * (Ainv[(size_t)r * ld + c + e] - ar * alpha[c + e]) : 0.0;
+        }
+    }
+
+    const size_t set_stride = (size_t)n * m;
+    const int T = 2 * P;
+    g2_stage(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m);
+    cp_async_commit();
+    double pplus = 0.0, pminus = 0.0;
+    for (int tt = 0; tt < T; ++tt) {
+        cp_async_wait<0>();
+        __syncthreads();
+        if (tt >= 2 && (tt & 1) == 0 && threadIdx.x == 0) {
+            const int i = (tt >> 1) - 1;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < PW_THREADS / 32; ++w) s += s_red[i & 1][w];
+            partial[(size_t)blockIdx.x * P + i] = s;
+        }
+        if (tt + 1 < T) {
+            g2_stage(g2_smem + ((tt + 1) & 1) * G2_STAGE_DOUBLES, F + (size_t)(tt + 2) * set_stride, Nrm + (size_t)(tt + 2) * n, row0, col0, n, m);
+        }
+        cp_async_commit();
+        const double* buf = g2_smem + (tt & 1) * G2_STAGE_DOUBLES;
+        const double* Fr = buf + (wr * 16 + g) * G2_PITCH + t;
+        const double* Fc = buf + PW_TILE * G2_PITCH + (wc * 32 + g) * G2_PITCH + t;
+        const double* nr = buf + 2 * PW_TILE * G2_PITCH;
+        double c[2][4][2];
+        {
+            const double n0 = -gam * nr[wr * 16 + g], n1 = -gam * nr[wr * 16 + 8 + g];
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                const double2 nc = *reinterpret_cast<const double2*>(&nr[PW_TILE + wc * 32 + cb * 8 + 2 * t]);
+                const double m0 = -gam * nc.x, m1 = -gam * nc.y;
+                c[0][cb][0] = n0 + m0; c[0][cb][1] = n0 + m1;
+                c[1][cb][0] = n1 + m0; c[1][cb][1] = n1 + m1;
+            }
+        }
+#pragma unroll 2
+        for (int kk = 0; kk < ksteps; ++kk) {
+            const double a0 = a_scale * Fr[kk * 4], a1 = a_scale * Fr[8 * G2_PITCH + kk * 4];
+            double b[4];
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) b[cb] = Fc[cb * 8 * G2_PITCH + kk * 4];
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                dmma884(c[0][cb][0], c[0][cb][1], a0, b[cb]);
+                dmma884(c[1][cb][0], c[1][cb][1], a1, b[cb]);
+            }
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) part = fma(br[rb][cb][e], outer_from_neg_gd2<OUTER>(c[rb][cb][e], hyp), part);
+        if (tt & 1) {
+            pminus = part;
+            double v = warp_sum(pplus - pminus);
+            if (lane == 0) s_red[(tt >> 1) & 1][warp] = v;
+        } else {
+            pplus = part;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int i = P - 1;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < PW_THREADS / 32; ++w) s += s_red[i & 1][w];
+        partial[(size_t)blockIdx.x * P + i] = s;
+    }
+}
+
+// squared norms of every feature row: Nrm[s*n + j] = sum_k F[s][j][k]^2 (one warp per 4 rows)
+__global__ void feature_norms_kernel(const double* __restrict__ F, long long rows, int m, double* __restrict__ Nrm) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const double* f = F + row * m;
+    double acc = 0.0;
+    for (int k = 0; k < m; ++k) acc = fma(f[k], f[k], acc);
+    Nrm[row] = acc;
 }
 
 constexpr int FID_KC_G = 16;
@@ -177,7 +346,8 @@ extern "C" {
 
 size_t dqgp_grad_workspace_bytes(int n, int P) {
     if (n <= 0 || P <= 0) return 0;
-    return sizeof(double) * (size_t)dqgp::grad_tiles(n) * (size_t)P;
+    // partial sums [tiles][P] followed by the squared feature norms [(2P+1)][n] of the DMMA formulation
+    return sizeof(double) * ((size_t)dqgp::grad_tiles(n) * (size_t)P + (size_t)(2 * P + 1) * (size_t)n);
 }
 
 int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, int ld, const double* d_alpha, const double* d_F,
@@ -190,10 +360,32 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
     const int tiles = grad_tiles(n);
     cudaStream_t st = as_stream(stream);
     double* partial = static_cast<double*>(d_work);
-    switch (outer) {
-        case DQGP_OUTER_GAUSSIAN: grad_projected_kernel<DQGP_OUTER_GAUSSIAN><<<tiles, PW_THREADS, 0, st>>>(d_Ainv, ld, d_alpha, d_F, n, m, P, hyp, partial); break;
-        case DQGP_OUTER_MATERN15: grad_projected_kernel<DQGP_OUTER_MATERN15><<<tiles, PW_THREADS, 0, st>>>(d_Ainv, ld, d_alpha, d_F, n, m, P, hyp, partial); break;
-        default: grad_projected_kernel<DQGP_OUTER_EXPSINE2><<<tiles, PW_THREADS, 0, st>>>(d_Ainv, ld, d_alpha, d_F, n, m, P, hyp, partial); break;
+    double* norms = partial + (size_t)tiles * P;
+    static const bool use_direct = getenv("DQGP_GRAD_DIRECT") != nullptr;   // v1 direct-difference kernel, kept for A/B checks
+    if (use_direct) {
+        switch (outer) {
+            case DQGP_OUTER_GAUSSIAN: grad_projected_kernel<DQGP_OUTER_GAUSSIAN><<<tiles, PW_THREADS, 0, st>>>(d_Ainv, ld, d_alpha, d_F, n, m, P, hyp, partial); break;
+            case DQGP_OUTER_MATERN15: grad_projected_kernel<DQGP_OUTER_MATERN15><<<tiles, PW_THREADS, 0, st>>>(d_Ainv, ld, d_alpha, d_F, n, m, P, hyp, partial); break;
+            default: grad_projected_kernel<DQGP_OUTER_EXPSINE2><<<tiles, PW_THREADS, 0, st>>>(d_Ainv, ld, d_alpha, d_F, n, m, P, hyp, partial); break;
+        }
+    } else {
+        const long long rows = (long long)(2 * P + 1) * n;
+        feature_norms_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d_F, rows, m, norms);
+#define DQGP_G2(OUT)                                                                                                         \
+    do {                                                                                                                     \
+        static bool attr_done = false;                                                                                       \
+        if (!attr_done) {                                                                                                    \
+            DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
+            attr_done = true;                                                                                                \
+        }                                                                                                                    \
+        grad_projected_dmma_kernel<OUT><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+    } while (0)
+        switch (outer) {
+            case DQGP_OUTER_GAUSSIAN: DQGP_G2(DQGP_OUTER_GAUSSIAN); break;
+            case DQGP_OUTER_MATERN15: DQGP_G2(DQGP_OUTER_MATERN15); break;
+            default: DQGP_G2(DQGP_OUTER_EXPSINE2); break;
+        }
+#undef DQGP_G2
     }
     DQGP_LAUNCH_CHECK("grad_projected_kernel");
     grad_reduce_kernel<<<P, 256, 0, st>>>(partial, tiles, P, 0.5 / (2.0 * h), d_grad);
