@@ -110,6 +110,83 @@ static void build(dqgp_circuit& c) {
     }
 }
 
+// Greedy regrouping of the gate list into register-blocked passes.  A gate joins the current pass if its target
+// is (or can still become) one of the <= 3 block qubits and none of its qubits is touched by a gate that was
+// skipped earlier in program order (gates on disjoint qubits commute, so pulling it forward is exact).
+static void build_plan(dqgp_circuit& c) {
+    const int n = (int)c.gates.size();
+    std::vector<char> done(n, 0);
+    std::vector<std::vector<int>> fused;   // constituent gates of every SV_U2, in application order
+    int remaining = n;
+    const int bmax = c.q < 3 ? c.q : 3;
+    while (remaining > 0) {
+        SvPass pass;
+        pass.nq = 0; pass.q[0] = pass.q[1] = pass.q[2] = -1;
+        pass.op_begin = (int)c.ops.size();
+        unsigned blocked = 0;                  // qubits of skipped gates
+        std::vector<int> members;
+        for (int g = 0; g < n; ++g) {
+            if (done[g]) continue;
+            const dqgp_gate& gt = c.gates[g];
+            const bool two = gt.kind >= DQGP_G_CX;
+            const int tgt = two ? gt.q1 : gt.q0;
+            const unsigned qs = (1u << tgt) | (two ? (1u << gt.q0) : 0u);
+            bool in_block = false;
+            for (int k = 0; k < pass.nq; ++k) in_block |= (pass.q[k] == tgt);
+            if ((qs & blocked) == 0 && (in_block || pass.nq < bmax)) {
+                if (!in_block) pass.q[pass.nq++] = tgt;
+                members.push_back(g);
+                done[g] = 1;
+                --remaining;
+            } else {
+                blocked |= qs;
+            }
+        }
+        // sort block qubits ascending and express the ops in local bits, fusing runs of 1-qubit gates per qubit
+        for (int a = 0; a < pass.nq; ++a)
+            for (int b = a + 1; b < pass.nq; ++b)
+                if (pass.q[b] < pass.q[a]) { int t = pass.q[a]; pass.q[a] = pass.q[b]; pass.q[b] = t; }
+        auto local_of = [&](int qubit) { for (int k = 0; k < pass.nq; ++k) if (pass.q[k] == qubit) return k; return -1; };
+        int open_mat[3] = {-1, -1, -1};          // per block qubit: U2 that can still absorb gates
+        for (int g : members) {
+            const dqgp_gate& gt = c.gates[g];
+            const bool two = gt.kind >= DQGP_G_CX;
+            if (!two) {
+                const int lb = local_of(gt.q0);
+                if (open_mat[lb] < 0) {
+                    SvOp op;
+                    op.kind = SV_U2; op.lbit = (int8_t)lb; op.cloc = -1; op.cq = -1; op.pad = 0;
+                    op.idx = (int16_t)fused.size();
+                    open_mat[lb] = (int)fused.size();
+                    fused.emplace_back();
+                    c.ops.push_back(op);
+                }
+                fused[open_mat[lb]].push_back(g);
+            } else {
+                SvOp op;
+                op.kind = (int8_t)(gt.kind == DQGP_G_CX ? SV_CX : SV_CRZ);
+                op.lbit = (int8_t)local_of(gt.q1);
+                op.cloc = (int8_t)local_of(gt.q0);
+                op.cq = (int8_t)(op.cloc < 0 ? gt.q0 : -1);
+                op.idx = (int16_t)g;
+                op.pad = 0;
+                c.ops.push_back(op);
+                open_mat[op.lbit] = -1;                       // later gates on the target must stay behind this op
+                if (op.cloc >= 0) open_mat[op.cloc] = -1;     // ... and so must gates on the control
+            }
+        }
+        pass.op_end = (int)c.ops.size();
+        c.passes.push_back(pass);
+    }
+    for (auto& f : fused) {
+        SvMat m;
+        m.g_begin = (int)c.mat_gates.size();
+        for (int g : f) c.mat_gates.push_back(g);
+        m.g_end = (int)c.mat_gates.size();
+        c.mats.push_back(m);
+    }
+}
+
 static std::mutex g_upload_mutex;
 int circuit_on_device(const dqgp_circuit* cc) {
     dqgp_circuit* c = const_cast<dqgp_circuit*>(cc);
@@ -120,6 +197,14 @@ int circuit_on_device(const dqgp_circuit* cc) {
     DQGP_REQUIRE(c->d_gates == nullptr, "circuit handle was created for device %d but used on device %d", c->device, dev);
     DQGP_CUDA(cudaMalloc(&c->d_gates, sizeof(dqgp_gate) * c->gates.size()));
     DQGP_CUDA(cudaMemcpy(c->d_gates, c->gates.data(), sizeof(dqgp_gate) * c->gates.size(), cudaMemcpyHostToDevice));
+    DQGP_CUDA(cudaMalloc(&c->d_passes, sizeof(SvPass) * c->passes.size()));
+    DQGP_CUDA(cudaMemcpy(c->d_passes, c->passes.data(), sizeof(SvPass) * c->passes.size(), cudaMemcpyHostToDevice));
+    DQGP_CUDA(cudaMalloc(&c->d_ops, sizeof(SvOp) * c->ops.size()));
+    DQGP_CUDA(cudaMemcpy(c->d_ops, c->ops.data(), sizeof(SvOp) * c->ops.size(), cudaMemcpyHostToDevice));
+    DQGP_CUDA(cudaMalloc(&c->d_mats, sizeof(SvMat) * (c->mats.size() + 1)));
+    DQGP_CUDA(cudaMemcpy(c->d_mats, c->mats.data(), sizeof(SvMat) * c->mats.size(), cudaMemcpyHostToDevice));
+    DQGP_CUDA(cudaMalloc(&c->d_mat_gates, sizeof(int) * (c->mat_gates.size() + 1)));
+    DQGP_CUDA(cudaMemcpy(c->d_mat_gates, c->mat_gates.data(), sizeof(int) * c->mat_gates.size(), cudaMemcpyHostToDevice));
     c->device = dev;
     return 0;
 }
@@ -141,8 +226,9 @@ int dqgp_circuit_create(int encoding, int num_qubits, int num_features, int num_
     dqgp_circuit* c = new dqgp_circuit();
     c->encoding = encoding; c->q = num_qubits; c->d = num_features; c->layers = num_layers;
     c->P = dqgp::count_parameters(encoding, num_qubits, num_layers);
-    c->uses_acos = false; c->d_gates = nullptr;
+    c->uses_acos = false; c->d_gates = nullptr; c->d_passes = nullptr; c->d_ops = nullptr; c->d_mats = nullptr; c->d_mat_gates = nullptr;
     dqgp::build(*c);
+    dqgp::build_plan(*c);
     c->device = -1;
     *out = c;   // the device copy of the program is made on first use (dqgp::circuit_on_device)
     return 0;
@@ -150,10 +236,15 @@ int dqgp_circuit_create(int encoding, int num_qubits, int num_features, int num_
 void dqgp_circuit_destroy(dqgp_circuit* c) {
     if (!c) return;
     if (c->d_gates) cudaFree(c->d_gates);
+    if (c->d_passes) cudaFree(c->d_passes);
+    if (c->d_ops) cudaFree(c->d_ops);
+    if (c->d_mats) cudaFree(c->d_mats);
+    if (c->d_mat_gates) cudaFree(c->d_mat_gates);
     delete c;
 }
 int dqgp_circuit_num_parameters(const dqgp_circuit* c) { return c ? c->P : -1; }
 int dqgp_circuit_num_gates(const dqgp_circuit* c) { return c ? (int)c->gates.size() : -1; }
+int dqgp_circuit_num_passes(const dqgp_circuit* c) { return c ? (int)c->passes.size() : -1; }
 int dqgp_circuit_describe(const dqgp_circuit* c, dqgp_gate* h_out, int capacity) {
     DQGP_REQUIRE(c && h_out, "dqgp_circuit_describe: NULL argument");
     int n = (int)c->gates.size();

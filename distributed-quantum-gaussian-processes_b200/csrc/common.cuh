@@ -59,10 +59,41 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 }  // namespace dqgp
 
+// Execution plan of the statevector kernel: the gate list regrouped into passes over <= 3 "block" qubits.
+// Within a pass every op's TARGET is a block qubit, so a lane holding the 2^b amplitudes of one block in
+// registers applies all of them back to back; controls may be any qubit (read-only index bits).  Runs of
+// single-qubit gates on one qubit are fused into one general 2x2 unitary (SV_U2) whose matrix is composed
+// per state from the cos/sin table (its constituents are mat_gates[g_begin, g_end) in application order).
+enum { SV_U2 = 0, SV_CX = 1, SV_CRZ = 2 };
+struct SvOp {
+    int8_t kind;    // SV_*
+    int8_t lbit;    // target as a local bit of the pass block (0..2)
+    int8_t cloc;    // control as a local bit of the block, or -1
+    int8_t cq;      // control as a global qubit (when not in the block), or -1
+    int16_t idx;    // SV_U2: matrix index; SV_CRZ: original gate index (selects the cos/sin pair)
+    int16_t pad;
+};
+struct SvMat {
+    int g_begin, g_end;   // range in mat_gates
+};
+struct SvPass {
+    int nq;         // block size 1..3
+    int q[3];       // block qubits, ascending
+    int op_begin, op_end;
+};
+
 struct dqgp_circuit {
     int encoding, q, d, layers, P;
     bool uses_acos;
     std::vector<dqgp_gate> gates;  // host copy
-    dqgp_gate* d_gates;            // device copy
+    std::vector<SvPass> passes;
+    std::vector<SvOp> ops;
+    std::vector<SvMat> mats;
+    std::vector<int> mat_gates;
+    dqgp_gate* d_gates;            // device copies
+    SvPass* d_passes;
+    SvOp* d_ops;
+    SvMat* d_mats;
+    int* d_mat_gates;
     int device;
 };

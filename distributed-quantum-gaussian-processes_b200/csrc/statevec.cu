@@ -3,13 +3,17 @@
 // Replaces what squlearn does behind q_kernel.evaluate for every sample and parameter set
 // (reference call site agent_riemannian.py:118; S = 2P+1 sets built at :245-256).
 //
-// Mapping: one warp owns one state (2^q complex128 amplitudes in shared memory, never in HBM); for
-// q <= 5 a warp is split into 32/2^(q-1) lane groups, one state per group, so no lane idles.  Each lane
-// owns 2^(q-1)/group amplitude pairs per gate; gates are applied in place with only __syncwarp between
-// them (no block barrier).  All sin/cos of a state's gate angles are computed once, cooperatively, into
-// a per-state table (a gate's angle is shared by all 2^(q-1) pairs), and arccos(x) once per sample.
-// The epilogue reduces <X_k>,<Y_k>,<Z_k> with group-local shuffles, or streams the state to HBM for the
-// fidelity kernel.  Work is a warp-granular grid-stride loop over S*n states on a grid sized to the SMs.
+// Mapping: one warp owns one state (2^q complex128 amplitudes in shared memory, never in HBM); for q <= 7 a
+// warp is split into lane groups, one state per group, so no lane idles.  The gate list is executed as
+// REGISTER-BLOCKED PASSES (plan built on the host, circuit.cu): a pass names <= 3 block qubits; a lane loads the
+// 2^3 amplitudes of one block into registers, applies every gate of the pass whose target is a block qubit
+// (runs of rotations / H on one qubit fused into a general 2x2 unitary composed per state; CX / CRZ with the
+// control read from the index or from the block) and stores them back — one
+// shared-memory round trip for ~15 gates instead of one per gate (v1: 59 round trips for config 4, 16.6 ms;
+// ncu profiles/r01_v1_statevec: LSU-wavefront bound, 27% bank conflicts).  All sin/cos of a state's gate
+// angles are computed once, cooperatively, into a per-state table; arccos(x) once per sample.  Only
+// __syncwarp separates passes.  The epilogue reduces <X_k>,<Y_k>,<Z_k> three qubits at a time from registers
+// with group-local shuffles, or streams the state to HBM for the fidelity kernel.
 #include "common.cuh"
 
 namespace dqgp {
@@ -19,36 +23,198 @@ __device__ __forceinline__ int insert_zero_bit(int k, int t) {
     return ((k >> t) << (t + 1)) | lo;
 }
 
+// Shared-memory placement of amplitude i: XOR the low three index bits with bits 3..5.  A lane's register block
+// is 8 amplitudes; when the block qubits are {0,1,2} consecutive lanes would otherwise sit 128 bytes apart and
+// every LDS.128 of a quarter-warp would hit the same four banks (32-way conflict, measured: v2 without the
+// swizzle was still 12.9 ms).  With it those accesses, and the {3,4,5} blocks, are conflict-free.
+__device__ __forceinline__ int sv_phys(int i) { return i ^ ((i >> 3) & 7); }
+
 template <int Q>
 struct SvGeom {
     static constexpr int DIM = 1 << Q;
-    static constexpr int PAIRS = (Q == 0) ? 1 : (DIM / 2);
-    static constexpr int GROUP = PAIRS >= 32 ? 32 : (PAIRS < 1 ? 1 : PAIRS);  // lanes per state
-    static constexpr int SPW = 32 / GROUP;                                     // states per warp
-    static constexpr int PPL = PAIRS / GROUP;                                  // pairs per lane
+    static constexpr int BMAX = Q < 3 ? Q : 3;
+    static constexpr int GROUPS = DIM >> BMAX;                    // register blocks per state (full-size pass)
+    static constexpr int LPS = GROUPS >= 32 ? 32 : GROUPS;        // lanes per state
+    static constexpr int SPW = 32 / LPS;                          // states per warp
 };
 
+// ---- ops on the register block, target = local bit L (compile time) ------------------------------------------
+// general 2x2 complex unitary u = {u00,u01,u10,u11} on every pair along bit L: 16 FP64 instructions per pair
+template <int N, int L>
+__device__ __forceinline__ void apply_u2(double2 (&r)[N], const double2 u00, const double2 u01, const double2 u10, const double2 u11) {
+    constexpr int BIT = 1 << L;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        if (j & BIT) continue;
+        const double2 a = r[j], b = r[j | BIT];
+        double2 na, nb;
+        na.x = fma(u01.x, b.x, fma(-u01.y, b.y, fma(u00.x, a.x, -u00.y * a.y)));
+        na.y = fma(u01.x, b.y, fma(u01.y, b.x, fma(u00.x, a.y, u00.y * a.x)));
+        nb.x = fma(u11.x, b.x, fma(-u11.y, b.y, fma(u10.x, a.x, -u10.y * a.y)));
+        nb.y = fma(u11.x, b.y, fma(u11.y, b.x, fma(u10.x, a.y, u10.y * a.x)));
+        r[j] = na;
+        r[j | BIT] = nb;
+    }
+}
+// CX (swap) / CRZ (phases e^{-+ i theta/2}) on the pairs whose control bit is set
+template <int N, int L>
+__device__ __forceinline__ void apply_controlled(double2 (&r)[N], int kind, int cloc, bool ext, double c, double s) {
+    constexpr int BIT = 1 << L;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        if (j & BIT) continue;
+        const bool on = cloc >= 0 ? (((j >> cloc) & 1) != 0) : ext;
+        const double2 a = r[j], b = r[j | BIT];
+        double2 na, nb;
+        if (kind == SV_CX) {
+            na = b;
+            nb = a;
+        } else {
+            na = make_double2(fma(c, a.x, s * a.y), fma(c, a.y, -s * a.x));
+            nb = make_double2(fma(c, b.x, -s * b.y), fma(c, b.y, s * b.x));
+        }
+        r[j] = on ? na : a;
+        r[j | BIT] = on ? nb : b;
+    }
+}
+
+template <int N, int L>
+__device__ __forceinline__ void apply_op(double2 (&r)[N], const SvOp op, int base, const double2* __restrict__ mats,
+                                         const double2* __restrict__ trig) {
+    if (op.kind == SV_U2) {
+        const double2* u = mats + 4 * op.idx;
+        apply_u2<N, L>(r, u[0], u[1], u[2], u[3]);
+    } else {
+        const bool ext = (op.cq >= 0) ? (((base >> op.cq) & 1) != 0) : false;
+        const double2 cs = (op.kind == SV_CRZ) ? trig[op.idx] : make_double2(1.0, 0.0);
+        apply_controlled<N, L>(r, op.kind, op.cloc, ext, cs.x, cs.y);
+    }
+}
+
+template <int B>
+__device__ __forceinline__ void run_pass(double2* __restrict__ amp, const SvPass& ps, const SvOp* __restrict__ ops,
+                                         const double2* __restrict__ mats, const double2* __restrict__ trig, int lig, int lps,
+                                         int groups) {
+    constexpr int N = 1 << B;
+    const int q0 = ps.q[0], q1 = ps.q[1], q2 = ps.q[2];
+    int off[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) off[j] = ((j & 1) ? (1 << q0) : 0) + ((B > 1 && (j & 2)) ? (1 << q1) : 0) + ((B > 2 && (j & 4)) ? (1 << q2) : 0);
+    for (int gi = lig; gi < groups; gi += lps) {
+        int base = insert_zero_bit(gi, q0);
+        if (B > 1) base = insert_zero_bit(base, q1);
+        if (B > 2) base = insert_zero_bit(base, q2);
+        double2 r[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) r[j] = amp[sv_phys(base + off[j])];
+#pragma unroll 1
+        for (int o = ps.op_begin; o < ps.op_end; ++o) {
+            const SvOp op = ops[o];
+            if (op.lbit == 0) apply_op<N, 0>(r, op, base, mats, trig);
+            else if (B > 1 && op.lbit == 1) apply_op<N, (B > 1 ? 1 : 0)>(r, op, base, mats, trig);
+            else if (B > 2) apply_op<N, (B > 2 ? 2 : 0)>(r, op, base, mats, trig);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) amp[sv_phys(base + off[j])] = r[j];
+    }
+}
+
+// matrix of one original gate from its (cos, sin) of the half angle
+__device__ __forceinline__ void gate_matrix(int kind, double c, double s, double2 (&g)[4]) {
+    const double r2 = 0.70710678118654752440;
+    switch (kind) {
+        case DQGP_G_H: g[0] = make_double2(r2, 0); g[1] = make_double2(r2, 0); g[2] = make_double2(r2, 0); g[3] = make_double2(-r2, 0); break;
+        case DQGP_G_RX: g[0] = make_double2(c, 0); g[1] = make_double2(0, -s); g[2] = make_double2(0, -s); g[3] = make_double2(c, 0); break;
+        case DQGP_G_RY: g[0] = make_double2(c, 0); g[1] = make_double2(-s, 0); g[2] = make_double2(s, 0); g[3] = make_double2(c, 0); break;
+        default: g[0] = make_double2(c, -s); g[1] = make_double2(0, 0); g[2] = make_double2(0, 0); g[3] = make_double2(c, s); break;   // RZ
+    }
+}
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+
+// <X>,<Y>,<Z> of qubits k0 .. k0+B-1 from register blocks; group-local shuffle reduction; lane 0 of the state writes
+template <int B, int Q>
+__device__ __forceinline__ void features_block(const double2* __restrict__ amp, int k0, int lig, int lps, bool live,
+                                               double* __restrict__ dst) {
+    constexpr int N = 1 << B;
+    const int groups = (1 << Q) >> B;
+    double fx[B], fy[B], fz[B];
+#pragma unroll
+    for (int l = 0; l < B; ++l) fx[l] = fy[l] = fz[l] = 0.0;
+    for (int gi = lig; gi < groups; gi += lps) {
+        int base = gi;
+#pragma unroll
+        for (int l = 0; l < B; ++l) base = insert_zero_bit(base, k0 + l);
+        double2 r[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            int o = 0;
+#pragma unroll
+            for (int l = 0; l < B; ++l) o += ((j >> l) & 1) << (k0 + l);
+            r[j] = amp[sv_phys(base + o)];
+        }
+#pragma unroll
+        for (int l = 0; l < B; ++l)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                if (j & (1 << l)) continue;
+                const double2 a = r[j], b = r[j | (1 << l)];
+                fx[l] += a.x * b.x + a.y * b.y;
+                fy[l] += a.x * b.y - a.y * b.x;
+                fz[l] += (a.x * a.x + a.y * a.y) - (b.x * b.x + b.y * b.y);
+            }
+    }
+#pragma unroll
+    for (int l = 0; l < B; ++l) {
+        for (int o = lps >> 1; o > 0; o >>= 1) {
+            fx[l] += __shfl_xor_sync(0xffffffffu, fx[l], o);
+            fy[l] += __shfl_xor_sync(0xffffffffu, fy[l], o);
+            fz[l] += __shfl_xor_sync(0xffffffffu, fz[l], o);
+        }
+        if (live && lig == 0) {
+            dst[k0 + l] = 2.0 * fx[l];
+            dst[Q + k0 + l] = 2.0 * fy[l];
+            dst[2 * Q + k0 + l] = fz[l];
+        }
+    }
+}
+
 template <int Q, bool WANT_STATES>
-__global__ void __launch_bounds__(128) statevec_kernel(const dqgp_gate* __restrict__ gates, int n_gates, int d, int P,
-                                                        int uses_acos, const double* __restrict__ X, int n,
-                                                        const double* __restrict__ Pm, int S, double* __restrict__ out) {
+__global__ void __launch_bounds__(128) statevec_kernel(const dqgp_gate* __restrict__ gates, int n_gates,
+                                                        const SvPass* __restrict__ passes, int n_passes,
+                                                        const SvOp* __restrict__ ops, const SvMat* __restrict__ mats,
+                                                        int n_mats, const int* __restrict__ mat_gates, int n_mat_gates, int d, int P,
+                                                        int uses_acos,
+                                                        const double* __restrict__ X, int n, const double* __restrict__ Pm,
+                                                        int S, double* __restrict__ out) {
     using G = SvGeom<Q>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // block layout: [gate program][per warp: SPW x (DIM double2 | n_gates double2 trig | d double acos)]
+    // block layout: [gate program][passes][ops][mats][mat_gates][per warp: SPW x (DIM amp | n_gates trig | n_mats x 4 u2 | d acos)]
+    const size_t gate_bytes = (sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15);
+    const size_t pass_bytes = (sizeof(SvPass) * n_passes + 15) & ~size_t(15);
+    const size_t op_bytes = (sizeof(SvOp) * n_gates + 15) & ~size_t(15);
+    const size_t mat_bytes = (sizeof(SvMat) * n_mats + sizeof(int) * n_mat_gates + 15) & ~size_t(15);
     dqgp_gate* s_gates = reinterpret_cast<dqgp_gate*>(smem_raw);
+    SvPass* s_passes = reinterpret_cast<SvPass*>(smem_raw + gate_bytes);
+    SvOp* s_ops = reinterpret_cast<SvOp*>(smem_raw + gate_bytes + pass_bytes);
+    SvMat* s_mats = reinterpret_cast<SvMat*>(smem_raw + gate_bytes + pass_bytes + op_bytes);
+    int* s_mat_gates = reinterpret_cast<int*>(s_mats + n_mats);
     const int warps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t gate_bytes = (sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15);
-    const size_t state_bytes = sizeof(double2) * G::DIM + sizeof(double2) * n_gates + ((sizeof(double) * d + 15) & ~size_t(15));
-    for (int i = threadIdx.x; i < n_gates; i += blockDim.x) s_gates[i] = gates[i];
+    const size_t state_bytes = sizeof(double2) * (G::DIM + n_gates + 4 * n_mats) + ((sizeof(double) * d + 15) & ~size_t(15));
+    for (int i = threadIdx.x; i < n_gates; i += blockDim.x) { s_gates[i] = gates[i]; s_ops[i] = ops[i]; }   // #ops <= #gates
+    for (int i = threadIdx.x; i < n_passes; i += blockDim.x) s_passes[i] = passes[i];
+    for (int i = threadIdx.x; i < n_mats; i += blockDim.x) s_mats[i] = mats[i];
+    for (int i = threadIdx.x; i < n_mat_gates; i += blockDim.x) s_mat_gates[i] = mat_gates[i];
     __syncthreads();
 
-    const int sub = lane / G::GROUP;   // which state of this warp
-    const int lig = lane % G::GROUP;   // lane in group
-    unsigned char* my = smem_raw + gate_bytes + state_bytes * (size_t(warp) * G::SPW + sub);
+    const int sub = lane / G::LPS;   // which state of this warp
+    const int lig = lane % G::LPS;   // lane in group
+    unsigned char* my = smem_raw + gate_bytes + pass_bytes + op_bytes + mat_bytes + state_bytes * (size_t(warp) * G::SPW + sub);
     double2* amp = reinterpret_cast<double2*>(my);
     double2* trig = amp + G::DIM;
-    double* acx = reinterpret_cast<double*>(trig + n_gates);
+    double2* u2 = trig + n_gates;
+    double* acx = reinterpret_cast<double*>(u2 + 4 * n_mats);
 
     const long long total = (long long)S * n;
     const long long n_groups = (total + G::SPW - 1) / G::SPW;
@@ -62,10 +228,10 @@ __global__ void __launch_bounds__(128) statevec_kernel(const dqgp_gate* __restri
         const double* p = Pm + (size_t)s * P;
 
         if (uses_acos) {
-            for (int f = lig; f < d; f += G::GROUP) acx[f] = acos(x[f]);
+            for (int f = lig; f < d; f += G::LPS) acx[f] = acos(x[f]);
             __syncwarp();
         }
-        for (int g = lig; g < n_gates; g += G::GROUP) {
+        for (int g = lig; g < n_gates; g += G::LPS) {
             const dqgp_gate gt = s_gates[g];
             if (gt.form == DQGP_A_NONE) continue;   // H, CX carry no angle
             double ang = 0.0;
@@ -81,85 +247,52 @@ __global__ void __launch_bounds__(128) statevec_kernel(const dqgp_gate* __restri
             sincos(0.5 * ang, &sn, &cs);
             trig[g] = make_double2(cs, sn);
         }
-        for (int i = lig; i < G::DIM; i += G::GROUP) amp[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
+        for (int i = lig; i < G::DIM; i += G::LPS) amp[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);   // sv_phys(0) == 0
+        __syncwarp();
+        // compose the fused 2x2 unitaries of this state: M = G_last ... G_first
+        for (int f = lig; f < n_mats; f += G::LPS) {
+            const SvMat mt = s_mats[f];
+            double2 mm[4];
+            {
+                const int g0 = s_mat_gates[mt.g_begin];
+                const double2 cs = trig[g0];
+                gate_matrix(s_gates[g0].kind, cs.x, cs.y, mm);
+            }
+            for (int e = mt.g_begin + 1; e < mt.g_end; ++e) {
+                const int g = s_mat_gates[e];
+                const double2 cs = trig[g];
+                double2 gg[4];
+                gate_matrix(s_gates[g].kind, cs.x, cs.y, gg);
+                const double2 n0 = cadd(cmul(gg[0], mm[0]), cmul(gg[1], mm[2]));
+                const double2 n1 = cadd(cmul(gg[0], mm[1]), cmul(gg[1], mm[3]));
+                const double2 n2 = cadd(cmul(gg[2], mm[0]), cmul(gg[3], mm[2]));
+                const double2 n3 = cadd(cmul(gg[2], mm[1]), cmul(gg[3], mm[3]));
+                mm[0] = n0; mm[1] = n1; mm[2] = n2; mm[3] = n3;
+            }
+            u2[4 * f + 0] = mm[0]; u2[4 * f + 1] = mm[1]; u2[4 * f + 2] = mm[2]; u2[4 * f + 3] = mm[3];
+        }
         __syncwarp();
 
-        for (int g = 0; g < n_gates; ++g) {
-            const dqgp_gate gt = s_gates[g];
-            const double2 cs = trig[g];
-            const double c = cs.x, sn = cs.y;
-            const int t = (gt.kind >= DQGP_G_CX) ? gt.q1 : gt.q0;
-            const int bit = 1 << t;
-            const int cbit = (gt.kind >= DQGP_G_CX) ? (1 << gt.q0) : 0;
-#pragma unroll
-            for (int r = 0; r < G::PPL; ++r) {
-                const int k = lig + G::GROUP * r;
-                const int i0 = insert_zero_bit(k, t), i1 = i0 | bit;
-                if (cbit && !(i0 & cbit)) continue;
-                const double2 a = amp[i0], b = amp[i1];
-                double2 na, nb;
-                switch (gt.kind) {
-                    case DQGP_G_H: {
-                        const double r2 = 0.70710678118654752440;
-                        na = make_double2((a.x + b.x) * r2, (a.y + b.y) * r2);
-                        nb = make_double2((a.x - b.x) * r2, (a.y - b.y) * r2);
-                        break;
-                    }
-                    case DQGP_G_RX:
-                        na = make_double2(c * a.x + sn * b.y, c * a.y - sn * b.x);
-                        nb = make_double2(sn * a.y + c * b.x, c * b.y - sn * a.x);
-                        break;
-                    case DQGP_G_RY:
-                        na = make_double2(c * a.x - sn * b.x, c * a.y - sn * b.y);
-                        nb = make_double2(sn * a.x + c * b.x, sn * a.y + c * b.y);
-                        break;
-                    case DQGP_G_RZ:
-                    case DQGP_G_CRZ:
-                        na = make_double2(c * a.x + sn * a.y, c * a.y - sn * a.x);
-                        nb = make_double2(c * b.x - sn * b.y, c * b.y + sn * b.x);
-                        break;
-                    default:  // CX
-                        na = b;
-                        nb = a;
-                        break;
-                }
-                amp[i0] = na;
-                amp[i1] = nb;
-            }
+        for (int ip = 0; ip < n_passes; ++ip) {
+            const SvPass ps = s_passes[ip];
+            if (ps.nq == 3) run_pass<(Q >= 3 ? 3 : 1)>(amp, ps, s_ops, u2, trig, lig, G::LPS, G::DIM >> 3);
+            else if (ps.nq == 2) run_pass<(Q >= 2 ? 2 : 1)>(amp, ps, s_ops, u2, trig, lig, G::LPS, G::DIM >> 2);
+            else run_pass<1>(amp, ps, s_ops, u2, trig, lig, G::LPS, G::DIM >> 1);
             __syncwarp();
         }
 
         if (WANT_STATES) {
             if (live) {
                 double2* dst = reinterpret_cast<double2*>(out) + (size_t)st * G::DIM;
-                for (int i = lig; i < G::DIM; i += G::GROUP) dst[i] = amp[i];
+                for (int i = lig; i < G::DIM; i += G::LPS) dst[i] = amp[sv_phys(i)];
             }
         } else {
             double* dst = out + (size_t)st * m;
+            constexpr int FULL = Q / 3, REM = Q % 3;
 #pragma unroll 1
-            for (int k = 0; k < Q; ++k) {
-                double fx = 0.0, fy = 0.0, fz = 0.0;
-#pragma unroll
-                for (int r = 0; r < G::PPL; ++r) {
-                    const int kk = lig + G::GROUP * r;
-                    const int i0 = insert_zero_bit(kk, k), i1 = i0 | (1 << k);
-                    const double2 a = amp[i0], b = amp[i1];
-                    fx += a.x * b.x + a.y * b.y;
-                    fy += a.x * b.y - a.y * b.x;
-                    fz += (a.x * a.x + a.y * a.y) - (b.x * b.x + b.y * b.y);
-                }
-#pragma unroll
-                for (int o = G::GROUP / 2; o > 0; o >>= 1) {
-                    fx += __shfl_xor_sync(0xffffffffu, fx, o);
-                    fy += __shfl_xor_sync(0xffffffffu, fy, o);
-                    fz += __shfl_xor_sync(0xffffffffu, fz, o);
-                }
-                if (live && lig == 0) {
-                    dst[k] = 2.0 * fx;
-                    dst[Q + k] = 2.0 * fy;
-                    dst[2 * Q + k] = fz;
-                }
-            }
+            for (int b = 0; b < FULL; ++b) features_block<(Q >= 3 ? 3 : 1), Q>(amp, 3 * b, lig, G::LPS, live, dst);
+            if (REM == 2) features_block<(Q >= 2 ? 2 : 1), Q>(amp, 3 * FULL, lig, G::LPS, live, dst);
+            if (REM == 1) features_block<1, Q>(amp, 3 * FULL, lig, G::LPS, live, dst);
         }
         __syncwarp();
     }
@@ -168,12 +301,17 @@ __global__ void __launch_bounds__(128) statevec_kernel(const dqgp_gate* __restri
 template <int Q, bool WANT_STATES>
 static int launch_sv(const dqgp_circuit* c, const double* X, int n, const double* Pm, int S, double* out, cudaStream_t st) {
     using G = SvGeom<Q>;
-    const int n_gates = (int)c->gates.size();
+    const int n_gates = (int)c->gates.size(), n_passes = (int)c->passes.size();
     const size_t gate_bytes = (sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15);
-    const size_t state_bytes = sizeof(double2) * G::DIM + sizeof(double2) * n_gates + ((sizeof(double) * c->d + 15) & ~size_t(15));
+    const size_t pass_bytes = (sizeof(SvPass) * n_passes + 15) & ~size_t(15);
+    const size_t op_bytes = (sizeof(SvOp) * n_gates + 15) & ~size_t(15);
+    const int n_mats = (int)c->mats.size(), n_mat_gates = (int)c->mat_gates.size();
+    const size_t mat_bytes = (sizeof(SvMat) * n_mats + sizeof(int) * n_mat_gates + 15) & ~size_t(15);
+    const size_t fixed = gate_bytes + pass_bytes + op_bytes + mat_bytes;
+    const size_t state_bytes = sizeof(double2) * (G::DIM + n_gates + 4 * n_mats) + ((sizeof(double) * c->d + 15) & ~size_t(15));
     int warps = 4;
-    while (warps > 1 && gate_bytes + state_bytes * G::SPW * warps > 100 * 1024) warps >>= 1;
-    const size_t smem = gate_bytes + state_bytes * G::SPW * warps;
+    while (warps > 1 && fixed + state_bytes * G::SPW * warps > 100 * 1024) warps >>= 1;
+    const size_t smem = fixed + state_bytes * G::SPW * warps;
     DQGP_REQUIRE(smem <= 227 * 1024, "statevector kernel needs %zu bytes of shared memory (q=%d, %d gates)", smem, Q, n_gates);
     auto kern = statevec_kernel<Q, WANT_STATES>;
     DQGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -186,7 +324,8 @@ static int launch_sv(const dqgp_circuit* c, const double* X, int n, const double
     const long long cap = (long long)sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) return 0;
-    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d, c->P, c->uses_acos ? 1 : 0, X, n, Pm, S, out);
+    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d_passes, n_passes, c->d_ops, c->d_mats, n_mats,
+                                                     c->d_mat_gates, n_mat_gates, c->d, c->P, c->uses_acos ? 1 : 0, X, n, Pm, S, out);
     DQGP_LAUNCH_CHECK("statevec_kernel");
     return 0;
 }

@@ -34,3 +34,22 @@ for _ in range(a.reps):
     torch.cuda.synchronize()
     print(f"step {e0.elapsed_time(e1):.2f} ms  nll {eng.d_nll[3].item():.6f}")
 eng.check_info()
+
+
+def timed(name, fn, reps=3):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"  {name:12s} {e0.elapsed_time(e1) / reps:8.3f} ms")
+    return e0.elapsed_time(e1) / reps
+
+
+timed("statevector", lambda: eng.simulate(z))
+g = timed("gram", eng.gram)
+timed("factor", lambda: (eng.gram(), eng.factor()))
+print(f"    (factor includes one gram: subtract {g:.3f})")
+timed("gradient", eng.gradient)
