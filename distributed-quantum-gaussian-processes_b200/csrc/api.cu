@@ -10,7 +10,7 @@ int dqgp_dgemm(int a_k_contig, int b_k_contig, int M, int N, int K, double alpha
                int ldb, double beta, double* d_C, int ldc, void* stream) {
     using namespace dqgp;
     DQGP_REQUIRE(d_A && d_B && d_C, "dqgp_dgemm: NULL argument");
-    DQGP_REQUIRE(M > 0 && N > 0 && K > 0 && M % GM_BM == 0 && N % GM_BN == 0 && K % GM_KC == 0,
+    DQGP_REQUIRE(M > 0 && N > 0 && K > 0 && M % GM_BM == 0 && N % 128 == 0 && K % GM_KC == 0,
                  "dqgp_dgemm: M,N must be multiples of 128 and K of 16 (got %d,%d,%d)", M, N, K);
     DQGP_REQUIRE(lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0, "dqgp_dgemm: leading dimensions must be even");
     DQGP_REQUIRE(((uintptr_t)d_A % 16 == 0) && ((uintptr_t)d_B % 16 == 0) && ((uintptr_t)d_C % 16 == 0), "dqgp_dgemm: pointers must be 16-byte aligned");

@@ -205,6 +205,18 @@ __global__ void pad_vector_kernel(const double* y, int n, int np, double* out, d
     if (i == 0) { *logdet = 0.0; *info = 0; }
 }
 
+// ---- copy the strictly-lower 128x128 blocks of src into dst (panels of L: T -> A) ---------------------------
+__global__ void copy_lower_blocks_kernel(const double* __restrict__ src, double* __restrict__ dst, int ld) {
+    const int rb = blockIdx.y + 1, cb = blockIdx.x;
+    if (cb >= rb) return;
+    const double2* s2 = reinterpret_cast<const double2*>(src + (size_t)rb * NB * ld + (size_t)cb * NB);
+    double2* d2 = reinterpret_cast<double2*>(dst + (size_t)rb * NB * ld + (size_t)cb * NB);
+    for (int e = threadIdx.x; e < NB * NB / 2; e += blockDim.x) {
+        const int r = e >> 6, c = e & 63;
+        d2[(size_t)r * (ld / 2) + c] = s2[(size_t)r * (ld / 2) + c];
+    }
+}
+
 // ---- w = W y (lower-triangular, one warp per row) --------------------------------------------------------
 __global__ void trmv_lower_kernel(const double* __restrict__ W, int np, int ld, const double* __restrict__ y, double* __restrict__ w) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -311,9 +323,11 @@ int dqgp_solver_create(int n, dqgp_solver** out) {
     // potrf steps
     for (int k = 0; k + 1 < nblk; ++k) {
         const int rest = np - (k + 1) * NB;
-        grp.push_back(make_task(at(s->A, k + 1, k), at(s->W, k, k), at(s->A, k + 1, k), rest, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
+        // panel solve out of place (A -> T): two 64-column tiles share the same input rows, so in place would race;
+        // the strictly-lower blocks of L are copied back T -> A once, after the last step
+        grp.push_back(make_task(at(s->A, k + 1, k), at(s->W, k, k), at(s->T, k + 1, k), rest, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
         s->trsm.push_back(push_group(grp));
-        grp.push_back(make_task(at(s->A, k + 1, k), at(s->A, k + 1, k), at(s->A, k + 1, k + 1), rest, rest, NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
+        grp.push_back(make_task(at(s->T, k + 1, k), at(s->T, k + 1, k), at(s->A, k + 1, k + 1), rest, rest, NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
         s->syrk.push_back(push_group(grp));
     }
     // trtri levels: spans of `span` blocks are already inverted; join neighbours pairwise
@@ -380,6 +394,10 @@ int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, dou
             rc = launch_gemm_group(s->d_tasks + s->syrk[k].first, s->syrk[k].count, s->syrk[k].tiles, st);
             if (rc) return rc;
         }
+    }
+    if (nblk > 1) {
+        copy_lower_blocks_kernel<<<dim3(nblk - 1, nblk - 1), 256, 0, st>>>(s->T, s->A, ld);
+        DQGP_LAUNCH_CHECK("copy_lower_blocks_kernel");
     }
     for (size_t l = 0; l < s->tri_t.size(); ++l) {
         int rc = launch_gemm_group(s->d_tasks + s->tri_t[l].first, s->tri_t[l].count, s->tri_t[l].tiles, st);

@@ -1,4 +1,6 @@
-// Grouped fp64 GEMM, 128x128 tile per CTA, 8 warps (2x4) each owning 64x32 = 8x4 DMMA 8x8 blocks.
+// Grouped fp64 GEMM, 128x64 tile per CTA, 8 warps (4x2) each owning 32x32 = 4x4 DMMA 8x8 blocks, two CTAs per SM
+// so one CTA's prologue / C read-modify-write overlaps the other's DMMA stream (v1 was 128x128, one CTA per SM:
+// 60% DMMA-pipe utilisation on the K=128 trailing updates, 83% on long K; ncu profiles/r01_v1_syrk0, _lauum).
 // Operands stream HBM/L2 -> shared memory through a 3-stage cp.async (LDGSTS) ring, 16-byte copies;
 // shared-memory pitches (20 / 132 doubles) make every DMMA fragment load bank-conflict-free.
 // A launch covers a *group* of independent tasks (device-resident table) so the many small products of
@@ -8,26 +10,28 @@
 
 namespace dqgp {
 
+template <int ROWS, int PITCH_R>
 __device__ __forceinline__ void gm_load_operand(double* sm, const double* __restrict__ g, int ld, int row0, int k0, int k_contig) {
-    // 128 rows x 16 k doubles = 1024 16-byte chunks, 4 per thread
+    // ROWS rows x 16 k doubles as 16-byte chunks
+    constexpr int CHUNKS = ROWS * GM_KC / 2;
     if (k_contig) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < CHUNKS / GM_THREADS; ++i) {
             const int c = threadIdx.x + GM_THREADS * i;
             const int row = c >> 3, kc = (c & 7) * 2;
             cp_async16(sm + row * GM_PITCH_K + kc, g + (size_t)(row0 + row) * ld + k0 + kc);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < CHUNKS / GM_THREADS; ++i) {
             const int c = threadIdx.x + GM_THREADS * i;
-            const int k = c >> 6, mc = (c & 63) * 2;
-            cp_async16(sm + k * GM_PITCH_M + mc, g + (size_t)(k0 + k) * ld + row0 + mc);
+            const int k = c / (ROWS / 2), mc = (c % (ROWS / 2)) * 2;
+            cp_async16(sm + k * PITCH_R + mc, g + (size_t)(k0 + k) * ld + row0 + mc);
         }
     }
 }
 
-__global__ void __launch_bounds__(GM_THREADS, 1) gemm_group_kernel(const GemmTask* __restrict__ tasks, int n_tasks) {
+__global__ void __launch_bounds__(GM_THREADS, 2) gemm_group_kernel(const GemmTask* __restrict__ tasks, int n_tasks) {
     extern __shared__ __align__(16) double gm_smem[];
     // locate the task that owns this tile (tables are short: <= a few hundred entries)
     int ti = 0;
@@ -42,12 +46,15 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_group_kernel(const GemmTas
     }
     const GemmTask T = tasks[ti];
     const int local = blockIdx.x - T.tile_begin;
+    constexpr int R = GM_BM / GM_BN;
     int tm, tn;
     if (T.lower_tiles) {
-        tm = int((sqrt(8.0 * local + 1.0) - 1.0) * 0.5);
-        while ((tm + 1) * (tm + 2) / 2 <= local) ++tm;
-        while (tm * (tm + 1) / 2 > local) --tm;
-        tn = local - tm * (tm + 1) / 2;
+        // row block tm owns R*(tm+1) tiles; tiles before it: R*tm*(tm+1)/2
+        const int q = local / R;
+        tm = int((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+        while (R * (tm + 1) * (tm + 2) / 2 <= local) ++tm;
+        while (R * tm * (tm + 1) / 2 > local) --tm;
+        tn = local - R * tm * (tm + 1) / 2;
     } else {
         const int tiles_n = T.N / GM_BN;
         tm = local / tiles_n;
@@ -56,28 +63,28 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_group_kernel(const GemmTas
     const int m0 = tm * GM_BM, n0 = tn * GM_BN;
     int kb = 0, ke = T.K;
     if (T.krule == GM_KRULE_A_LOWER) ke = min(T.K, m0 + GM_BM);
-    else if (T.krule == GM_KRULE_B_LOWER) kb = n0;
-    else if (T.krule == GM_KRULE_LAUUM) kb = max(m0, n0);
+    else if (T.krule == GM_KRULE_B_LOWER) kb = (n0 / GM_KC) * GM_KC;
+    else if (T.krule == GM_KRULE_LAUUM) kb = max(m0, (n0 / GM_KC) * GM_KC);
     const int n_chunks = (ke - kb) / GM_KC;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = warp >> 2, wn = warp & 3;     // 2 x 4 warps
+    const int wm = warp >> 1, wn = warp & 1;     // 4 x 2 warps, 32 x 32 each
     const int g = lane >> 2, t = lane & 3;
 
-    double acc[8][4][2];
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    auto stage_a = [&](int s) { return gm_smem + (size_t)s * 2 * GM_OPERAND_DOUBLES; };
-    auto stage_b = [&](int s) { return gm_smem + (size_t)s * 2 * GM_OPERAND_DOUBLES + GM_OPERAND_DOUBLES; };
+    auto stage_a = [&](int s) { return gm_smem + (size_t)s * GM_STAGE_DOUBLES; };
+    auto stage_b = [&](int s) { return gm_smem + (size_t)s * GM_STAGE_DOUBLES + GM_A_DOUBLES; };
 
 #pragma unroll
     for (int s = 0; s < GM_STAGES - 1; ++s) {
         if (s < n_chunks) {
-            gm_load_operand(stage_a(s), T.A, T.lda, m0, kb + s * GM_KC, T.a_k_contig);
-            gm_load_operand(stage_b(s), T.B, T.ldb, n0, kb + s * GM_KC, T.b_k_contig);
+            gm_load_operand<GM_BM, GM_PITCH_M>(stage_a(s), T.A, T.lda, m0, kb + s * GM_KC, T.a_k_contig);
+            gm_load_operand<GM_BN, GM_PITCH_N>(stage_b(s), T.B, T.ldb, n0, kb + s * GM_KC, T.b_k_contig);
         }
         cp_async_commit();
     }
@@ -88,8 +95,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_group_kernel(const GemmTas
             const int nx = ch + GM_STAGES - 1;
             if (nx < n_chunks) {
                 const int s = nx % GM_STAGES;
-                gm_load_operand(stage_a(s), T.A, T.lda, m0, kb + nx * GM_KC, T.a_k_contig);
-                gm_load_operand(stage_b(s), T.B, T.ldb, n0, kb + nx * GM_KC, T.b_k_contig);
+                gm_load_operand<GM_BM, GM_PITCH_M>(stage_a(s), T.A, T.lda, m0, kb + nx * GM_KC, T.a_k_contig);
+                gm_load_operand<GM_BN, GM_PITCH_N>(stage_b(s), T.B, T.ldb, n0, kb + nx * GM_KC, T.b_k_contig);
             }
             cp_async_commit();
         }
@@ -97,23 +104,23 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_group_kernel(const GemmTas
         const double* Bs = stage_b(ch % GM_STAGES);
 #pragma unroll
         for (int kk = 0; kk < GM_KC / 4; ++kk) {
-            double a[8], b[4];
+            double a[4], b[4];
             if (T.a_k_contig) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = As[(wm * 64 + i * 8 + g) * GM_PITCH_K + kk * 4 + t];
+                for (int i = 0; i < 4; ++i) a[i] = As[(wm * 32 + i * 8 + g) * GM_PITCH_K + kk * 4 + t];
             } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) a[i] = As[(kk * 4 + t) * GM_PITCH_M + wm * 64 + i * 8 + g];
+                for (int i = 0; i < 4; ++i) a[i] = As[(kk * 4 + t) * GM_PITCH_M + wm * 32 + i * 8 + g];
             }
             if (T.b_k_contig) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) b[j] = Bs[(wn * 32 + j * 8 + g) * GM_PITCH_K + kk * 4 + t];
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Bs[(kk * 4 + t) * GM_PITCH_M + wn * 32 + j * 8 + g];
+                for (int j = 0; j < 4; ++j) b[j] = Bs[(kk * 4 + t) * GM_PITCH_N + wn * 32 + j * 8 + g];
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
@@ -122,8 +129,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_group_kernel(const GemmTas
 
     // epilogue: each lane owns 2 adjacent doubles per 8x8 block -> 16-byte accesses
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = m0 + wm * 64 + i * 8 + g;
+    for (int i = 0; i < 4; ++i) {
+        const int r = m0 + wm * 32 + i * 8 + g;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = n0 + wn * 32 + j * 8 + 2 * t;

@@ -5,15 +5,18 @@
 
 namespace dqgp {
 
-constexpr int GM_BM = 128, GM_BN = 128, GM_KC = 16, GM_STAGES = 3, GM_THREADS = 256;
+constexpr int GM_BM = 128, GM_BN = 64, GM_KC = 16, GM_STAGES = 3, GM_THREADS = 256;
 constexpr int GM_PITCH_K = GM_KC + 4;    // operand stored [row][k]  (k contiguous in HBM)
-constexpr int GM_PITCH_M = GM_BM + 4;    // operand stored [k][row]  (row contiguous in HBM)
-constexpr int GM_OPERAND_DOUBLES = (GM_BM * GM_PITCH_K > GM_KC * GM_PITCH_M) ? GM_BM * GM_PITCH_K : GM_KC * GM_PITCH_M;
-constexpr size_t GM_SMEM_BYTES = size_t(GM_STAGES) * 2 * GM_OPERAND_DOUBLES * sizeof(double);
+constexpr int GM_PITCH_M = GM_BM + 4;    // A operand stored [k][row]  (row contiguous in HBM)
+constexpr int GM_PITCH_N = GM_BN + 4;    // B operand stored [k][col]
+constexpr int GM_A_DOUBLES = (GM_BM * GM_PITCH_K > GM_KC * GM_PITCH_M) ? GM_BM * GM_PITCH_K : GM_KC * GM_PITCH_M;
+constexpr int GM_B_DOUBLES = (GM_BN * GM_PITCH_K > GM_KC * GM_PITCH_N) ? GM_BN * GM_PITCH_K : GM_KC * GM_PITCH_N;
+constexpr int GM_STAGE_DOUBLES = GM_A_DOUBLES + GM_B_DOUBLES;
+constexpr size_t GM_SMEM_BYTES = size_t(GM_STAGES) * GM_STAGE_DOUBLES * sizeof(double);
 
 enum { GM_KRULE_ALL = 0, GM_KRULE_A_LOWER = 1, GM_KRULE_B_LOWER = 2, GM_KRULE_LAUUM = 3 };
 
-// C(MxN) = alpha * A(MxK) * B(KxN) + beta * C.  M, N multiples of 128; K multiple of 16.
+// C(MxN) = alpha * A(MxK) * B(KxN) + beta * C.  M multiple of 128, N multiple of 64 (callers use 128); K multiple of 16.
 struct GemmTask {
     const double* A;   // a_rowmajor_k ? A[m*lda + k] : A[k*lda + m]
     const double* B;   // b_rowmajor_k ? B[n*ldb + k] : B[k*ldb + n]
@@ -31,9 +34,12 @@ struct GemmTask {
 int launch_gemm_group(const GemmTask* d_tasks, int n_tasks, int total_tiles, cudaStream_t st);
 int gemm_init();   // raises the dynamic shared memory limit once per process/device
 
+// lower_tiles: square output, only tiles that intersect the lower triangle: row block tm (128 rows) needs column
+// blocks 0 .. (tm+1)*(BM/BN)-1, i.e. R*(tm+1) tiles with R = BM/BN.
 static inline int gemm_task_tiles(const GemmTask& t) {
     const int tm = t.M / GM_BM, tn = t.N / GM_BN;
-    return t.lower_tiles ? tm * (tm + 1) / 2 : tm * tn;
+    constexpr int R = GM_BM / GM_BN;
+    return t.lower_tiles ? R * tm * (tm + 1) / 2 : tm * tn;
 }
 
 }  // namespace dqgp
