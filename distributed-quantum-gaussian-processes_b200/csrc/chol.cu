@@ -23,7 +23,10 @@ struct dqgp_solver {
     dqgp::GemmTask* d_tasks;
     // launch groups: [first task, task count, tiles]
     struct Group { int first, count, tiles; };
-    std::vector<Group> trsm, syrk;         // per potrf step
+    std::vector<Group> trsm, syrk_panel, syrk_rest;   // per potrf step (trailing update split for look-ahead)
+    cudaStream_t helper;                              // HIGH-priority stream carrying the critical path (leaf, panel solve, next column)
+    cudaEvent_t ev_fork, ev_join;
+    std::vector<cudaEvent_t> ev_trsm, ev_rest;
     std::vector<Group> tri_t, tri_w;       // per trtri level
     Group lauum, quad;
     size_t bytes;
@@ -296,6 +299,7 @@ int dqgp_solver_create(int n, dqgp_solver** out) {
     s->ld = s->np;
     s->A = s->W = s->T = s->y_pad = s->w = s->partial = s->strip = s->V = nullptr;
     s->d_tasks = nullptr;
+    s->helper = nullptr; s->ev_fork = nullptr; s->ev_join = nullptr;
     cudaError_t e = cudaGetDevice(&s->device);
     const size_t mat = sizeof(double) * (size_t)s->np * s->ld;
     s->bytes = 3 * mat;
@@ -327,8 +331,13 @@ int dqgp_solver_create(int n, dqgp_solver** out) {
         // the strictly-lower blocks of L are copied back T -> A once, after the last step
         grp.push_back(make_task(at(s->A, k + 1, k), at(s->W, k, k), at(s->T, k + 1, k), rest, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
         s->trsm.push_back(push_group(grp));
-        grp.push_back(make_task(at(s->T, k + 1, k), at(s->T, k + 1, k), at(s->A, k + 1, k + 1), rest, rest, NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
-        s->syrk.push_back(push_group(grp));
+        // trailing update, split: block column k+1 first (critical path: next leaf + panel solve need it) ...
+        grp.push_back(make_task(at(s->T, k + 1, k), at(s->T, k + 1, k), at(s->A, k + 1, k + 1), rest, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+        s->syrk_panel.push_back(push_group(grp));
+        // ... and the rest (columns k+2..) on the helper stream, overlapping the next leaf / panel solve
+        if (rest > NB)
+            grp.push_back(make_task(at(s->T, k + 2, k), at(s->T, k + 2, k), at(s->A, k + 2, k + 2), rest - NB, rest - NB, NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
+        s->syrk_rest.push_back(push_group(grp));
     }
     // trtri levels: spans of `span` blocks are already inverted; join neighbours pairwise
     for (int span = 1; span < nblk; span *= 2) {
@@ -356,6 +365,19 @@ int dqgp_solver_create(int n, dqgp_solver** out) {
 
     e = cudaMalloc(&s->d_tasks, sizeof(GemmTask) * tasks.size());
     if (e == cudaSuccess) e = cudaMemcpy(s->d_tasks, tasks.data(), sizeof(GemmTask) * tasks.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&s->helper, cudaStreamNonBlocking, hi);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
+    for (int k = 0; k + 1 < nblk && e == cudaSuccess; ++k) {
+        cudaEvent_t a, b;
+        e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
+        if (e == cudaSuccess) { s->ev_trsm.push_back(a); s->ev_rest.push_back(b); }
+    }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM_V2);
     if (e != cudaSuccess) { dqgp_solver_destroy(s); return cuda_fail(e, "dqgp_solver_create (task table)"); }
     int rc = gemm_init();
@@ -366,6 +388,11 @@ int dqgp_solver_create(int n, dqgp_solver** out) {
 
 void dqgp_solver_destroy(dqgp_solver* s) {
     if (!s) return;
+    for (auto ev : s->ev_trsm) cudaEventDestroy(ev);
+    for (auto ev : s->ev_rest) cudaEventDestroy(ev);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->helper) cudaStreamDestroy(s->helper);
     cudaFree(s->A); cudaFree(s->W); cudaFree(s->T); cudaFree(s->y_pad); cudaFree(s->w); cudaFree(s->partial); cudaFree(s->strip); cudaFree(s->V); cudaFree(s->d_tasks);
     delete s;
 }
@@ -385,16 +412,36 @@ int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, dou
     pad_vector_kernel<<<(np + 255) / 256, 256, 0, st>>>(d_y, s->n, np, s->y_pad, d_logdet, d_info);
     if (np != s->n) pad_identity_kernel<<<np, 256, 0, st>>>(s->A, s->n, np, ld);
     DQGP_LAUNCH_CHECK("pad kernels");
+    // Right-looking Cholesky with one step of look-ahead.  The critical path leaf(k) -> panel solve(k) -> update of
+    // block column k+1 runs on the solver's HIGH-priority stream; the bulk of update k (columns k+2..) stays on the
+    // caller's stream and overlaps the next leaf / panel solve.  Priority matters: a leaf CTA needs 133 KB of shared
+    // memory and only fits beside ONE resident GEMM CTA, so it must win the slot a retiring GEMM CTA frees.
+    cudaStream_t crit = s->helper;
+    DQGP_CUDA(cudaEventRecord(s->ev_fork, st));
+    DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_fork, 0));
+    int last_rest = -1;
     for (int k = 0; k < nblk; ++k) {
-        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, st>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
+        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, crit>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
         DQGP_LAUNCH_CHECK("potrf_leaf_kernel");
         if (k + 1 < nblk) {
-            int rc = launch_gemm_group(s->d_tasks + s->trsm[k].first, s->trsm[k].count, s->trsm[k].tiles, st);
+            int rc = launch_gemm_group(s->d_tasks + s->trsm[k].first, s->trsm[k].count, s->trsm[k].tiles, crit);
             if (rc) return rc;
-            rc = launch_gemm_group(s->d_tasks + s->syrk[k].first, s->syrk[k].count, s->syrk[k].tiles, st);
+            const bool has_rest = s->syrk_rest[k].tiles > 0;
+            if (has_rest) DQGP_CUDA(cudaEventRecord(s->ev_trsm[k], crit));
+            if (last_rest >= 0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_rest[last_rest], 0));   // column k+1 got rest(j<k)
+            rc = launch_gemm_group(s->d_tasks + s->syrk_panel[k].first, s->syrk_panel[k].count, s->syrk_panel[k].tiles, crit);
             if (rc) return rc;
+            if (has_rest) {
+                DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_trsm[k], 0));
+                rc = launch_gemm_group(s->d_tasks + s->syrk_rest[k].first, s->syrk_rest[k].count, s->syrk_rest[k].tiles, st);
+                if (rc) return rc;
+                DQGP_CUDA(cudaEventRecord(s->ev_rest[k], st));
+                last_rest = k;
+            }
         }
     }
+    DQGP_CUDA(cudaEventRecord(s->ev_join, crit));
+    DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
     if (nblk > 1) {
         copy_lower_blocks_kernel<<<dim3(nblk - 1, nblk - 1), 256, 0, st>>>(s->T, s->A, ld);
         DQGP_LAUNCH_CHECK("copy_lower_blocks_kernel");
