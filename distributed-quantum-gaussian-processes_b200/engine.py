@@ -170,6 +170,27 @@ def synthetic_dataset(n, d, encoding, seed=0):
     return x, y
 
 
+def agent_block(rank, world_size, n_agents):
+    """Contiguous block of agents owned by `rank`: agent a lives on rank a // (A / world).  The blocks are in
+    rank order, so an all-gather of the per-rank (A/world, P) rows reproduces the (A, P) arrays in agent order and
+    every rank sums the consensus in the same order as np.sum(axis=0) (riemannian_optimizer.py:42-43)."""
+    if n_agents % world_size:
+        raise ValueError(f"{n_agents} agents do not split evenly over {world_size} ranks")
+    per = n_agents // world_size
+    return range(rank * per, (rank + 1) * per)
+
+
+def exchange_rows(full, local, group=None, world_size=1):
+    """The ONLY cross-agent exchange of the path (main.py:2523 / :2550-2555): gather every rank's (A_local, P) rows of
+    theta or psi into the replicated (A, P) array.  NCCL over NVLink for CUDA tensors, gloo in the CPU tests."""
+    if world_size == 1:
+        full.copy_(local)
+        return full
+    import torch.distributed as dist
+    dist.all_gather_into_tensor(full.view(-1), local.contiguous().view(-1), group=group)
+    return full
+
+
 class AdmmEngine:
     """All agents of a run, sharded over ranks in contiguous blocks (agent a lives on rank a // (A/world))."""
 
@@ -179,12 +200,11 @@ class AdmmEngine:
         self.A_total = int(theta0.shape[0])
         self.P = int(theta0.shape[1])
         self.world, self.rank, self.pg = int(world_size), int(rank), process_group
-        if self.A_total % self.world:
-            raise ValueError(f"{self.A_total} agents do not split evenly over {self.world} ranks")
-        self.A_local = self.A_total // self.world
+        block = agent_block(self.rank, self.world, self.A_total)
+        self.A_local = len(block)
         if len(shards) != self.A_local:
             raise ValueError(f"rank {rank} expects {self.A_local} shards, got {len(shards)}")
-        self.first = self.rank * self.A_local
+        self.first = block.start
         self.rho = float(rho)
         lips = L if np.ndim(L) else [L] * self.A_total
         self.agents = [AgentEngine(x, y, rho=rho, L=lips[self.first + i], **agent_kw) for i, (x, y) in enumerate(shards)]
@@ -219,13 +239,8 @@ class AdmmEngine:
                 done = torch.cuda.Event()
                 done.record(s)
                 main.wait_event(done)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self.theta, self.local_theta, group=self.pg)
-            dist.all_gather_into_tensor(self.psi, self.local_psi, group=self.pg)
-        else:
-            self.theta.copy_(self.local_theta)
-            self.psi.copy_(self.local_psi)
+        exchange_rows(self.theta, self.local_theta, self.pg, self.world)
+        exchange_rows(self.psi, self.local_psi, self.pg, self.world)
 
     def state(self):
         """(z, theta, psi, per-agent NLL) on the host (synchronises)."""
