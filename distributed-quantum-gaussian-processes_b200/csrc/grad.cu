@@ -100,35 +100,48 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
 }
 
+// Stage one parameter set's row and column feature tiles (64 x m each) + their squared norms.  Four threads per
+// sample row, no integer division: thread (row = tid>>2, lane4 = tid&3) copies chunks lane4, lane4+4, ... of its row.
+// VEC=2: m even -> 16-byte cp.async (row starts are 16-byte aligned); VEC=1: 8-byte copies.
+template <int VEC>
 __device__ __forceinline__ void g2_stage(double* buf, const double* __restrict__ Fs, const double* __restrict__ Ns, int row0,
                                          int col0, int n, int m) {
-    double* Fr = buf;
-    double* Fc = buf + PW_TILE * G2_PITCH;
-    double* nr = buf + 2 * PW_TILE * G2_PITCH;
-    for (int e = threadIdx.x; e < PW_TILE * m; e += PW_THREADS) {
-        const int r = e / m, k = e - r * m;
-        cp_async8(&Fr[r * G2_PITCH + k], &Fs[(size_t)min(row0 + r, n - 1) * m + k]);
-        cp_async8(&Fc[r * G2_PITCH + k], &Fs[(size_t)min(col0 + r, n - 1) * m + k]);
+    const int r = threadIdx.x >> 2, l4 = threadIdx.x & 3;
+    const double* src_r = Fs + (size_t)min(row0 + r, n - 1) * m;
+    const double* src_c = Fs + (size_t)min(col0 + r, n - 1) * m;
+    double* dst_r = buf + r * G2_PITCH;
+    double* dst_c = buf + PW_TILE * G2_PITCH + r * G2_PITCH;
+    if (VEC == 2) {
+        for (int k = 2 * l4; k < m; k += 8) {
+            cp_async16(dst_r + k, src_r + k);
+            cp_async16(dst_c + k, src_c + k);
+        }
+    } else {
+        for (int k = l4; k < m; k += 4) {
+            cp_async8(dst_r + k, src_r + k);
+            cp_async8(dst_c + k, src_c + k);
+        }
     }
+    double* nr = buf + 2 * PW_TILE * G2_PITCH;
     if (threadIdx.x < PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(row0 + threadIdx.x, n - 1)]);
     else if (threadIdx.x < 2 * PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(col0 + threadIdx.x - PW_TILE, n - 1)]);
 }
 
 template <int OUTER>
-__device__ __forceinline__ double outer_from_neg_gd2(double v, const OuterHyp& h) {
-    // v = -gamma_eff * d^2 (gamma_eff = gamma for the Gaussian, 1 otherwise)
+__device__ __forceinline__ double outer_from_neg_gd2(double v, const OuterHyp& h, double tab) {
+    // v = -gamma_eff * d^2 (gamma_eff = gamma for the Gaussian, 1 otherwise); warp-collective (table shuffle)
     if (OUTER == DQGP_OUTER_GAUSSIAN) {
-        return fast_exp(fmax(v, -700.0));
+        return fast_exp_tab(fmax(v, -700.0), tab);
     } else if (OUTER == DQGP_OUTER_MATERN15) {
         const double k = sqrt(fmax(-v, 0.0)) * h.a * 1.7320508075688772;
-        return (1.0 + k) * fast_exp(fmax(-k, -700.0));
+        return (1.0 + k) * fast_exp_tab(fmax(-k, -700.0), tab);
     } else {
         const double sn = sin(sqrt(fmax(-v, 0.0)) * h.b) * h.a;
-        return fast_exp(fmax(-2.0 * (sn * sn), -700.0));
+        return fast_exp_tab(fmax(-2.0 * (sn * sn), -700.0), tab);
     }
 }
 
-template <int OUTER>
+template <int OUTER, int VEC>
 __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(const double* __restrict__ Ainv, int ld,
                                                                            const double* __restrict__ alpha,
                                                                            const double* __restrict__ F,
@@ -144,6 +157,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
     const int ksteps = (m + 3) >> 2;
     const double gam = (OUTER == DQGP_OUTER_GAUSSIAN) ? hyp.a : 1.0;
     const double a_scale = 2.0 * gam;
+    const double tab = exp_table_entry();
 
     // zero the k-padding columns of both stages once (cp.async never writes them)
     for (int e = threadIdx.x; e < 2 * 2 * PW_TILE * (G2_PITCH - m); e += PW_THREADS) {
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
 
     const size_t set_stride = (size_t)n * m;
     const int T = 2 * P;
-    g2_stage(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m);
+    g2_stage<VEC>(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m);
     cp_async_commit();
     double pplus = 0.0, pminus = 0.0;
     for (int tt = 0; tt < T; ++tt) {
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
             partial[(size_t)blockIdx.x * P + i] = s;
         }
         if (tt + 1 < T) {
-            g2_stage(g2_smem + ((tt + 1) & 1) * G2_STAGE_DOUBLES, F + (size_t)(tt + 2) * set_stride, Nrm + (size_t)(tt + 2) * n, row0, col0, n, m);
+            g2_stage<VEC>(g2_smem + ((tt + 1) & 1) * G2_STAGE_DOUBLES, F + (size_t)(tt + 2) * set_stride, Nrm + (size_t)(tt + 2) * n, row0, col0, n, m);
         }
         cp_async_commit();
         const double* buf = g2_smem + (tt & 1) * G2_STAGE_DOUBLES;
@@ -221,7 +235,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) part = fma(br[rb][cb][e], outer_from_neg_gd2<OUTER>(c[rb][cb][e], hyp), part);
+                for (int e = 0; e < 2; ++e) part = fma(br[rb][cb][e], outer_from_neg_gd2<OUTER>(c[rb][cb][e], hyp, tab), part);
         if (tt & 1) {
             pminus = part;
             double v = warp_sum(pplus - pminus);
@@ -375,10 +389,14 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
     do {                                                                                                                     \
         static bool attr_done = false;                                                                                       \
         if (!attr_done) {                                                                                                    \
-            DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
+            DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
+            DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             attr_done = true;                                                                                                \
         }                                                                                                                    \
-        grad_projected_dmma_kernel<OUT><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+        if ((m & 1) == 0 && (reinterpret_cast<uintptr_t>(d_F) & 15) == 0)                                                    \
+            grad_projected_dmma_kernel<OUT, 2><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+        else                                                                                                                 \
+            grad_projected_dmma_kernel<OUT, 1><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
     } while (0)
         switch (outer) {
             case DQGP_OUTER_GAUSSIAN: DQGP_G2(DQGP_OUTER_GAUSSIAN); break;
