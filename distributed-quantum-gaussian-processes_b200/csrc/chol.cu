@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
     double* s_diag = M + NB * LP;
     double* s_rdiag = s_diag + NB;
     __shared__ double s_red[LEAF_THREADS / 32];
+    __shared__ double s_blk[64];
     __shared__ int s_bad;
     const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
     double* Ablk = A + (size_t)blk * NB * ld + (size_t)blk * NB;
@@ -86,40 +87,57 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
                 a[6] = fma(-lik, v3.x, a[6]); a[7] = fma(-lik, v3.y, a[7]);
             }
         }
-        if (warp == (j0 >> 5)) {
-            // the warp that owns rows j0..j0+7 factors the 8x8 block and finishes its own rows with shuffles
+        // rows j0..j0+7 publish their updated 8x8 diagonal block; every thread then factors it redundantly in
+        // registers (no cross-lane dependency chain: v2 did this with ~60 dependent shuffles per panel) and
+        // forward-substitutes its own row against it
+        if (i >= j0 && i < j0 + 8) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int src_lane = (j0 + c) & 31;
-                const double piv = __shfl_sync(0xffffffffu, a[c], src_lane);
-                if (!(piv > 0.0) && lane == 0 && s_bad == 0) s_bad = j0 + c + 1;
-                const double d = sqrt(piv), rd = 1.0 / d;
-                if (i > j0 + c) a[c] *= rd;
-                else if (i == j0 + c) { a[c] = d; s_diag[i] = d; s_rdiag[i] = rd; }
-#pragma unroll
-                for (int c2 = c + 1; c2 < 8; ++c2) {
-                    const double lc = __shfl_sync(0xffffffffu, a[c], (j0 + c2) & 31);   // L[j0+c2][j0+c]
-                    if (i > j0 + c) a[c2] = fma(-a[c], lc, a[c2]);
-                }
-            }
-            if (i >= j0) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (i > j0 + c) M[(j0 + c) * LP + i] = a[c];
-            }
+            for (int c = 0; c < 8; ++c) s_blk[(i - j0) * 8 + c] = a[c];
         }
         __syncthreads();
-        if (warp != (j0 >> 5) && i >= j0 + 8) {
-            // rows owned by the other warps: forward substitution against the 8x8 block now in shared memory
+        if (i >= j0) {
+            double l[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c) l[r][c] = s_blk[r * 8 + c];
+            double rd[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                double x = a[c];
+                const double piv = l[c][c];
+                if (!(piv > 0.0) && i == j0 && s_bad == 0) s_bad = j0 + c + 1;
+                rd[c] = rsqrt(piv);
+                l[c][c] = piv * rd[c];
 #pragma unroll
-                for (int k = 0; k < c; ++k) x = fma(-a[k], M[(j0 + k) * LP + j0 + c], x);
-                x *= s_rdiag[j0 + c];
-                a[c] = x;
-                M[(j0 + c) * LP + i] = x;
+                for (int r = c + 1; r < 8; ++r) l[r][c] *= rd[c];
+#pragma unroll
+                for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+                    for (int r = c2; r < 8; ++r) l[r][c2] = fma(-l[r][c], l[c2][c], l[r][c2]);
             }
+            if (i < j0 + 8) {
+                // my row of the factored block
+                const int r0 = i - j0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r == r0) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) a[c] = (c <= r) ? l[r][c] : 0.0;
+                        s_diag[i] = l[r][r];
+                        s_rdiag[i] = rd[r];
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    double x = a[c];
+#pragma unroll
+                    for (int k = 0; k < c; ++k) x = fma(-a[k], l[c][k], x);
+                    a[c] = x * rd[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (i > j0 + c) M[(j0 + c) * LP + i] = a[c];
         }
         if (i >= j0) {
             double2* dst = reinterpret_cast<double2*>(Ablk + (size_t)i * ld + j0);

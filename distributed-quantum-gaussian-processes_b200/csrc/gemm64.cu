@@ -31,6 +31,9 @@ __device__ __forceinline__ void gm_load_operand(double* sm, const double* __rest
     }
 }
 
+template <int AK, int BK>
+__device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* gm_smem);
+
 __global__ void __launch_bounds__(GM_THREADS, 2) gemm_group_kernel(const GemmTask* __restrict__ tasks, int n_tasks) {
     extern __shared__ __align__(16) double gm_smem[];
     // locate the task that owns this tile (tables are short: <= a few hundred entries)
@@ -46,6 +49,16 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemm_group_kernel(const GemmTas
     }
     const GemmTask T = tasks[ti];
     const int local = blockIdx.x - T.tile_begin;
+    // operand layouts are compile-time inside the tile routine (no predicated duplicate fragment loads)
+    if (T.a_k_contig) {
+        if (T.b_k_contig) gemm_tile<1, 1>(T, local, gm_smem); else gemm_tile<1, 0>(T, local, gm_smem);
+    } else {
+        if (T.b_k_contig) gemm_tile<0, 1>(T, local, gm_smem); else gemm_tile<0, 0>(T, local, gm_smem);
+    }
+}
+
+template <int AK, int BK>
+__device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* gm_smem) {
     constexpr int R = GM_BM / GM_BN;
     int tm, tn;
     if (T.lower_tiles) {
@@ -83,8 +96,8 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemm_group_kernel(const GemmTas
 #pragma unroll
     for (int s = 0; s < GM_STAGES - 1; ++s) {
         if (s < n_chunks) {
-            gm_load_operand<GM_BM, GM_PITCH_M>(stage_a(s), T.A, T.lda, m0, kb + s * GM_KC, T.a_k_contig);
-            gm_load_operand<GM_BN, GM_PITCH_N>(stage_b(s), T.B, T.ldb, n0, kb + s * GM_KC, T.b_k_contig);
+            gm_load_operand<GM_BM, GM_PITCH_M>(stage_a(s), T.A, T.lda, m0, kb + s * GM_KC, AK);
+            gm_load_operand<GM_BN, GM_PITCH_N>(stage_b(s), T.B, T.ldb, n0, kb + s * GM_KC, BK);
         }
         cp_async_commit();
     }
@@ -95,8 +108,8 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemm_group_kernel(const GemmTas
             const int nx = ch + GM_STAGES - 1;
             if (nx < n_chunks) {
                 const int s = nx % GM_STAGES;
-                gm_load_operand<GM_BM, GM_PITCH_M>(stage_a(s), T.A, T.lda, m0, kb + nx * GM_KC, T.a_k_contig);
-                gm_load_operand<GM_BN, GM_PITCH_N>(stage_b(s), T.B, T.ldb, n0, kb + nx * GM_KC, T.b_k_contig);
+                gm_load_operand<GM_BM, GM_PITCH_M>(stage_a(s), T.A, T.lda, m0, kb + nx * GM_KC, AK);
+                gm_load_operand<GM_BN, GM_PITCH_N>(stage_b(s), T.B, T.ldb, n0, kb + nx * GM_KC, BK);
             }
             cp_async_commit();
         }
@@ -105,14 +118,14 @@ __global__ void __launch_bounds__(GM_THREADS, 2) gemm_group_kernel(const GemmTas
 #pragma unroll
         for (int kk = 0; kk < GM_KC / 4; ++kk) {
             double a[4], b[4];
-            if (T.a_k_contig) {
+            if (AK) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) a[i] = As[(wm * 32 + i * 8 + g) * GM_PITCH_K + kk * 4 + t];
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) a[i] = As[(kk * 4 + t) * GM_PITCH_M + wm * 32 + i * 8 + g];
             }
-            if (T.b_k_contig) {
+            if (BK) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) b[j] = Bs[(wn * 32 + j * 8 + g) * GM_PITCH_K + kk * 4 + t];
             } else {
