@@ -247,14 +247,15 @@ def run_e2e(args, w, d, torch, dist, world, rank, shards, theta0, psi0, n_i, P, 
                                 outer_kernel=w["outer"], training_ignores_outer_kernel=not w["honour_outer"])
               for i, (x, y) in enumerate(shards)]
     _, _, admm = d.create_riemannian_framework(P, rho=RHO)
+    streams = [torch.cuda.Stream() for _ in agents]
     theta, psi = theta0.copy(), psi0.copy()
 
     def one_iteration():
         nonlocal theta, psi
         z = np.round(admm.update_z(theta, psi), 4)
         loc = np.empty((per, 2, P))
-        for i, ag in enumerate(agents):
-            th, ps, _, _, _ = ag.train_and_update(z, psi[rank * per + i])
+        results = d.train_agents(agents, z, [psi[rank * per + i] for i in range(per)], streams)
+        for i, (th, ps, _, _, _) in enumerate(results):
             loc[i, 0], loc[i, 1] = np.round(th, 4), np.round(ps, 4)
         if world > 1:
             buf = torch.from_numpy(loc).cuda()
@@ -280,7 +281,7 @@ def run_e2e(args, w, d, torch, dist, world, rank, shards, theta0, psi0, n_i, P, 
     sec = float(el.item()) / steps
     return {"value": entries_per_iter / sec, "unit": "entries/s", "admm_iters_per_s": 1.0 / sec, "steps": steps,
             "h2d_bytes_per_step": int(sum(a.h2d_bytes for a in agents)) * world, "d2h_bytes_per_step": int(sum(a.d2h_bytes for a in agents)) * world,
-            "api": "RiemannianAgent.train_and_update(z, psi_i) with host arrays + host RiemannianADMM.update_z"}
+            "api": "dqgp_b200.train_agents (= RiemannianAgent.train_and_update per agent, one stream each) with host arrays + host RiemannianADMM.update_z"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ from .riemannian import (RiemannianADMM, RiemannianOptimizer, TorusManifold, cir
                          create_riemannian_framework)
 from .kernels import (EncodingCircuit, Executor, FidelityKernel, ProjectedQuantumKernel,  # noqa: F401
                       create_quantum_kernel)
-from .agent import RiemannianAgent, process_agent_training  # noqa: F401
+from .agent import RiemannianAgent, process_agent_training, train_agents  # noqa: F401
 from .engine import AgentEngine, AdmmEngine, agent_block, exchange_rows, synthetic_dataset  # noqa: F401
 from .predict import k_fold_cross_validation_consensus, nlpd, predict_quantum_gp  # noqa: F401
 

@@ -36,6 +36,7 @@ SIGNATURES = {
     "dqgp_circuit_num_parameters": (_i, [_vp]),
     "dqgp_circuit_num_gates": (_i, [_vp]),
     "dqgp_circuit_num_passes": (_i, [_vp]),
+    "dqgp_circuit_num_fused_ops": (_i, [_vp]),
     "dqgp_circuit_describe": (_i, [_vp, C.POINTER(Gate), _i]),
     "dqgp_features": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "dqgp_states": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),

@@ -68,7 +68,7 @@ class RiemannianAgent:
 
     def _engine(self):
         n, d = self.X_sub.shape
-        key = (n, d, self.encoding_type, self.kernel_type, self.num_qubits, self.num_layers, self.outer_kernel,
+        key = (self.agent_id, n, d, self.encoding_type, self.kernel_type, self.num_qubits, self.num_layers, self.outer_kernel,
                float(self.noise_std), float(self.rho), float(self.L), float(self.shift_value), self.training_ignores_outer_kernel)
         return _engine_for(key, lambda: AgentEngine(
             self.X_sub, self.Y_sub, encoding_type=self.encoding_type, kernel_type=self.kernel_type, num_qubits=self.num_qubits,
@@ -77,19 +77,37 @@ class RiemannianAgent:
 
     def train_and_update(self, z, psi_i):
         """-> (theta_i, psi_i, nll_loss, condition_number, nll_components), as agent_riemannian.py:491."""
+        return self.collect(self.submit(z, psi_i))
+
+    def submit(self, z, psi_i, stream=None):
+        """Enqueue the whole step (H2D of shard, z, psi; all kernels; packing of the result) on `stream` without
+        waiting for it.  `collect()` reads the result back.  Lets a driver overlap the agents of one GPU — the
+        reference overlaps them with a process pool (main.py:2530-2542)."""
         eng = self._engine()
         z = np.asarray(z, dtype=np.float64).reshape(-1)
         psi_i = np.asarray(psi_i, dtype=np.float64).reshape(-1)
         if z.size != eng.P or psi_i.size != eng.P:
             raise ValueError(f"expected {eng.P} parameters, got z {z.size}, psi {psi_i.size}")
         self._setup_riemannian_framework(eng.P)
-        eng.load_data(self.X_sub, self.Y_sub)
-        d_in = dev_f64(np.stack([z, psi_i]))
-        d_out = torch.empty((2, eng.P), dtype=torch.float64, device=d_in.device)
-        eng.step(d_in[0], d_in[1], d_out[0], d_out[1])
-        packed = torch.cat([d_out.reshape(-1), eng.d_nll, eng.d_grad, eng.d_info.to(torch.float64)]).cpu().numpy()   # one D2H
+        ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
+        with ctx:
+            eng.load_data(self.X_sub, self.Y_sub)
+            d_in = dev_f64(np.stack([z, psi_i]))
+            d_out = torch.empty((2, eng.P), dtype=torch.float64, device=d_in.device)
+            eng.step(d_in[0], d_in[1], d_out[0], d_out[1])
+            packed = torch.cat([d_out.reshape(-1), eng.d_nll, eng.d_grad, eng.d_info.to(torch.float64)])
+            host = torch.empty(packed.shape, dtype=torch.float64, pin_memory=True)
+            host.copy_(packed, non_blocking=True)          # one D2H
+            done = torch.cuda.Event()
+            done.record()
         self.h2d_bytes = self.X_sub.nbytes + self.Y_sub.nbytes + z.nbytes + psi_i.nbytes
-        self.d2h_bytes = packed.nbytes
+        self.d2h_bytes = host.numel() * 8
+        return (eng, d_in, packed, host, done)
+
+    def collect(self, pending):
+        eng, d_in, _packed, host, done = pending
+        done.synchronize()
+        packed = host.numpy()
         p = eng.P
         theta_i, psi_new = packed[:p].copy(), packed[p:2 * p].copy()
         terms = packed[2 * p:2 * p + 4]
@@ -101,8 +119,7 @@ class RiemannianAgent:
             raise np.linalg.LinAlgError(f"Agent {self.agent_id}: Cholesky failed at pivot {info} (K + sigma^2 I not SPD)")
         cond = float("nan")
         if self.compute_condition_number:
-            k = eng.solver.matrix()    # holds L after the step; recompute the Gram for the diagnostic
-            eng.simulate(d_in[0]); eng.gram()
+            eng.simulate(d_in[0]); eng.gram()      # the solver matrix holds L after the step: rebuild K for the diagnostic
             k = torch.tril(eng.solver.matrix()); k = k + k.T - torch.diag(torch.diagonal(k))
             k = k - (self.noise_std ** 2) * torch.eye(eng.n, dtype=torch.float64, device=k.device)
             sv = torch.linalg.svdvals(k)
@@ -110,6 +127,36 @@ class RiemannianAgent:
         comps = {"log_det_term": float(terms[0]), "quadratic_term": float(terms[1]), "constant_term": float(terms[2]),
                  "total": float(terms[3])}
         return theta_i, psi_new, float(terms[3]), cond, comps
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def train_agents(agents, z, psis, streams=None):
+    """Run `train_and_update(z, psis[i])` for several agents of this GPU concurrently (one CUDA stream each) and
+    return the list of 5-tuples in agent order — the GPU counterpart of the reference's
+    `executor.map(process_agent_training, ...)` fan-out (main.py:2530-2542).  Agents must have distinct shard shapes
+    or configurations only if they are meant to share nothing: engines are cached per (shape, configuration), so
+    agents with identical keys are serialised on one engine."""
+    if streams is None:
+        streams = [torch.cuda.Stream() for _ in agents]
+    main = torch.cuda.current_stream()
+    ready = torch.cuda.Event()
+    ready.record(main)
+    pending, seen = [], {}
+    for ag, psi, st in zip(agents, psis, streams):
+        key = id(ag._engine())
+        if key in seen:                       # same cached engine: keep program order on its stream
+            st = seen[key]
+        seen[key] = st
+        st.wait_event(ready)
+        pending.append(ag.submit(z, psi, stream=st))
+    return [ag.collect(p) for ag, p in zip(agents, pending)]
 
 
 def process_agent_training(agent_data):

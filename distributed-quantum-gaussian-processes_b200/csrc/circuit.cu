@@ -245,6 +245,7 @@ void dqgp_circuit_destroy(dqgp_circuit* c) {
 int dqgp_circuit_num_parameters(const dqgp_circuit* c) { return c ? c->P : -1; }
 int dqgp_circuit_num_gates(const dqgp_circuit* c) { return c ? (int)c->gates.size() : -1; }
 int dqgp_circuit_num_passes(const dqgp_circuit* c) { return c ? (int)c->passes.size() : -1; }
+int dqgp_circuit_num_fused_ops(const dqgp_circuit* c) { return c ? (int)c->ops.size() : -1; }
 int dqgp_circuit_describe(const dqgp_circuit* c, dqgp_gate* h_out, int capacity) {
     DQGP_REQUIRE(c && h_out, "dqgp_circuit_describe: NULL argument");
     int n = (int)c->gates.size();

@@ -135,7 +135,7 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 // <X>,<Y>,<Z> of qubits k0 .. k0+B-1 from register blocks; group-local shuffle reduction; lane 0 of the state writes
 template <int B, int Q>
 __device__ __forceinline__ void features_block(const double2* __restrict__ amp, int k0, int lig, int lps, bool live,
-                                               double* __restrict__ dst) {
+                                               double* __restrict__ dst, double* __restrict__ red = nullptr) {
     constexpr int N = 1 << B;
     const int groups = (1 << Q) >> B;
     double fx[B], fy[B], fz[B];
@@ -164,18 +164,36 @@ __device__ __forceinline__ void features_block(const double2* __restrict__ amp, 
                 fz[l] += (a.x * a.x + a.y * a.y) - (b.x * b.x + b.y * b.y);
             }
     }
+    if (lps <= 32) {
 #pragma unroll
-    for (int l = 0; l < B; ++l) {
-        for (int o = lps >> 1; o > 0; o >>= 1) {
-            fx[l] += __shfl_xor_sync(0xffffffffu, fx[l], o);
-            fy[l] += __shfl_xor_sync(0xffffffffu, fy[l], o);
-            fz[l] += __shfl_xor_sync(0xffffffffu, fz[l], o);
+        for (int l = 0; l < B; ++l) {
+            for (int o = lps >> 1; o > 0; o >>= 1) {
+                fx[l] += __shfl_xor_sync(0xffffffffu, fx[l], o);
+                fy[l] += __shfl_xor_sync(0xffffffffu, fy[l], o);
+                fz[l] += __shfl_xor_sync(0xffffffffu, fz[l], o);
+            }
+            if (live && lig == 0) {
+                dst[k0 + l] = 2.0 * fx[l];
+                dst[Q + k0 + l] = 2.0 * fy[l];
+                dst[2 * Q + k0 + l] = fz[l];
+            }
         }
-        if (live && lig == 0) {
-            dst[k0 + l] = 2.0 * fx[l];
-            dst[Q + k0 + l] = 2.0 * fy[l];
-            dst[2 * Q + k0 + l] = fz[l];
+    } else {
+        // team = whole block (several warps per state): warp shuffle, then a fixed-order sum over warps in shared memory
+        const int warp = lig >> 5, nw = lps >> 5;
+#pragma unroll
+        for (int l = 0; l < B; ++l) {
+            fx[l] = warp_sum(fx[l]); fy[l] = warp_sum(fy[l]); fz[l] = warp_sum(fz[l]);
+            if ((lig & 31) == 0) { red[(warp * 3 + 0) * 3 + l] = fx[l]; red[(warp * 3 + 1) * 3 + l] = fy[l]; red[(warp * 3 + 2) * 3 + l] = fz[l]; }
         }
+        __syncthreads();
+        if (lig < 3 * B) {
+            const int which = lig / B, l = lig - which * B;
+            double t = 0.0;
+            for (int w = 0; w < nw; ++w) t += red[(w * 3 + which) * 3 + l];
+            if (live) dst[which * Q + k0 + l] = (which == 2) ? t : 2.0 * t;
+        }
+        __syncthreads();
     }
 }
 
@@ -298,6 +316,135 @@ __global__ void __launch_bounds__(128) statevec_kernel(const dqgp_gate* __restri
     }
 }
 
+// ---- q >= 9: one state per CTA (2^(q-3) threads: 64 .. 512), so the 16 KB+ of amplitudes per state buy
+// 2..16 warps of parallelism instead of one (q=10 warp-per-state ran at 8 warps/SM: 139 ms per agent at config 5).
+template <int Q, bool WANT_STATES>
+__global__ void __launch_bounds__(((1 << Q) >> 3)) statevec_block_kernel(const dqgp_gate* __restrict__ gates, int n_gates,
+                                                                          const SvPass* __restrict__ passes, int n_passes,
+                                                                          const SvOp* __restrict__ ops, const SvMat* __restrict__ mats,
+                                                                          int n_mats, const int* __restrict__ mat_gates,
+                                                                          int n_mat_gates, int d, int P, int uses_acos,
+                                                                          const double* __restrict__ X, int n,
+                                                                          const double* __restrict__ Pm, int S, double* __restrict__ out) {
+    constexpr int DIM = 1 << Q;
+    constexpr int TEAM = DIM >> 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t gate_bytes = (sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15);
+    const size_t pass_bytes = (sizeof(SvPass) * n_passes + 15) & ~size_t(15);
+    const size_t op_bytes = (sizeof(SvOp) * n_gates + 15) & ~size_t(15);
+    const size_t mat_bytes = (sizeof(SvMat) * n_mats + sizeof(int) * n_mat_gates + 15) & ~size_t(15);
+    dqgp_gate* s_gates = reinterpret_cast<dqgp_gate*>(smem_raw);
+    SvPass* s_passes = reinterpret_cast<SvPass*>(smem_raw + gate_bytes);
+    SvOp* s_ops = reinterpret_cast<SvOp*>(smem_raw + gate_bytes + pass_bytes);
+    SvMat* s_mats = reinterpret_cast<SvMat*>(smem_raw + gate_bytes + pass_bytes + op_bytes);
+    int* s_mat_gates = reinterpret_cast<int*>(s_mats + n_mats);
+    double2* amp = reinterpret_cast<double2*>(smem_raw + gate_bytes + pass_bytes + op_bytes + mat_bytes);
+    double2* trig = amp + DIM;
+    double2* u2 = trig + n_gates;
+    double* acx = reinterpret_cast<double*>(u2 + 4 * n_mats);
+    double* red = acx + ((d + 1) & ~1);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_gates; i += TEAM) { s_gates[i] = gates[i]; s_ops[i] = ops[i]; }
+    for (int i = tid; i < n_passes; i += TEAM) s_passes[i] = passes[i];
+    for (int i = tid; i < n_mats; i += TEAM) s_mats[i] = mats[i];
+    for (int i = tid; i < n_mat_gates; i += TEAM) s_mat_gates[i] = mat_gates[i];
+    __syncthreads();
+    const long long total = (long long)S * n;
+    const int m = 3 * Q;
+    for (long long st = blockIdx.x; st < total; st += gridDim.x) {
+        const int s = int(st / n), j = int(st % n);
+        const double* x = X + (size_t)j * d;
+        const double* p = Pm + (size_t)s * P;
+        if (uses_acos) {
+            for (int f = tid; f < d; f += TEAM) acx[f] = acos(x[f]);
+            __syncthreads();
+        }
+        for (int g = tid; g < n_gates; g += TEAM) {
+            const dqgp_gate gt = s_gates[g];
+            if (gt.form == DQGP_A_NONE) continue;
+            double ang = 0.0;
+            switch (gt.form) {
+                case DQGP_A_P: ang = p[gt.pidx]; break;
+                case DQGP_A_X: ang = x[gt.fidx]; break;
+                case DQGP_A_P_PLUS_CX: ang = p[gt.pidx] + gt.coef * x[gt.fidx]; break;
+                case DQGP_A_P_TIMES_ACOS: ang = p[gt.pidx] * acx[gt.fidx]; break;
+                case DQGP_A_C_TIMES_ACOS: ang = gt.coef * acx[gt.fidx]; break;
+                default: break;
+            }
+            double sn, cs;
+            sincos(0.5 * ang, &sn, &cs);
+            trig[g] = make_double2(cs, sn);
+        }
+        for (int i = tid; i < DIM; i += TEAM) amp[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
+        __syncthreads();
+        for (int f = tid; f < n_mats; f += TEAM) {
+            const SvMat mt = s_mats[f];
+            double2 mm[4];
+            {
+                const int g0 = s_mat_gates[mt.g_begin];
+                const double2 cs = trig[g0];
+                gate_matrix(s_gates[g0].kind, cs.x, cs.y, mm);
+            }
+            for (int e = mt.g_begin + 1; e < mt.g_end; ++e) {
+                const int g = s_mat_gates[e];
+                const double2 cs = trig[g];
+                double2 gg[4];
+                gate_matrix(s_gates[g].kind, cs.x, cs.y, gg);
+                const double2 n0 = cadd(cmul(gg[0], mm[0]), cmul(gg[1], mm[2]));
+                const double2 n1 = cadd(cmul(gg[0], mm[1]), cmul(gg[1], mm[3]));
+                const double2 n2 = cadd(cmul(gg[2], mm[0]), cmul(gg[3], mm[2]));
+                const double2 n3 = cadd(cmul(gg[2], mm[1]), cmul(gg[3], mm[3]));
+                mm[0] = n0; mm[1] = n1; mm[2] = n2; mm[3] = n3;
+            }
+            u2[4 * f + 0] = mm[0]; u2[4 * f + 1] = mm[1]; u2[4 * f + 2] = mm[2]; u2[4 * f + 3] = mm[3];
+        }
+        __syncthreads();
+        for (int ip = 0; ip < n_passes; ++ip) {
+            const SvPass ps = s_passes[ip];
+            if (ps.nq == 3) run_pass<3>(amp, ps, s_ops, u2, trig, tid, TEAM, DIM >> 3);
+            else if (ps.nq == 2) run_pass<2>(amp, ps, s_ops, u2, trig, tid, TEAM, DIM >> 2);
+            else run_pass<1>(amp, ps, s_ops, u2, trig, tid, TEAM, DIM >> 1);
+            __syncthreads();
+        }
+        if (WANT_STATES) {
+            double2* dst = reinterpret_cast<double2*>(out) + (size_t)st * DIM;
+            for (int i = tid; i < DIM; i += TEAM) dst[i] = amp[sv_phys(i)];
+        } else {
+            double* dst = out + (size_t)st * m;
+            constexpr int FULL = Q / 3, REM = Q % 3;
+#pragma unroll 1
+            for (int b = 0; b < FULL; ++b) features_block<3, Q>(amp, 3 * b, tid, TEAM, true, dst, red);
+            if (REM == 2) features_block<2, Q>(amp, 3 * FULL, tid, TEAM, true, dst, red);
+            if (REM == 1) features_block<1, Q>(amp, 3 * FULL, tid, TEAM, true, dst, red);
+        }
+        __syncthreads();
+    }
+}
+
+template <int Q, bool WANT_STATES>
+static int launch_sv_block(const dqgp_circuit* c, const double* X, int n, const double* Pm, int S, double* out, cudaStream_t st) {
+    constexpr int DIM = 1 << Q, TEAM = DIM >> 3;
+    const int n_gates = (int)c->gates.size(), n_passes = (int)c->passes.size();
+    const int n_mats = (int)c->mats.size(), n_mat_gates = (int)c->mat_gates.size();
+    const size_t fixed = ((sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvPass) * n_passes + 15) & ~size_t(15)) +
+                         ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvMat) * n_mats + sizeof(int) * n_mat_gates + 15) & ~size_t(15));
+    const size_t smem = fixed + sizeof(double2) * (DIM + n_gates + 4 * n_mats) + sizeof(double) * (((c->d + 1) & ~1) + 9 * (TEAM / 32));
+    DQGP_REQUIRE(smem <= 227 * 1024, "statevector kernel needs %zu bytes of shared memory (q=%d, %d gates)", smem, Q, n_gates);
+    auto kern = statevec_block_kernel<Q, WANT_STATES>;
+    DQGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TEAM, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)S * n;
+    const long long cap = (long long)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) return 0;
+    kern<<<(unsigned)blocks, TEAM, smem, st>>>(c->d_gates, n_gates, c->d_passes, n_passes, c->d_ops, c->d_mats, n_mats, c->d_mat_gates,
+                                              n_mat_gates, c->d, c->P, c->uses_acos ? 1 : 0, X, n, Pm, S, out);
+    DQGP_LAUNCH_CHECK("statevec_block_kernel");
+    return 0;
+}
+
 template <int Q, bool WANT_STATES>
 static int launch_sv(const dqgp_circuit* c, const double* X, int n, const double* Pm, int S, double* out, cudaStream_t st) {
     using G = SvGeom<Q>;
@@ -341,7 +488,10 @@ static int dispatch_sv(const dqgp_circuit* c, const double* X, int n, const doub
     switch (c->q) {
 #define DQGP_SV_CASE(QQ) case QQ: return launch_sv<QQ, WANT_STATES>(c, X, n, Pm, S, out, st);
         DQGP_SV_CASE(1) DQGP_SV_CASE(2) DQGP_SV_CASE(3) DQGP_SV_CASE(4) DQGP_SV_CASE(5) DQGP_SV_CASE(6)
-        DQGP_SV_CASE(7) DQGP_SV_CASE(8) DQGP_SV_CASE(9) DQGP_SV_CASE(10) DQGP_SV_CASE(11) DQGP_SV_CASE(12)
+        DQGP_SV_CASE(7) DQGP_SV_CASE(8)
+#undef DQGP_SV_CASE
+#define DQGP_SV_CASE(QQ) case QQ: return launch_sv_block<QQ, WANT_STATES>(c, X, n, Pm, S, out, st);
+        DQGP_SV_CASE(9) DQGP_SV_CASE(10) DQGP_SV_CASE(11) DQGP_SV_CASE(12)
 #undef DQGP_SV_CASE
     }
     set_error("statevector: unsupported qubit count %d", c->q);

@@ -108,12 +108,15 @@ class AgentEngine:
         self.d_Y.copy_(torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)).pin_memory(), non_blocking=True)
 
     # -- phases (each enqueues on the current stream) ----------------------------------------------------------
-    def simulate(self, d_z):
+    def simulate(self, d_z, first=0, count=None):
+        """Parameter sets (all 2P+1, always) + statevector features/states of sets [first, first+count)."""
         lib, st = self._lib, stream_ptr()
-        check(lib.dqgp_shift_parameter_sets(d_z.data_ptr(), self.P, self.h, PERIOD, self.d_Pm.data_ptr(), st), "shift sets")
+        if first == 0:
+            check(lib.dqgp_shift_parameter_sets(d_z.data_ptr(), self.P, self.h, PERIOD, self.d_Pm.data_ptr(), st), "shift sets")
+        count = self.S - first if count is None else count
         fn = lib.dqgp_features if self.kernel_type == "projected" else lib.dqgp_states
-        check(fn(self.circuit.handle, self.d_X.data_ptr(), self.n, self.d_Pm.data_ptr(), self.S, self.d_feat.data_ptr(), st),
-              "statevector")
+        check(fn(self.circuit.handle, self.d_X.data_ptr(), self.n, self.d_Pm[first].data_ptr(), count,
+                 self.d_feat[first].data_ptr(), st), "statevector")
 
     def gram(self):
         lib, st, s = self._lib, stream_ptr(), self.solver
@@ -148,6 +151,8 @@ class AgentEngine:
                                         PERIOD, d_theta_out.data_ptr(), d_psi_out.data_ptr(), stream_ptr()), "admm local")
 
     def step(self, d_z, d_psi, d_theta_out, d_psi_out):
+        # (Running the 2P shifted simulations on a side stream to overlap the factorisation was measured and
+        #  gives nothing: the GEMM CTAs hold every register of an SM, and both kernels want the same FP64 pipe.)
         self.simulate(d_z)
         self.gram()
         self.factor()

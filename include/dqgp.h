@@ -58,6 +58,7 @@ void dqgp_circuit_destroy(dqgp_circuit* c);
 int dqgp_circuit_num_parameters(const dqgp_circuit* c); /* = encoding_circuit.num_parameters (main.py:199) */
 int dqgp_circuit_num_gates(const dqgp_circuit* c);
 int dqgp_circuit_num_passes(const dqgp_circuit* c); /* shared-memory passes of the register-blocked simulator */
+int dqgp_circuit_num_fused_ops(const dqgp_circuit* c); /* ops after fusing runs of 1-qubit gates (2x2 unitaries + CX/CRZ) */
 int dqgp_circuit_describe(const dqgp_circuit* c, dqgp_gate* h_out, int capacity); /* host copy of the program */
 
 /* ---- statevector simulation (what q_kernel.evaluate does per sample, agent_riemannian.py:118):
