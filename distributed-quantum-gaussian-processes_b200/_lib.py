@@ -43,6 +43,7 @@ SIGNATURES = {
     "dqgp_gram_projected": (_i, [_i, _dp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "dqgp_gram_fidelity": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "dqgp_solver_create": (_i, [_i, C.POINTER(_vp)]),
+    "dqgp_solver_create_ex": (_i, [_i, _i, C.POINTER(_vp)]),
     "dqgp_solver_destroy": (None, [_vp]),
     "dqgp_solver_n": (_i, [_vp]),
     "dqgp_solver_ld": (_i, [_vp]),

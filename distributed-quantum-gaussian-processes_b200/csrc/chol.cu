@@ -23,7 +23,9 @@ struct dqgp_solver {
     dqgp::GemmTask* d_tasks;
     // launch groups: [first task, task count, tiles]
     struct Group { int first, count, tiles; };
-    std::vector<Group> trsm, syrk_panel, syrk_rest;   // per potrf step (trailing update split for look-ahead)
+    std::vector<Group> trsm, inner;                   // per 128-column step: panel solve, update inside the outer panel
+    std::vector<Group> syrk_next, syrk_rest;          // per outer panel (512 columns): next panel's columns / the bulk
+    int ob;                                           // outer panel width in 128-blocks (1 = single-level)
     cudaStream_t helper;                              // HIGH-priority stream carrying the critical path (leaf, panel solve, next column)
     cudaEvent_t ev_fork, ev_join;
     std::vector<cudaEvent_t> ev_trsm, ev_rest;
@@ -305,13 +307,16 @@ static GemmTask make_task(const double* A, const double* B, double* C, int M, in
 
 extern "C" {
 
-int dqgp_solver_create(int n, dqgp_solver** out) {
+int dqgp_solver_create(int n, dqgp_solver** out) { return dqgp_solver_create_ex(n, 0, out); }
+
+int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
     using namespace dqgp;
     DQGP_REQUIRE(out != nullptr, "dqgp_solver_create: out is NULL");
     *out = nullptr;
     DQGP_REQUIRE(n >= 1 && n <= (1 << 17), "dqgp_solver_create: n = %d outside [1, 131072]", n);
     dqgp_solver* s = new dqgp_solver();
     s->n = n;
+    s->ob = outer_blocks > 0 ? (outer_blocks > 16 ? 16 : outer_blocks) : 4;
     s->nblk = (n + NB - 1) / NB;
     s->np = s->nblk * NB;
     s->ld = s->np;
@@ -342,19 +347,31 @@ int dqgp_solver_create(int n, dqgp_solver** out) {
     const int ld = s->ld, np = s->np, nblk = s->nblk;
     auto at = [&](double* base, int rb, int cb) { return base + (size_t)rb * NB * ld + (size_t)cb * NB; };
     std::vector<GemmTask> grp;
-    // potrf steps
+    // potrf: two-level blocking.  Outer panels of OB = 4 block columns (512); inside a panel the 128-wide steps
+    // update only the panel's own columns (K = 128, little work); the trailing matrix gets ONE rank-512 update per
+    // outer panel (K = 512: the GEMM runs near its long-K efficiency instead of the 60% of K = 128 updates).
+    const int OB = s->ob;
     for (int k = 0; k + 1 < nblk; ++k) {
         const int rest = np - (k + 1) * NB;
         // panel solve out of place (A -> T): two 64-column tiles share the same input rows, so in place would race;
         // the strictly-lower blocks of L are copied back T -> A once, after the last step
         grp.push_back(make_task(at(s->A, k + 1, k), at(s->W, k, k), at(s->T, k + 1, k), rest, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
         s->trsm.push_back(push_group(grp));
-        // trailing update, split: block column k+1 first (critical path: next leaf + panel solve need it) ...
-        grp.push_back(make_task(at(s->T, k + 1, k), at(s->T, k + 1, k), at(s->A, k + 1, k + 1), rest, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
-        s->syrk_panel.push_back(push_group(grp));
-        // ... and the rest (columns k+2..) on the helper stream, overlapping the next leaf / panel solve
-        if (rest > NB)
-            grp.push_back(make_task(at(s->T, k + 2, k), at(s->T, k + 2, k), at(s->A, k + 2, k + 2), rest - NB, rest - NB, NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
+        const int pend = std::min(((k / OB) + 1) * OB, nblk);     // first block column after this outer panel
+        for (int c = k + 1; c < pend; ++c)                         // block column c of the panel, rows c..end
+            grp.push_back(make_task(at(s->T, c, k), at(s->T, c, k), at(s->A, c, c), np - c * NB, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+        s->inner.push_back(push_group(grp));
+    }
+    for (int p0 = 0; p0 < nblk; p0 += OB) {
+        const int w = std::min(OB, nblk - p0);                    // panel width in blocks
+        const int c0 = p0 + w;                                    // first trailing block column
+        const int wn = std::min(OB, nblk - c0);                   // width of the next panel
+        if (wn > 0)   // columns of the next outer panel, all rows below: on the critical path
+            grp.push_back(make_task(at(s->T, c0, p0), at(s->T, c0, p0), at(s->A, c0, c0), np - c0 * NB, wn * NB, w * NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+        s->syrk_next.push_back(push_group(grp));
+        const int c1 = c0 + wn;
+        if (wn > 0 && c1 < nblk)   // everything further right: the bulk, overlapped with the next panel's factorisation
+            grp.push_back(make_task(at(s->T, c1, p0), at(s->T, c1, p0), at(s->A, c1, c1), np - c1 * NB, np - c1 * NB, w * NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
         s->syrk_rest.push_back(push_group(grp));
     }
     // trtri levels: spans of `span` blocks are already inverted; join neighbours pairwise
@@ -390,7 +407,7 @@ int dqgp_solver_create(int n, dqgp_solver** out) {
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
-    for (int k = 0; k + 1 < nblk && e == cudaSuccess; ++k) {
+    for (int k = 0; k < (nblk + s->ob - 1) / s->ob && e == cudaSuccess; ++k) {
         cudaEvent_t a, b;
         e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
@@ -430,31 +447,37 @@ int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, dou
     pad_vector_kernel<<<(np + 255) / 256, 256, 0, st>>>(d_y, s->n, np, s->y_pad, d_logdet, d_info);
     if (np != s->n) pad_identity_kernel<<<np, 256, 0, st>>>(s->A, s->n, np, ld);
     DQGP_LAUNCH_CHECK("pad kernels");
-    // Right-looking Cholesky with one step of look-ahead.  The critical path leaf(k) -> panel solve(k) -> update of
-    // block column k+1 runs on the solver's HIGH-priority stream; the bulk of update k (columns k+2..) stays on the
-    // caller's stream and overlaps the next leaf / panel solve.  Priority matters: a leaf CTA needs 133 KB of shared
+    // Two-level right-looking Cholesky with look-ahead.  The critical path (leaves, panel solves, updates inside the
+    // current 512-column outer panel, and the rank-512 update of the NEXT panel's columns) runs on the solver's
+    // HIGH-priority stream; the bulk rank-512 update of everything further right stays on the caller's stream and
+    // overlaps the next panel's factorisation.  Priority matters: a leaf CTA needs 133 KB of shared
     // memory and only fits beside ONE resident GEMM CTA, so it must win the slot a retiring GEMM CTA frees.
     cudaStream_t crit = s->helper;
     DQGP_CUDA(cudaEventRecord(s->ev_fork, st));
     DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_fork, 0));
     int last_rest = -1;
+    const int OB = s->ob;
     for (int k = 0; k < nblk; ++k) {
         potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, crit>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
         DQGP_LAUNCH_CHECK("potrf_leaf_kernel");
-        if (k + 1 < nblk) {
-            int rc = launch_gemm_group(s->d_tasks + s->trsm[k].first, s->trsm[k].count, s->trsm[k].tiles, crit);
-            if (rc) return rc;
-            const bool has_rest = s->syrk_rest[k].tiles > 0;
-            if (has_rest) DQGP_CUDA(cudaEventRecord(s->ev_trsm[k], crit));
-            if (last_rest >= 0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_rest[last_rest], 0));   // column k+1 got rest(j<k)
-            rc = launch_gemm_group(s->d_tasks + s->syrk_panel[k].first, s->syrk_panel[k].count, s->syrk_panel[k].tiles, crit);
+        if (k + 1 >= nblk) break;
+        int rc = launch_gemm_group(s->d_tasks + s->trsm[k].first, s->trsm[k].count, s->trsm[k].tiles, crit);
+        if (rc) return rc;
+        rc = launch_gemm_group(s->d_tasks + s->inner[k].first, s->inner[k].count, s->inner[k].tiles, crit);
+        if (rc) return rc;
+        if ((k + 1) % OB == 0) {                       // an outer panel is complete: rank-(OB*128) trailing update
+            const int p = k / OB;
+            const bool has_rest = s->syrk_rest[p].tiles > 0;
+            if (has_rest) DQGP_CUDA(cudaEventRecord(s->ev_trsm[p], crit));
+            if (last_rest >= 0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_rest[last_rest], 0));   // earlier bulk updates hit these columns
+            rc = launch_gemm_group(s->d_tasks + s->syrk_next[p].first, s->syrk_next[p].count, s->syrk_next[p].tiles, crit);
             if (rc) return rc;
             if (has_rest) {
-                DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_trsm[k], 0));
-                rc = launch_gemm_group(s->d_tasks + s->syrk_rest[k].first, s->syrk_rest[k].count, s->syrk_rest[k].tiles, st);
+                DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_trsm[p], 0));
+                rc = launch_gemm_group(s->d_tasks + s->syrk_rest[p].first, s->syrk_rest[p].count, s->syrk_rest[p].tiles, st);
                 if (rc) return rc;
-                DQGP_CUDA(cudaEventRecord(s->ev_rest[k], st));
-                last_rest = k;
+                DQGP_CUDA(cudaEventRecord(s->ev_rest[p], st));
+                last_rest = p;
             }
         }
     }

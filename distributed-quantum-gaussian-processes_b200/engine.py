@@ -37,10 +37,10 @@ class _DeviceMatrix:
 class Solver:
     """``dqgp_solver`` handle: padded fp64 workspace + task tables for Cholesky / inverse / solve."""
 
-    def __init__(self, n):
+    def __init__(self, n, outer_blocks=0):
         self._lib = _lib.load()
         h = C.c_void_p()
-        check(self._lib.dqgp_solver_create(int(n), C.byref(h)), "dqgp_solver_create")
+        check(self._lib.dqgp_solver_create_ex(int(n), int(outer_blocks), C.byref(h)), "dqgp_solver_create")
         self.handle, self.n = h, int(n)
         self.ld = self._lib.dqgp_solver_ld(h)
         self.matrix_ptr = self._lib.dqgp_solver_matrix(h)
@@ -66,7 +66,7 @@ class Solver:
 
 class AgentEngine:
     def __init__(self, X, Y, *, encoding_type, kernel_type, num_qubits, num_layers, noise_std, rho, L,
-                 outer_kernel="gaussian", shift_value=np.pi / 8, training_ignores_outer_kernel=True):
+                 outer_kernel="gaussian", shift_value=np.pi / 8, training_ignores_outer_kernel=True, cholesky_outer_blocks=0):
         _require_cuda()
         self._lib = _lib.load()
         X = np.asarray(X, dtype=np.float64)
@@ -91,7 +91,7 @@ class AgentEngine:
         self.m = 3 * self.q if kernel_type == "projected" else 2 * (1 << self.q)   # doubles per sample per set
         self.d_Pm = torch.empty((self.S, self.P), **f64)
         self.d_feat = torch.empty((self.S, self.n, self.m), **f64)
-        self.solver = Solver(self.n)
+        self.solver = Solver(self.n, cholesky_outer_blocks)
         self.d_alpha = torch.empty(self.n, **f64)
         self.d_logdet = torch.zeros(1, **f64)
         self.d_info = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -212,6 +212,8 @@ class AdmmEngine:
         self.first = block.start
         self.rho = float(rho)
         lips = L if np.ndim(L) else [L] * self.A_total
+        # one agent per GPU: latency matters -> single-level Cholesky panels; several: throughput -> rank-512 updates
+        agent_kw.setdefault("cholesky_outer_blocks", 1 if self.A_local == 1 else 4)
         self.agents = [AgentEngine(x, y, rho=rho, L=lips[self.first + i], **agent_kw) for i, (x, y) in enumerate(shards)]
         if any(a.P != self.P for a in self.agents):
             raise ValueError("theta0 does not match the circuit's parameter count")

@@ -83,6 +83,9 @@ int dqgp_gram_fidelity(const double* d_Psi1, int n1, const double* d_Psi2, int n
  *      *d_info = 0 ok, j>0 = first non-positive pivot (1-based) so the host can mirror the
  *      reference's LU -> pinv ladder (agent_riemannian.py:419-428) or raise. */
 int dqgp_solver_create(int n, dqgp_solver** out);
+/* outer_blocks: width of the outer Cholesky panel in 128-column blocks. 4 (default, = 0) gives rank-512 trailing
+ * updates (best throughput when several agents share a GPU); 1 is the shortest critical path (one agent per GPU). */
+int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out);
 void dqgp_solver_destroy(dqgp_solver* s);
 int dqgp_solver_n(const dqgp_solver* s);
 int dqgp_solver_ld(const dqgp_solver* s);
