@@ -40,6 +40,8 @@ SIGNATURES = {
     "dqgp_circuit_describe": (_i, [_vp, C.POINTER(Gate), _i]),
     "dqgp_features": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "dqgp_states": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "dqgp_features_shifted": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "dqgp_states_shifted": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "dqgp_gram_projected": (_i, [_i, _dp, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "dqgp_gram_fidelity": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "dqgp_solver_create": (_i, [_i, C.POINTER(_vp)]),

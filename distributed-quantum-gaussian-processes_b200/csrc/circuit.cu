@@ -185,6 +185,34 @@ static void build_plan(dqgp_circuit& c) {
         m.g_end = (int)c.mat_gates.size();
         c.mats.push_back(m);
     }
+    // where does each parameter enter?  (gate -> fused matrix / CRZ op -> pass)
+    const int P = c.P;
+    std::vector<int> uses(P, 0), gate_mat(n, -1), gate_pass(n, -1);
+    c.par_gate.assign(P, -1);
+    for (int g = 0; g < n; ++g)
+        if (c.gates[g].pidx >= 0) { ++uses[c.gates[g].pidx]; c.par_gate[c.gates[g].pidx] = g; }
+    c.shareable = P > 0;
+    for (int i = 0; i < P; ++i) c.shareable = c.shareable && uses[i] == 1;
+    for (int ip = 0; ip < (int)c.passes.size(); ++ip)
+        for (int o = c.passes[ip].op_begin; o < c.passes[ip].op_end; ++o) {
+            const SvOp& op = c.ops[o];
+            if (op.kind == SV_U2) {
+                for (int e = c.mats[op.idx].g_begin; e < c.mats[op.idx].g_end; ++e) { gate_mat[c.mat_gates[e]] = op.idx; gate_pass[c.mat_gates[e]] = ip; }
+            } else {
+                gate_pass[op.idx] = ip;
+            }
+        }
+    c.par_mat.assign(P, -1);
+    c.pass_par_begin.assign(c.passes.size() + 1, 0);
+    if (c.shareable) {
+        for (int i = 0; i < P; ++i) c.par_mat[i] = gate_mat[c.par_gate[i]];
+        for (int ip = 0; ip < (int)c.passes.size(); ++ip) {
+            c.pass_par_begin[ip] = (int)c.pass_params.size();
+            for (int i = 0; i < P; ++i)
+                if (gate_pass[c.par_gate[i]] == ip) c.pass_params.push_back(i);
+        }
+        c.pass_par_begin[c.passes.size()] = (int)c.pass_params.size();
+    }
 }
 
 static std::mutex g_upload_mutex;
@@ -205,6 +233,15 @@ int circuit_on_device(const dqgp_circuit* cc) {
     DQGP_CUDA(cudaMemcpy(c->d_mats, c->mats.data(), sizeof(SvMat) * c->mats.size(), cudaMemcpyHostToDevice));
     DQGP_CUDA(cudaMalloc(&c->d_mat_gates, sizeof(int) * (c->mat_gates.size() + 1)));
     DQGP_CUDA(cudaMemcpy(c->d_mat_gates, c->mat_gates.data(), sizeof(int) * c->mat_gates.size(), cudaMemcpyHostToDevice));
+    if (c->shareable) {
+        std::vector<int> pack;
+        pack.insert(pack.end(), c->par_gate.begin(), c->par_gate.end());
+        pack.insert(pack.end(), c->par_mat.begin(), c->par_mat.end());
+        pack.insert(pack.end(), c->pass_par_begin.begin(), c->pass_par_begin.end());
+        pack.insert(pack.end(), c->pass_params.begin(), c->pass_params.end());
+        DQGP_CUDA(cudaMalloc(&c->d_share, sizeof(int) * pack.size()));
+        DQGP_CUDA(cudaMemcpy(c->d_share, pack.data(), sizeof(int) * pack.size(), cudaMemcpyHostToDevice));
+    }
     c->device = dev;
     return 0;
 }
@@ -226,7 +263,7 @@ int dqgp_circuit_create(int encoding, int num_qubits, int num_features, int num_
     dqgp_circuit* c = new dqgp_circuit();
     c->encoding = encoding; c->q = num_qubits; c->d = num_features; c->layers = num_layers;
     c->P = dqgp::count_parameters(encoding, num_qubits, num_layers);
-    c->uses_acos = false; c->d_gates = nullptr; c->d_passes = nullptr; c->d_ops = nullptr; c->d_mats = nullptr; c->d_mat_gates = nullptr;
+    c->uses_acos = false; c->d_gates = nullptr; c->d_passes = nullptr; c->d_ops = nullptr; c->d_mats = nullptr; c->d_mat_gates = nullptr; c->d_share = nullptr; c->shareable = false;
     dqgp::build(*c);
     dqgp::build_plan(*c);
     c->device = -1;
@@ -240,6 +277,7 @@ void dqgp_circuit_destroy(dqgp_circuit* c) {
     if (c->d_ops) cudaFree(c->d_ops);
     if (c->d_mats) cudaFree(c->d_mats);
     if (c->d_mat_gates) cudaFree(c->d_mat_gates);
+    if (c->d_share) cudaFree(c->d_share);
     delete c;
 }
 int dqgp_circuit_num_parameters(const dqgp_circuit* c) { return c ? c->P : -1; }

@@ -90,6 +90,13 @@ struct dqgp_circuit {
     std::vector<SvOp> ops;
     std::vector<SvMat> mats;
     std::vector<int> mat_gates;
+    // prefix sharing across the 2P+1 central-difference sets: where each parameter enters the plan
+    bool shareable;                 // every parameter is used by exactly one gate
+    std::vector<int> par_gate;      // [P] gate using parameter i
+    std::vector<int> par_mat;       // [P] fused matrix containing that gate, or -1 (CRZ)
+    std::vector<int> pass_par_begin;// [n_passes+1] ranges into pass_params
+    std::vector<int> pass_params;   // [P] parameters ordered by the pass their op belongs to
+    int* d_share;                   // device copy: par_gate | par_mat | pass_par_begin | pass_params
     dqgp_gate* d_gates;            // device copies
     SvPass* d_passes;
     SvOp* d_ops;

@@ -78,15 +78,22 @@ __device__ __forceinline__ void apply_controlled(double2 (&r)[N], int kind, int 
     }
 }
 
+// one shifted parameter: either a replacement for fused matrix `mat`, or replacement cos/sin for CRZ gate `gate`
+struct SvAlt {
+    int mat;            // fused-matrix index replaced by u[0..3], or -1
+    int gate;           // CRZ gate index whose (cos, sin) is u[0], or -1
+    const double2* u;
+};
+
 template <int N, int L>
 __device__ __forceinline__ void apply_op(double2 (&r)[N], const SvOp op, int base, const double2* __restrict__ mats,
-                                         const double2* __restrict__ trig) {
+                                         const double2* __restrict__ trig, const SvAlt& alt) {
     if (op.kind == SV_U2) {
-        const double2* u = mats + 4 * op.idx;
+        const double2* u = (op.idx == alt.mat) ? alt.u : mats + 4 * op.idx;
         apply_u2<N, L>(r, u[0], u[1], u[2], u[3]);
     } else {
         const bool ext = (op.cq >= 0) ? (((base >> op.cq) & 1) != 0) : false;
-        const double2 cs = (op.kind == SV_CRZ) ? trig[op.idx] : make_double2(1.0, 0.0);
+        const double2 cs = (op.kind == SV_CRZ) ? ((op.idx == alt.gate) ? alt.u[0] : trig[op.idx]) : make_double2(1.0, 0.0);
         apply_controlled<N, L>(r, op.kind, op.cloc, ext, cs.x, cs.y);
     }
 }
@@ -94,7 +101,7 @@ __device__ __forceinline__ void apply_op(double2 (&r)[N], const SvOp op, int bas
 template <int B>
 __device__ __forceinline__ void run_pass(double2* __restrict__ amp, const SvPass& ps, const SvOp* __restrict__ ops,
                                          const double2* __restrict__ mats, const double2* __restrict__ trig, int lig, int lps,
-                                         int groups) {
+                                         int groups, const SvAlt alt = SvAlt{-1, -1, nullptr}) {
     constexpr int N = 1 << B;
     const int q0 = ps.q[0], q1 = ps.q[1], q2 = ps.q[2];
     int off[N];
@@ -110,9 +117,9 @@ __device__ __forceinline__ void run_pass(double2* __restrict__ amp, const SvPass
 #pragma unroll 1
         for (int o = ps.op_begin; o < ps.op_end; ++o) {
             const SvOp op = ops[o];
-            if (op.lbit == 0) apply_op<N, 0>(r, op, base, mats, trig);
-            else if (B > 1 && op.lbit == 1) apply_op<N, (B > 1 ? 1 : 0)>(r, op, base, mats, trig);
-            else if (B > 2) apply_op<N, (B > 2 ? 2 : 0)>(r, op, base, mats, trig);
+            if (op.lbit == 0) apply_op<N, 0>(r, op, base, mats, trig, alt);
+            else if (B > 1 && op.lbit == 1) apply_op<N, (B > 1 ? 1 : 0)>(r, op, base, mats, trig, alt);
+            else if (B > 2) apply_op<N, (B > 2 ? 2 : 0)>(r, op, base, mats, trig, alt);
         }
 #pragma unroll
         for (int j = 0; j < N; ++j) amp[sv_phys(base + off[j])] = r[j];
@@ -421,6 +428,228 @@ __global__ void __launch_bounds__(((1 << Q) >> 3)) statevec_block_kernel(const d
     }
 }
 
+// ---- all 2P+1 central-difference parameter sets of one sample with PREFIX SHARING ---------------------------------
+// Set s = 1+2i+sg differs from the base set only in parameter i, i.e. in ONE fused matrix (or one CRZ angle) of the
+// plan.  A team (lane group / warp for q <= 8, CTA for q >= 9) owns one sample: it advances the base state pass by pass
+// and, before executing pass p, forks every parameter whose op lives in pass p: copy base -> scratch, run passes p..end
+// with the replaced matrix, reduce the features.  Work drops from (2P+1) full circuits to 1 + sum_i 2*(suffix of i):
+// ~1.6x fewer pass executions for config 4, ~1.8x for config 5 — and results are bit-identical to the per-set kernel.
+__device__ __forceinline__ double np_mod_d(double x, double p) {
+    double r = fmod(x, p);
+    if (r != 0.0) { if ((p < 0.0) != (r < 0.0)) r += p; } else r = copysign(0.0, p);
+    return r;
+}
+
+__device__ __forceinline__ double gate_angle(const dqgp_gate& gt, double pval, const double* __restrict__ x, const double* __restrict__ acx) {
+    switch (gt.form) {
+        case DQGP_A_P: return pval;
+        case DQGP_A_X: return x[gt.fidx];
+        case DQGP_A_P_PLUS_CX: return pval + gt.coef * x[gt.fidx];
+        case DQGP_A_P_TIMES_ACOS: return pval * acx[gt.fidx];
+        case DQGP_A_C_TIMES_ACOS: return gt.coef * acx[gt.fidx];
+        default: return 0.0;
+    }
+}
+
+// compose fused matrix f from the cos/sin table, with gate `g_alt` (if >= 0) using `cs_alt` instead of its table entry
+__device__ __forceinline__ void compose_matrix(const SvMat mt, const int* __restrict__ s_mat_gates, const dqgp_gate* __restrict__ s_gates,
+                                               const double2* __restrict__ trig, int g_alt, double2 cs_alt, double2* __restrict__ dst) {
+    double2 mm[4];
+    {
+        const int g0 = s_mat_gates[mt.g_begin];
+        const double2 cs = (g0 == g_alt) ? cs_alt : trig[g0];
+        gate_matrix(s_gates[g0].kind, cs.x, cs.y, mm);
+    }
+    for (int e = mt.g_begin + 1; e < mt.g_end; ++e) {
+        const int g = s_mat_gates[e];
+        const double2 cs = (g == g_alt) ? cs_alt : trig[g];
+        double2 gg[4];
+        gate_matrix(s_gates[g].kind, cs.x, cs.y, gg);
+        const double2 n0 = cadd(cmul(gg[0], mm[0]), cmul(gg[1], mm[2]));
+        const double2 n1 = cadd(cmul(gg[0], mm[1]), cmul(gg[1], mm[3]));
+        const double2 n2 = cadd(cmul(gg[2], mm[0]), cmul(gg[3], mm[2]));
+        const double2 n3 = cadd(cmul(gg[2], mm[1]), cmul(gg[3], mm[3]));
+        mm[0] = n0; mm[1] = n1; mm[2] = n2; mm[3] = n3;
+    }
+    dst[0] = mm[0]; dst[1] = mm[1]; dst[2] = mm[2]; dst[3] = mm[3];
+}
+
+template <int Q>
+struct SvTeam {
+    static constexpr bool BLOCK = Q >= 9;
+    static constexpr int DIM = 1 << Q;
+    static constexpr int SIZE = BLOCK ? (DIM >> 3) : SvGeom<Q>::LPS;      // threads cooperating on one sample
+    static constexpr int PER_WARP = BLOCK ? 1 : SvGeom<Q>::SPW;           // samples per warp (lane-group teams)
+    static constexpr int SLOTS = SIZE < 32 ? SIZE : 32;                   // forks whose matrices are prepared together
+    static constexpr int THREADS = BLOCK ? SIZE : 128;
+    __device__ static __forceinline__ void sync() { if (BLOCK) __syncthreads(); else __syncwarp(); }
+};
+
+template <int Q, bool WANT_STATES>
+__device__ __forceinline__ void sv_emit(const double2* __restrict__ amp, int lig, bool live, double* __restrict__ out, long long row,
+                                        double* __restrict__ red) {
+    using T = SvTeam<Q>;
+    if (WANT_STATES) {
+        if (live) {
+            double2* dst = reinterpret_cast<double2*>(out) + (size_t)row * T::DIM;
+            for (int i = lig; i < T::DIM; i += T::SIZE) dst[i] = amp[sv_phys(i)];
+        }
+    } else {
+        double* dst = out + (size_t)row * (3 * Q);
+        constexpr int FULL = Q / 3, REM = Q % 3;
+#pragma unroll 1
+        for (int b = 0; b < FULL; ++b) features_block<(Q >= 3 ? 3 : 1), Q>(amp, 3 * b, lig, T::SIZE, live, dst, red);
+        if (REM == 2) features_block<(Q >= 2 ? 2 : 1), Q>(amp, 3 * FULL, lig, T::SIZE, live, dst, red);
+        if (REM == 1) features_block<1, Q>(amp, 3 * FULL, lig, T::SIZE, live, dst, red);
+    }
+}
+
+template <int Q>
+__device__ __forceinline__ void sv_run_passes(double2* __restrict__ amp, const SvPass* __restrict__ s_passes, int p_from, int n_passes,
+                                              const SvOp* __restrict__ s_ops, const double2* __restrict__ u2, const double2* __restrict__ trig,
+                                              int lig, const SvAlt alt, int only_one) {
+    using T = SvTeam<Q>;
+    const int p_to = only_one ? p_from + 1 : n_passes;
+    for (int ip = p_from; ip < p_to; ++ip) {
+        const SvPass ps = s_passes[ip];
+        if (ps.nq == 3) run_pass<(Q >= 3 ? 3 : 1)>(amp, ps, s_ops, u2, trig, lig, T::SIZE, T::DIM >> 3, alt);
+        else if (ps.nq == 2) run_pass<(Q >= 2 ? 2 : 1)>(amp, ps, s_ops, u2, trig, lig, T::SIZE, T::DIM >> 2, alt);
+        else run_pass<1>(amp, ps, s_ops, u2, trig, lig, T::SIZE, T::DIM >> 1, alt);
+        T::sync();
+    }
+}
+
+template <int Q, bool WANT_STATES>
+__global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_shared_kernel(
+    const dqgp_gate* __restrict__ gates, int n_gates, const SvPass* __restrict__ passes, int n_passes, const SvOp* __restrict__ ops,
+    const SvMat* __restrict__ mats, int n_mats, const int* __restrict__ mat_gates, int n_mat_gates, const int* __restrict__ share,
+    int d, int P, int uses_acos, const double* __restrict__ X, int n, const double* __restrict__ Pm, double* __restrict__ out) {
+    using T = SvTeam<Q>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t gate_bytes = (sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15);
+    const size_t pass_bytes = (sizeof(SvPass) * n_passes + 15) & ~size_t(15);
+    const size_t op_bytes = (sizeof(SvOp) * n_gates + 15) & ~size_t(15);
+    const size_t mat_bytes = (sizeof(SvMat) * n_mats + sizeof(int) * n_mat_gates + 15) & ~size_t(15);
+    const int n_share = 2 * P + n_passes + 1 + P;
+    const size_t share_bytes = (sizeof(int) * n_share + 15) & ~size_t(15);
+    dqgp_gate* s_gates = reinterpret_cast<dqgp_gate*>(smem_raw);
+    SvPass* s_passes = reinterpret_cast<SvPass*>(smem_raw + gate_bytes);
+    SvOp* s_ops = reinterpret_cast<SvOp*>(smem_raw + gate_bytes + pass_bytes);
+    SvMat* s_mats = reinterpret_cast<SvMat*>(smem_raw + gate_bytes + pass_bytes + op_bytes);
+    int* s_mat_gates = reinterpret_cast<int*>(s_mats + n_mats);
+    int* s_share = reinterpret_cast<int*>(smem_raw + gate_bytes + pass_bytes + op_bytes + mat_bytes);
+    const int* par_gate = s_share;
+    const int* par_mat = s_share + P;
+    const int* pass_par_begin = s_share + 2 * P;
+    const int* pass_params = s_share + 2 * P + n_passes + 1;
+    for (int i = threadIdx.x; i < n_gates; i += blockDim.x) { s_gates[i] = gates[i]; s_ops[i] = ops[i]; }
+    for (int i = threadIdx.x; i < n_passes; i += blockDim.x) s_passes[i] = passes[i];
+    for (int i = threadIdx.x; i < n_mats; i += blockDim.x) s_mats[i] = mats[i];
+    for (int i = threadIdx.x; i < n_mat_gates; i += blockDim.x) s_mat_gates[i] = mat_gates[i];
+    for (int i = threadIdx.x; i < n_share; i += blockDim.x) s_share[i] = share[i];
+    __syncthreads();
+
+    // per-team storage: base amplitudes | scratch amplitudes | cos/sin table | fused matrices | fork matrices | acos | reduction
+    const size_t team_bytes = sizeof(double2) * (2 * T::DIM + n_gates + 4 * n_mats + 4 * T::SLOTS) +
+                              sizeof(double) * (((d + 1) & ~1) + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int team_in_block = T::BLOCK ? 0 : warp * T::PER_WARP + lane / T::SIZE;
+    const int lig = T::BLOCK ? threadIdx.x : lane % T::SIZE;
+    const int teams_per_block = T::BLOCK ? 1 : (blockDim.x >> 5) * T::PER_WARP;
+    unsigned char* my = smem_raw + gate_bytes + pass_bytes + op_bytes + mat_bytes + share_bytes + team_bytes * team_in_block;
+    double2* base = reinterpret_cast<double2*>(my);
+    double2* scr = base + T::DIM;
+    double2* trig = scr + T::DIM;
+    double2* u2 = trig + n_gates;
+    double2* altm = u2 + 4 * n_mats;
+    double* acx = reinterpret_cast<double*>(altm + 4 * T::SLOTS);
+    double* red = acx + ((d + 1) & ~1);
+    const SvAlt no_alt = SvAlt{-1, -1, nullptr};
+
+    // lane-group teams of one warp must iterate together (the plan is identical, only the data differ)
+    const long long n_rounds = (n + (long long)gridDim.x * teams_per_block - 1) / ((long long)gridDim.x * teams_per_block);
+    for (long long round = 0; round < n_rounds; ++round) {
+        long long j = (round * gridDim.x + blockIdx.x) * teams_per_block + team_in_block;
+        const bool live = j < n;
+        if (!live) j = n - 1;
+        const double* x = X + (size_t)j * d;
+        if (uses_acos) {
+            for (int f = lig; f < d; f += T::SIZE) acx[f] = acos(x[f]);
+            T::sync();
+        }
+        for (int g = lig; g < n_gates; g += T::SIZE) {
+            const dqgp_gate gt = s_gates[g];
+            if (gt.form == DQGP_A_NONE) continue;
+            double sn, cs;
+            sincos(0.5 * gate_angle(gt, gt.pidx >= 0 ? Pm[gt.pidx] : 0.0, x, acx), &sn, &cs);
+            trig[g] = make_double2(cs, sn);
+        }
+        for (int i = lig; i < T::DIM; i += T::SIZE) base[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0);
+        T::sync();
+        for (int f = lig; f < n_mats; f += T::SIZE) compose_matrix(s_mats[f], s_mat_gates, s_gates, trig, -1, make_double2(0, 0), u2 + 4 * f);
+        T::sync();
+
+        for (int ip = 0; ip < n_passes; ++ip) {
+            const int pb = pass_par_begin[ip], pe = pass_par_begin[ip + 1];
+            for (int f0 = 2 * pb; f0 < 2 * pe; f0 += T::SLOTS) {          // forks: (parameter, sign) pairs of this pass
+                const int cnt = min(T::SLOTS, 2 * pe - f0);
+                if (lig < cnt) {
+                    const int fk = f0 + lig, i = pass_params[fk >> 1], sg = fk & 1;
+                    const int g = par_gate[i];
+                    double sn, cs;
+                    sincos(0.5 * gate_angle(s_gates[g], Pm[(size_t)(1 + 2 * i + sg) * P + i], x, acx), &sn, &cs);
+                    if (par_mat[i] >= 0) compose_matrix(s_mats[par_mat[i]], s_mat_gates, s_gates, trig, g, make_double2(cs, sn), altm + 4 * lig);
+                    else altm[4 * lig] = make_double2(cs, sn);
+                }
+                T::sync();
+                for (int t = 0; t < cnt; ++t) {
+                    const int fk = f0 + t, i = pass_params[fk >> 1], sg = fk & 1;
+                    for (int a = lig; a < T::DIM; a += T::SIZE) scr[a] = base[a];
+                    T::sync();
+                    const SvAlt alt = SvAlt{par_mat[i], par_mat[i] >= 0 ? -1 : par_gate[i], altm + 4 * t};
+                    sv_run_passes<Q>(scr, s_passes, ip, n_passes, s_ops, u2, trig, lig, alt, 0);
+                    sv_emit<Q, WANT_STATES>(scr, lig, live, out, (long long)(1 + 2 * i + sg) * n + j, red);
+                    T::sync();
+                }
+            }
+            sv_run_passes<Q>(base, s_passes, ip, n_passes, s_ops, u2, trig, lig, no_alt, 1);
+        }
+        sv_emit<Q, WANT_STATES>(base, lig, live, out, j, red);
+        T::sync();
+    }
+}
+
+template <int Q, bool WANT_STATES>
+static int launch_sv_shared(const dqgp_circuit* c, const double* X, int n, const double* Pm, double* out, cudaStream_t st) {
+    using T = SvTeam<Q>;
+    const int n_gates = (int)c->gates.size(), n_passes = (int)c->passes.size();
+    const int n_mats = (int)c->mats.size(), n_mat_gates = (int)c->mat_gates.size();
+    const int n_share = 2 * c->P + n_passes + 1 + c->P;
+    const size_t fixed = ((sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvPass) * n_passes + 15) & ~size_t(15)) +
+                         ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvMat) * n_mats + sizeof(int) * n_mat_gates + 15) & ~size_t(15)) +
+                         ((sizeof(int) * n_share + 15) & ~size_t(15));
+    const size_t team_bytes = sizeof(double2) * (2 * T::DIM + n_gates + 4 * n_mats + 4 * T::SLOTS) +
+                              sizeof(double) * (((c->d + 1) & ~1) + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0));
+    int warps = T::BLOCK ? T::SIZE / 32 : 4;
+    int teams = T::BLOCK ? 1 : warps * T::PER_WARP;
+    while (!T::BLOCK && warps > 1 && fixed + team_bytes * teams > 100 * 1024) { warps >>= 1; teams = warps * T::PER_WARP; }
+    const size_t smem = fixed + team_bytes * teams;
+    DQGP_REQUIRE(smem <= 227 * 1024, "statevector kernel needs %zu bytes of shared memory (q=%d, %d gates)", smem, Q, n_gates);
+    auto kern = statevec_shared_kernel<Q, WANT_STATES>;
+    DQGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = ((long long)n + teams - 1) / teams;
+    const long long cap = (long long)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) return 0;
+    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d_passes, n_passes, c->d_ops, c->d_mats, n_mats, c->d_mat_gates,
+                                                     n_mat_gates, c->d_share, c->d, c->P, c->uses_acos ? 1 : 0, X, n, Pm, out);
+    DQGP_LAUNCH_CHECK("statevec_shared_kernel");
+    return 0;
+}
+
 template <int Q, bool WANT_STATES>
 static int launch_sv_block(const dqgp_circuit* c, const double* X, int n, const double* Pm, int S, double* out, cudaStream_t st) {
     constexpr int DIM = 1 << Q, TEAM = DIM >> 3;
@@ -498,9 +727,35 @@ static int dispatch_sv(const dqgp_circuit* c, const double* X, int n, const doub
     return -1;
 }
 
+template <bool WANT_STATES>
+static int dispatch_sv_shared(const dqgp_circuit* c, const double* X, int n, const double* Pm, int P, double* out, void* stream) {
+    DQGP_REQUIRE(n >= 0, "statevector: negative size");
+    if (n == 0) return 0;
+    DQGP_REQUIRE(c && X && Pm && out, "statevector: NULL argument");
+    DQGP_REQUIRE(P == c->P, "statevector: circuit has %d parameters, got %d", c->P, P);
+    if (!c->shareable) return dispatch_sv<WANT_STATES>(c, X, n, Pm, 2 * P + 1, out, stream);   // a parameter feeds several gates
+    int rc = circuit_on_device(c);
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    switch (c->q) {
+#define DQGP_SV_CASE(QQ) case QQ: return launch_sv_shared<QQ, WANT_STATES>(c, X, n, Pm, out, st);
+        DQGP_SV_CASE(1) DQGP_SV_CASE(2) DQGP_SV_CASE(3) DQGP_SV_CASE(4) DQGP_SV_CASE(5) DQGP_SV_CASE(6)
+        DQGP_SV_CASE(7) DQGP_SV_CASE(8) DQGP_SV_CASE(9) DQGP_SV_CASE(10) DQGP_SV_CASE(11) DQGP_SV_CASE(12)
+#undef DQGP_SV_CASE
+    }
+    set_error("statevector: unsupported qubit count %d", c->q);
+    return -1;
+}
+
 }  // namespace dqgp
 
 extern "C" {
+int dqgp_features_shifted(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int P, double* d_F, void* stream) {
+    return dqgp::dispatch_sv_shared<false>(c, d_X, n, d_Pm, P, d_F, stream);
+}
+int dqgp_states_shifted(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int P, double* d_Psi, void* stream) {
+    return dqgp::dispatch_sv_shared<true>(c, d_X, n, d_Pm, P, d_Psi, stream);
+}
 int dqgp_features(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int S, double* d_F, void* stream) {
     return dqgp::dispatch_sv<false>(c, d_X, n, d_Pm, S, d_F, stream);
 }

@@ -99,6 +99,7 @@ class AgentEngine:
         self.d_nll = torch.empty(4, **f64)
         self.d_work = torch.empty(max(1, self._lib.dqgp_grad_workspace_bytes(self.n, self.P) // 8), **f64)
         self.entries_per_step = self.S * self.n * self.n    # full squares, all 2P+1 sets
+        self.share_prefix = True
 
     def load_data(self, X, Y):
         """Refresh the resident shard from host arrays (the e2e path does this every call, like the
@@ -114,6 +115,12 @@ class AgentEngine:
         if first == 0:
             check(lib.dqgp_shift_parameter_sets(d_z.data_ptr(), self.P, self.h, PERIOD, self.d_Pm.data_ptr(), st), "shift sets")
         count = self.S - first if count is None else count
+        if first == 0 and count == self.S and self.share_prefix:
+            # all 2P+1 central-difference sets of a sample share the circuit prefix before the shifted gate
+            fn = lib.dqgp_features_shifted if self.kernel_type == "projected" else lib.dqgp_states_shifted
+            check(fn(self.circuit.handle, self.d_X.data_ptr(), self.n, self.d_Pm.data_ptr(), self.P, self.d_feat.data_ptr(), st),
+                  "statevector (shared prefix)")
+            return
         fn = lib.dqgp_features if self.kernel_type == "projected" else lib.dqgp_states
         check(fn(self.circuit.handle, self.d_X.data_ptr(), self.n, self.d_Pm[first].data_ptr(), count,
                  self.d_feat[first].data_ptr(), st), "statevector")

@@ -67,6 +67,12 @@ int dqgp_circuit_describe(const dqgp_circuit* c, dqgp_gate* h_out, int capacity)
 int dqgp_features(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int S, double* d_F, void* stream);
 int dqgp_states(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int S, double* d_Psi, void* stream);
 
+/* Same outputs for the 2P+1 central-difference sets of dqgp_shift_parameter_sets (d_Pm (2P+1,P): row 0 the base
+ * set, rows 1+2i / 2+2i differing from it in parameter i only), computed with prefix sharing: the part of the circuit
+ * that precedes the shifted gate is simulated once per sample.  Bit-identical to dqgp_features / dqgp_states. */
+int dqgp_features_shifted(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int P, double* d_F, void* stream);
+int dqgp_states_shifted(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int P, double* d_Psi, void* stream);
+
 /* ---- Gram matrices.  d_K (n1,n2) with leading dimension ldk (>= n2).
  *      projected: K = outer(f1_j, f2_k); hyp = {gamma} | {length_scale} | {length_scale, periodicity}
  *      (ProjectedQuantumKernel.evaluate, main.py:130-137);  fidelity: K = |<psi2_k|psi1_j>|^2

@@ -51,6 +51,30 @@ def test_features_and_states_match_oracle(d, enc, q, dd, layers):
         assert np.abs(F[s] - statevector.pauli_features(ref, q)).max() < 1e-12
 
 
+@pytest.mark.parametrize("enc,q,dd,layers", [("chebyshev", 3, 2, 1), ("chebyshev", 4, 2, 3), ("hubregtsen", 5, 2, 2), ("yz_cx", 8, 4, 3),
+                                            ("yz_cx", 1, 1, 2), ("kyriienko", 10, 6, 2), ("hubregtsen", 9, 3, 1), ("yz_cx", 6, 3, 2)])
+def test_shared_prefix_simulation_is_bit_identical(d, enc, q, dd, layers):
+    """dqgp_features_shifted / dqgp_states_shifted (prefix sharing over the 2P+1 central-difference sets) must equal
+    the per-set kernels bit for bit, including circuits whose parameters sit on CRZ gates."""
+    from oracle import agent_step, circuits
+    rng = np.random.default_rng(7 * q + dd)
+    n = 45
+    lo, hi = (-0.99, 0.99) if enc in ("chebyshev", "kyriienko") else (-2, 2)
+    x = rng.uniform(lo, hi, (n, dd))
+    P = circuits.num_parameters(enc, q, layers)
+    pm = agent_step.shifted_parameter_sets(np.round(rng.uniform(-0.5, 3.5, P), 4), np.pi / 8)
+    ec = d.EncodingCircuit(enc, q, dd, layers)
+    dx, dpm = d.kernels.dev_f64(x), d.kernels.dev_f64(pm)
+    lib = d.load()
+    F_ref, S_ref = ec.features(dx, dpm), ec.states(dx, dpm)
+    F = torch.full_like(F_ref, float("nan"))
+    S = torch.full_like(S_ref, float("nan"))
+    assert lib.dqgp_features_shifted(ec.handle, dx.data_ptr(), n, dpm.data_ptr(), P, F.data_ptr(), _sp()) == 0, lib.dqgp_last_error()
+    assert lib.dqgp_states_shifted(ec.handle, dx.data_ptr(), n, dpm.data_ptr(), P, S.data_ptr(), _sp()) == 0, lib.dqgp_last_error()
+    assert torch.equal(F, F_ref)
+    assert torch.equal(S, S_ref)
+
+
 def test_features_empty_and_single(d):
     ec = d.EncodingCircuit("yz_cx", 3, 2, 1)
     dx = d.kernels.dev_f64(np.zeros((0, 2)))
