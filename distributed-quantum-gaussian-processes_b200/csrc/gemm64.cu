@@ -69,9 +69,19 @@ __device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* 
         while (R * tm * (tm + 1) / 2 > local) --tm;
         tn = local - R * tm * (tm + 1) / 2;
     } else {
-        const int tiles_n = T.N / GM_BN;
-        tm = local / tiles_n;
-        tn = local - tm * tiles_n;
+        // full tile grid: enumerate so that tiles with the LONGEST contraction range come first (the triangular
+        // operands clip k per tile), otherwise the last wave is a few long tiles on an idle machine
+        const int tiles_n = T.N / GM_BN, tiles_m = T.M / GM_BM;
+        if (T.krule == GM_KRULE_B_LOWER) {          // k >= n0: long for small tn -> column-major
+            tn = local / tiles_m;
+            tm = local - tn * tiles_m;
+        } else if (T.krule == GM_KRULE_A_LOWER) {   // k < m0 + 128: long for large tm -> rows in descending order
+            tm = tiles_m - 1 - local / tiles_n;
+            tn = local % tiles_n;
+        } else {
+            tm = local / tiles_n;
+            tn = local - tm * tiles_n;
+        }
     }
     const int m0 = tm * GM_BM, n0 = tn * GM_BN;
     int kb = 0, ke = T.K;

@@ -733,7 +733,10 @@ static int dispatch_sv_shared(const dqgp_circuit* c, const double* X, int n, con
     if (n == 0) return 0;
     DQGP_REQUIRE(c && X && Pm && out, "statevector: NULL argument");
     DQGP_REQUIRE(P == c->P, "statevector: circuit has %d parameters, got %d", c->P, P);
-    if (!c->shareable) return dispatch_sv<WANT_STATES>(c, X, n, Pm, 2 * P + 1, out, stream);   // a parameter feeds several gates
+    // prefix sharing parallelises over samples only: with few samples (or a parameter feeding several gates) the
+    // per-set kernel, which parallelises over samples x sets, fills the machine better
+    const long long teams = c->q >= 9 ? n : (long long)n * (c->q > 3 ? (1 << (c->q - 3)) : 1) / 32;
+    if (!c->shareable || teams < (c->q >= 9 ? 600 : 1200)) return dispatch_sv<WANT_STATES>(c, X, n, Pm, 2 * P + 1, out, stream);
     int rc = circuit_on_device(c);
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
