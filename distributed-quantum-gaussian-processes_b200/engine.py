@@ -100,6 +100,8 @@ class AgentEngine:
         self.d_work = torch.empty(max(1, self._lib.dqgp_grad_workspace_bytes(self.n, self.P) // 8), **f64)
         self.entries_per_step = self.S * self.n * self.n    # full squares, all 2P+1 sets
         self.share_prefix = True
+        self.overlap_sim = False
+        self._side = None
 
     def load_data(self, X, Y):
         """Refresh the resident shard from host arrays (the e2e path does this every call, like the
@@ -158,11 +160,28 @@ class AgentEngine:
                                         PERIOD, d_theta_out.data_ptr(), d_psi_out.data_ptr(), stream_ptr()), "admm local")
 
     def step(self, d_z, d_psi, d_theta_out, d_psi_out):
-        # (Running the 2P shifted simulations on a side stream to overlap the factorisation was measured and
-        #  gives nothing: the GEMM CTAs hold every register of an SM, and both kernels want the same FP64 pipe.)
-        self.simulate(d_z)
-        self.gram()
-        self.factor()
+        """One agent step.  With `overlap_sim` (one agent per GPU) the 2P shifted simulations are enqueued on a side
+        stream AFTER the factorisation's launches: K only needs the unshifted set, and the simulator's CTAs then fill
+        the SMs the Cholesky leaves idle on its latency-bound critical path.  (Enqueued before the factorisation they
+        just delay its GEMMs — measured, no gain.)"""
+        if not self.overlap_sim:
+            self.simulate(d_z)
+            self.gram()
+            self.factor()
+        else:
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+                self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+            self.simulate(d_z, 0, 1)
+            self._ev_fork.record(main)
+            self.gram()
+            self.factor()
+            self._side.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._side):
+                self.simulate(d_z, 1, self.S - 1)
+                self._ev_join.record(self._side)
+            main.wait_event(self._ev_join)
         self.gradient()
         self.update(d_psi, d_theta_out, d_psi_out)
 
