@@ -55,6 +55,39 @@ def test_process_agent_training_tuple_interface(d):
     assert np.max(np.abs(theta - g["theta_out"])) < 1e-12 and np.max(np.abs(psi - g["psi_out"])) < 1e-9
 
 
+def test_train_agents_concurrent_equals_sequential(d):
+    """dqgp_b200.train_agents (one CUDA stream per agent, async submit/collect) returns exactly what sequential
+    train_and_update calls return — the GPU counterpart of the reference's executor.map fan-out (main.py:2530-2542)."""
+    cases = ["yzcx_proj_gauss_q4", "cheb_proj_gauss_q4", "hub_fid_q5"]
+    gs = [load_golden(f"agent_step_{c}.npz") for c in cases[:1]] * 3
+    agents = [_agent(d, g) for g in gs]
+    for i, a in enumerate(agents):
+        a.agent_id = f"agent_{i}"                      # distinct engines -> really concurrent
+    z, psis = gs[0]["z"], [gs[0]["psi"], gs[0]["psi"] * 0.5, gs[0]["psi"] * 0.25]
+    par = d.train_agents(agents, z, psis)
+    seq = [a.train_and_update(z, p) for a, p in zip(agents, psis)]
+    for (t1, p1, n1, _, _), (t2, p2, n2, _, _) in zip(par, seq):
+        assert np.array_equal(t1, t2) and np.array_equal(p1, p2) and n1 == n2
+    assert np.max(np.abs(par[0][0] - gs[0]["theta_out"])) < 1e-12
+
+
+@pytest.mark.parametrize("outer_blocks", [1, 2, 4])
+def test_cholesky_panel_width_does_not_change_results(d, outer_blocks):
+    from oracle import driver
+    x, y = driver.synthetic_dataset(1100, 4, "yz_cx")
+    res = []
+    for ob in (0, outer_blocks):
+        eng = d.AgentEngine(x, y, encoding_type="yz_cx", kernel_type="projected", num_qubits=4, num_layers=2, noise_std=0.1,
+                            rho=100.0, L=100.0, cholesky_outer_blocks=ob)
+        z = d.kernels.dev_f64(np.round(np.random.RandomState(1).rand(eng.P), 4))
+        eng.simulate(z); eng.gram(); eng.factor(); eng.gradient()
+        torch.cuda.synchronize()
+        eng.check_info()
+        res.append((eng.d_grad.cpu().numpy(), eng.d_nll.cpu().numpy()))
+    assert np.max(np.abs(res[0][0] - res[1][0])) < 1e-9 * max(1.0, np.abs(res[0][0]).max())
+    assert abs(res[0][1][3] - res[1][1][3]) < 1e-9 * abs(res[0][1][3])
+
+
 def test_wrong_parameter_count_raises(d):
     g = load_golden("agent_step_yzcx_fid_q2.npz")
     with pytest.raises(ValueError):
