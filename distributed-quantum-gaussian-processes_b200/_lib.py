@@ -56,6 +56,7 @@ SIGNATURES = {
     "dqgp_add_diagonal": (_i, [_vp, _i, _i, _d, _vp]),
     "dqgp_potrf_solve_inv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "dqgp_solver_quadform_rows": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "dqgp_solver_apply_factor": (_i, [_vp, _vp, _vp, _vp]),
     "dqgp_dgemm": (_i, [_i, _i, _i, _i, _i, _d, _vp, _i, _vp, _i, _d, _vp, _i, _vp]),
     "dqgp_shift_parameter_sets": (_i, [_vp, _i, _d, _d, _vp, _vp]),
     "dqgp_grad_workspace_bytes": (_sz, [_i, _i]),

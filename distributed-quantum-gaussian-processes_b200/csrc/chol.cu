@@ -224,7 +224,7 @@ __global__ void pad_identity_kernel(double* A, int n, int np, int ld) {
 }
 __global__ void pad_vector_kernel(const double* y, int n, int np, double* out, double* logdet, int* info) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < np) out[i] = (i < n) ? y[i] : 0.0;
+    if (i < np) out[i] = (y != nullptr && i < n) ? y[i] : 0.0;
     if (i == 0) { *logdet = 0.0; *info = 0; }
 }
 
@@ -441,10 +441,11 @@ size_t dqgp_solver_bytes(const dqgp_solver* s) { return s ? s->bytes : 0; }
 int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, double* d_logdet, int* d_info, int want_inverse,
                          void* stream) {
     using namespace dqgp;
-    DQGP_REQUIRE(s && d_y && d_alpha && d_logdet && d_info, "dqgp_potrf_solve_inv: NULL argument");
+    const bool factor_only = want_inverse < 0;
+    DQGP_REQUIRE(s && d_logdet && d_info && (factor_only || (d_y && d_alpha)), "dqgp_potrf_solve_inv: NULL argument");
     cudaStream_t st = as_stream(stream);
     const int np = s->np, ld = s->ld, nblk = s->nblk;
-    pad_vector_kernel<<<(np + 255) / 256, 256, 0, st>>>(d_y, s->n, np, s->y_pad, d_logdet, d_info);
+    pad_vector_kernel<<<(np + 255) / 256, 256, 0, st>>>(factor_only ? nullptr : d_y, s->n, np, s->y_pad, d_logdet, d_info);
     if (np != s->n) pad_identity_kernel<<<np, 256, 0, st>>>(s->A, s->n, np, ld);
     DQGP_LAUNCH_CHECK("pad kernels");
     // Two-level right-looking Cholesky with look-ahead.  The critical path (leaves, panel solves, updates inside the
@@ -487,6 +488,7 @@ int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, dou
         copy_lower_blocks_kernel<<<dim3(nblk - 1, nblk - 1), 256, 0, st>>>(s->T, s->A, ld);
         DQGP_LAUNCH_CHECK("copy_lower_blocks_kernel");
     }
+    if (factor_only) return 0;      // L is in place (dqgp_solver_factor); its diagonal-block inverses are in W
     for (size_t l = 0; l < s->tri_t.size(); ++l) {
         int rc = launch_gemm_group(s->d_tasks + s->tri_t[l].first, s->tri_t[l].count, s->tri_t[l].tiles, st);
         if (rc) return rc;
@@ -506,6 +508,18 @@ int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, dou
             DQGP_LAUNCH_CHECK("symmetrize_lower_kernel");
         }
     }
+    return 0;
+}
+
+int dqgp_solver_apply_factor(dqgp_solver* s, const double* d_x, double* d_y, void* stream) {
+    // y = L x with the Cholesky factor held by the solver (sampling from N(0, K): main.py:272-274)
+    using namespace dqgp;
+    DQGP_REQUIRE(s && d_x && d_y, "dqgp_solver_apply_factor: NULL argument");
+    cudaStream_t st = as_stream(stream);
+    pad_vector_kernel<<<(s->np + 255) / 256, 256, 0, st>>>(d_x, s->n, s->np, s->y_pad, s->w, reinterpret_cast<int*>(s->w + 1));
+    trmv_lower_kernel<<<(s->np + 7) / 8, 256, 0, st>>>(s->A, s->np, s->ld, s->y_pad, s->partial);
+    DQGP_LAUNCH_CHECK("apply_factor kernels");
+    DQGP_CUDA(cudaMemcpyAsync(d_y, s->partial, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 

@@ -102,6 +102,9 @@ size_t dqgp_solver_bytes(const dqgp_solver* s);
 int dqgp_add_diagonal(double* d_A, int n, int lda, double value, void* stream);
 int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, double* d_logdet, int* d_info,
                          int want_inverse, void* stream);
+/* want_inverse < 0 in dqgp_potrf_solve_inv = factor only (d_y, d_alpha may be NULL).
+ * y = L x with the factor held by the solver: sampling from the GP prior (main.py:272-274). */
+int dqgp_solver_apply_factor(dqgp_solver* s, const double* d_x, double* d_y, void* stream);
 /* v = L^-1 B^T for B (nb, n): returns column sums of v^2 -> d_out[nb] (main.py:1462-1463) */
 int dqgp_solver_quadform_rows(dqgp_solver* s, const double* d_B, int nb, int ldb, double* d_out, void* stream);
 

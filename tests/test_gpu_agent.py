@@ -148,6 +148,19 @@ def test_predict_matches_reference(d, case):
     assert abs(d.nlpd(g["Y_test"], mean, var) - d.predict_quantum_gp.last_nlpd) < 1e-10
 
 
+def test_generate_quantum_gp_data_matches_reference_main(d):
+    """the dataset main.main() generated for configs[0] (seed 42, data seed 7), regenerated on the GPU
+    with the same host RNG stream, split like main.py:2356: X identical, Y equal to the Cholesky-sampling accuracy."""
+    from sklearn.model_selection import train_test_split
+    data = load_golden("trajectory_cfg1_data.npz")
+    X, Y, truth = d.generate_quantum_gp_data(1000, 2, 3, 1, (-2.0, 2.0), 0.1, True, None, "chebyshev", "projected", "XYZ", "matern",
+                                             {"length_scale": 1.0, "nu": 1.5}, None, data_seed=7, param_seed=42)
+    Xtr, Xte, Ytr, Yte = train_test_split(X, Y, test_size=0.1, random_state=42, shuffle=True)
+    assert np.array_equal(Xtr, data["X_train"])
+    assert np.max(np.abs(Ytr - data["Y_train"])) < 1e-6 * max(1.0, np.abs(data["Y_train"]).max())
+    assert truth.shape == (12,) and np.all((truth >= 0) & (truth <= np.pi))
+
+
 def test_cv_nlpd_matches_reference_main(d):
     with open(os.path.join(GOLDEN, "trajectory_cfg1.json")) as f:
         rec = json.load(f)
