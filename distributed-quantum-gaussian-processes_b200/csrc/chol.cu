@@ -36,17 +36,21 @@ struct dqgp_solver {
 
 namespace dqgp {
 
-// ---- leaf: Cholesky of a 128x128 diagonal block and its triangular inverse, one CTA, 128 threads -----------
+// ---- leaf: Cholesky of a 128x128 diagonal block and its triangular inverse, one CTA, 256 threads -----------
 // One shared 128x130 array M holds both results: the strict upper triangle keeps L transposed
 // (M[k][i] = L[i][k], k < i) and the strict lower triangle receives W = L^-1 (M[k][j] = W[k][j], j < k);
-// the diagonals live in s_diag / s_rdiag.  Phase 1 is a left-looking Cholesky in panels of 8 columns: thread
-// i owns row i, keeps its 8 panel entries in registers, and per k issues 1 conflict-free LDS + 4 broadcast
-// LDS.128 for 8 DFMA; the 8x8 diagonal block is factored inside one warp with shuffles.  Phase 2 inverts L
-// column by column (thread j owns column j of W) in panels of 8 rows with the same 5-loads-per-8-DFMA
-// pattern and no barrier at all.  (v1 was an unblocked right-looking loop: 281 us per leaf; ncu r01_v1_leaf.)
-constexpr int LEAF_THREADS = 128;
+// the diagonals live in s_diag / s_rdiag.
+// Phase 1 is a left-looking Cholesky in panels of 8 columns.  Row i is owned by the thread pair (i, i+128): both
+// run the update loop over half of the k range each (per k: 1 conflict-free LDS + 4 broadcast LDS.128 for 8 DFMA),
+// the helper hands its partial sums over through shared memory, and the primary thread factors the 8x8 diagonal
+// block redundantly in registers (no cross-lane chain) and forward-substitutes its row.
+// Phase 2 inverts L column by column in panels of 8 rows; column j is owned by two ADJACENT lanes that split the k
+// range and combine with one shuffle, so warps never wait for each other (no block barrier in the whole phase).
+// Measured with clock64 (round 1): v3 (128 threads) spent 32K cycles in the phase-1 k-loops, 50K in the per-panel
+// serial part, 51K in the phase-2 k-loops of the slowest thread, 19K in its serial part, 9K storing W = 164K cycles.
+constexpr int LEAF_THREADS = 256;
 constexpr int LP = 130;
-constexpr size_t LEAF_SMEM_V2 = sizeof(double) * (NB * LP + 2 * NB);
+constexpr size_t LEAF_SMEM_V2 = sizeof(double) * (NB * LP + 2 * NB + 8 * NB);
 
 __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __restrict__ A, int ld, double* __restrict__ W,
                                                                       int blk, double* logdet, int* info, int n_real) {
@@ -54,32 +58,41 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
     double* M = leaf_smem;
     double* s_diag = M + NB * LP;
     double* s_rdiag = s_diag + NB;
+    double* s_part = s_rdiag + NB;            // [8][128] partial sums of the helper threads
     __shared__ double s_red[LEAF_THREADS / 32];
     __shared__ double s_blk[64];
     __shared__ int s_bad;
-    const int i = threadIdx.x, lane = i & 31, warp = i >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = tid & (NB - 1);             // row owned in phase 1
+    const bool helper = tid >= NB;
     double* Ablk = A + (size_t)blk * NB * ld + (size_t)blk * NB;
     double* Wblk = W + (size_t)blk * NB * ld + (size_t)blk * NB;
-    if (i == 0) s_bad = 0;
+    if (tid == 0) s_bad = 0;
     __syncthreads();
 
     // ---------------- phase 1: Cholesky ----------------
     double a[8];
-    {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = 0.0;
+    if (!helper) {
         const double2* src = reinterpret_cast<const double2*>(Ablk + (size_t)i * ld);
 #pragma unroll
         for (int c = 0; c < 4; ++c) { const double2 v = src[c]; a[2 * c] = v.x; a[2 * c + 1] = v.y; }
     }
     for (int j0 = 0; j0 < NB; j0 += 8) {
         double nxt[8];
-        if (j0 + 8 < NB && i >= j0 + 8) {   // prefetch the next panel's entries of this row (hidden behind the update)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) nxt[c] = 0.0;
+        if (!helper && j0 + 8 < NB && i >= j0 + 8) {   // prefetch the next panel's entries of this row
             const double2* src = reinterpret_cast<const double2*>(Ablk + (size_t)i * ld + j0 + 8);
 #pragma unroll
             for (int c = 0; c < 4; ++c) { const double2 v = src[c]; nxt[2 * c] = v.x; nxt[2 * c + 1] = v.y; }
         }
         if (i >= j0) {
+            const int kh = (j0 >> 1) & ~3;
+            const int kb = helper ? kh : 0, ke = helper ? j0 : kh;
 #pragma unroll 4
-            for (int k = 0; k < j0; ++k) {
+            for (int k = kb; k < ke; ++k) {
                 const double lik = M[k * LP + i];
                 const double2* row = reinterpret_cast<const double2*>(&M[k * LP + j0]);
                 const double2 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
@@ -88,16 +101,23 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
                 a[4] = fma(-lik, v2.x, a[4]); a[5] = fma(-lik, v2.y, a[5]);
                 a[6] = fma(-lik, v3.x, a[6]); a[7] = fma(-lik, v3.y, a[7]);
             }
-        }
-        // rows j0..j0+7 publish their updated 8x8 diagonal block; every thread then factors it redundantly in
-        // registers (no cross-lane dependency chain: v2 did this with ~60 dependent shuffles per panel) and
-        // forward-substitutes its own row against it
-        if (i >= j0 && i < j0 + 8) {
+            if (helper) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) s_blk[(i - j0) * 8 + c] = a[c];
+                for (int c = 0; c < 8; ++c) s_part[c * NB + i] = a[c];
+            }
         }
         __syncthreads();
-        if (i >= j0) {
+        if (!helper && i >= j0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] += s_part[c * NB + i];
+            if (i < j0 + 8) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) s_blk[(i - j0) * 8 + c] = a[c];
+            }
+        }
+        __syncthreads();
+        if (!helper && i >= j0) {
+            // every primary thread factors the 8x8 diagonal block redundantly in registers, then substitutes its row
             double l[8][8];
 #pragma unroll
             for (int r = 0; r < 8; ++r)
@@ -118,7 +138,6 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
                     for (int r = c2; r < 8; ++r) l[r][c2] = fma(-l[r][c], l[c2][c], l[r][c2]);
             }
             if (i < j0 + 8) {
-                // my row of the factored block
                 const int r0 = i - j0;
 #pragma unroll
                 for (int r = 0; r < 8; ++r)
@@ -129,19 +148,18 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
                         s_rdiag[i] = rd[r];
                     }
             } else {
+                // column-oriented substitution: as soon as x_k is known it is removed from all later columns
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    double x = a[c];
+                    const double x = a[c] * rd[c];
+                    a[c] = x;
 #pragma unroll
-                    for (int k = 0; k < c; ++k) x = fma(-a[k], l[c][k], x);
-                    a[c] = x * rd[c];
+                    for (int c2 = c + 1; c2 < 8; ++c2) a[c2] = fma(-x, l[c2][c], a[c2]);
                 }
             }
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 if (i > j0 + c) M[(j0 + c) * LP + i] = a[c];
-        }
-        if (i >= j0) {
             double2* dst = reinterpret_cast<double2*>(Ablk + (size_t)i * ld + j0);
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -149,14 +167,14 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
         }
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) a[c] = nxt[c];
+        for (int c = 0; c < 8; ++c) a[c] = nxt[c];     // helpers restart from zero
     }
     {
-        double v = log(s_diag[i]);
+        double v = (tid < NB) ? log(s_diag[tid]) : 0.0;
         v = warp_sum(v);
         if (lane == 0) s_red[warp] = v;
         __syncthreads();
-        if (i == 0) {
+        if (tid == 0) {
             double tot = 0.0;
 #pragma unroll
             for (int w = 0; w < LEAF_THREADS / 32; ++w) tot += s_red[w];
@@ -165,24 +183,18 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
         }
     }
 
-    // ---------------- phase 2: W = L^-1, thread j owns column j ----------------
-    const int j = i;
+    // ---------------- phase 2: W = L^-1; column j is owned by lanes (2*(j%16), 2*(j%16)+1) of warp j/16 ----------------
+    const int j = warp * 16 + (lane >> 1);
+    const int h = lane & 1;
     for (int i0 = 0; i0 < NB; i0 += 8) {
-        if (j > i0 + 7) continue;
+        if (warp * 16 > i0 + 7) continue;         // whole warp is right of this row panel (warp-uniform)
         double acc[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) acc[r] = 0.0;
         if (j < i0) {
-            {   // k = j: W[j][j] = 1 / L[j][j]
-                const double w = s_rdiag[j];
-                const double2* row = reinterpret_cast<const double2*>(&M[j * LP + i0]);
-                const double2 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
-                acc[0] = w * v0.x; acc[1] = w * v0.y; acc[2] = w * v1.x; acc[3] = w * v1.y;
-                acc[4] = w * v2.x; acc[5] = w * v2.y; acc[6] = w * v3.x; acc[7] = w * v3.y;
-            }
-#pragma unroll 4
-            for (int k = j + 1; k < i0; ++k) {
-                const double w = M[k * LP + j];
+            // k = j .. i0-1 (W[j][j] = 1/L[j][j], W[k][j] = M[k][j] for k > j); the two lanes take alternate k
+            for (int k = j + h; k < i0; k += 2) {
+                const double w = (k == j) ? s_rdiag[j] : M[k * LP + j];
                 const double2* row = reinterpret_cast<const double2*>(&M[k * LP + i0]);
                 const double2 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
                 acc[0] = fma(w, v0.x, acc[0]); acc[1] = fma(w, v0.y, acc[1]);
@@ -191,27 +203,35 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
                 acc[6] = fma(w, v3.x, acc[6]); acc[7] = fma(w, v3.y, acc[7]);
             }
         }
-        double wv[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int row = i0 + r;
-            double w = 0.0;
-            if (row == j) w = s_rdiag[j];
-            else if (row > j) {
-                double sres = acc[r];
+        for (int r = 0; r < 8; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
+        if (h == 0 && j <= i0 + 7) {
+            double wv[8];
 #pragma unroll
-                for (int r2 = 0; r2 < r; ++r2)
-                    if (i0 + r2 >= j) sres = fma(M[(i0 + r2) * LP + row], wv[r2], sres);
-                w = -sres * s_rdiag[row];
-                M[row * LP + j] = w;
+            for (int r = 0; r < 8; ++r) {
+                const int row = i0 + r;
+                double w = 0.0;
+                if (row == j) w = s_rdiag[j];
+                else if (row > j) {
+                    double sres = acc[r];
+#pragma unroll
+                    for (int r2 = 0; r2 < r; ++r2)
+                        if (i0 + r2 >= j) sres = fma(M[(i0 + r2) * LP + row], wv[r2], sres);
+                    w = -sres * s_rdiag[row];
+                    M[row * LP + j] = w;
+                }
+                wv[r] = w;
             }
-            wv[r] = w;
         }
+        __syncwarp();
     }
     __syncthreads();
-    for (int e = i; e < NB * NB; e += LEAF_THREADS) {
-        const int r = e >> 7, c = e & 127;
-        Wblk[(size_t)r * ld + c] = (c < r) ? M[r * LP + c] : (c == r ? s_rdiag[r] : 0.0);
+    for (int e = tid; e < NB * NB / 2; e += LEAF_THREADS) {
+        const int r = e >> 6, c = (e & 63) * 2;
+        double2 v;
+        v.x = (c < r) ? M[r * LP + c] : (c == r ? s_rdiag[r] : 0.0);
+        v.y = (c + 1 < r) ? M[r * LP + c + 1] : (c + 1 == r ? s_rdiag[r] : 0.0);
+        *reinterpret_cast<double2*>(Wblk + (size_t)r * ld + c) = v;
     }
 }
 
