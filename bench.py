@@ -197,10 +197,16 @@ def run_ours(args, w):
         r["frac"] = r["achieved"] / r["peak"]
     dominant = max(("gradient", "factor", "statevector", "gram"), key=lambda k: phases[k])
     primary = dict(roof.get(dominant, roof["factor"]))
-    primary.update({"kernel": {"gradient": "grad_projected_kernel" if w["kernel"] == "projected" else "grad_fidelity_kernel",
+    traffic = load_json(os.path.join(ROOT, "profiles", "r01_traffic.json"), {})
+    primary.update({"kernel": {"gradient": "grad_projected_dmma_kernel" if w["kernel"] == "projected" else "grad_fidelity_kernel",
                                "factor": "gemm_group_kernel", "gram": "gram_projected_kernel"}.get(dominant, "statevec_kernel"),
                     "traffic": None, "peak_source": "profiles/r01_fp64_peak.json (measured on this pool: pure DMMA/DFMA issue loops)"
                     if primary["bound"] != "hbm" else "MEASURED_PEAKS.json"})
+
+    tk = traffic.get(primary["kernel"].replace("grad_projected_kernel", "grad_projected_dmma_kernel"), {})
+    if tk.get("dram_bytes"):
+        primary["traffic"] = tk["dram_bytes"]
+        primary["traffic_note"] = ("dram__bytes_read+write of one launch under ncu (profiles/r01_traffic.json): " + tk.get("launch", tk.get("note", "")))
 
     # ---- e2e: host buffers through RiemannianAgent.train_and_update + host consensus ------------------------------
     e2e = None if args.skip_e2e else run_e2e(args, w, d, torch, dist, world, rank, shards, theta0, psi0, n_i, P, entries_per_iter)
