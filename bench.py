@@ -215,7 +215,7 @@ def run_ours(args, w):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_sample(w, n_i, P)
 
-    launches = sum(launches_per_agent_step(a) for a in eng.agents) + 3
+    launches = (sum(a.launches_per_step() for a in eng.agents) + 3) * world    # + consensus, 2 row exchanges; all ranks
     if rank == 0:
         ms_per_step = total_ms / args.steps
         line = {
@@ -235,12 +235,6 @@ def run_ours(args, w):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def launches_per_agent_step(ag):
-    nblk = (ag.n + 127) // 128
-    levels = int(np.ceil(np.log2(nblk))) if nblk > 1 else 0
-    return 1 + 1 + 1 + 1 + 2 + nblk + 2 * (nblk - 1) + 2 * levels + 3 + 1 + 2 + 1 + 1
 
 
 def run_e2e(args, w, d, torch, dist, world, rank, shards, theta0, psi0, n_i, P, entries_per_iter):

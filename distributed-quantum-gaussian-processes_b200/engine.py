@@ -91,6 +91,7 @@ class AgentEngine:
         self.m = 3 * self.q if kernel_type == "projected" else 2 * (1 << self.q)   # doubles per sample per set
         self.d_Pm = torch.empty((self.S, self.P), **f64)
         self.d_feat = torch.empty((self.S, self.n, self.m), **f64)
+        self.cholesky_outer_blocks = int(cholesky_outer_blocks)
         self.solver = Solver(self.n, cholesky_outer_blocks)
         self.d_alpha = torch.empty(self.n, **f64)
         self.d_logdet = torch.zeros(1, **f64)
@@ -184,6 +185,18 @@ class AgentEngine:
             main.wait_event(self._ev_join)
         self.gradient()
         self.update(d_psi, d_theta_out, d_psi_out)
+
+    def launches_per_step(self):
+        """Kernel launches of one step() (counted from the launch structure of csrc/chol.cu and friends)."""
+        nblk = (self.n + 127) // 128
+        ob = self.cholesky_outer_blocks if self.cholesky_outer_blocks > 0 else 4
+        panels = (nblk + ob - 1) // ob
+        inner = sum(1 for k in range(nblk - 1) if k + 1 < min((k // ob + 1) * ob, nblk))
+        levels = int(np.ceil(np.log2(nblk))) if nblk > 1 else 0
+        potrf = nblk + (nblk - 1) + inner + max(panels - 1, 0) + max(panels - 2, 0) + (1 if nblk > 1 else 0)
+        pad = 1 + (1 if self.n % 128 else 0)
+        return (2 + 2 + pad + potrf + 2 * levels + 3 + 1        # sets, sim, gram, diag, pad, potrf, trtri, solve, lauum
+                + (3 if self.kernel_type == "projected" else 2) + 1 + 1)   # (norms) grad reduce, nll, local update
 
     def check_info(self):
         """Host check of the Cholesky status (syncs).  >0 = index of the first non-positive pivot."""
