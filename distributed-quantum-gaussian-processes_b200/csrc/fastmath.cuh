@@ -36,19 +36,15 @@ __device__ __forceinline__ double fast_exp(double x) {
 // Table variant: x = (32 e + j) ln2/32 + r, |r| <= ln2/64, result = 2^e * T[j] * e^r with a degree-6 polynomial.
 // T[j] = 2^(j/32) lives one entry per lane in a register (`tab` = exp_table_entry()) and is fetched with a warp
 // shuffle, so the FP64 pipe sees 11 instructions instead of 16.  All lanes of the warp must call it together.
-__device__ __forceinline__ double exp_table_entry() {
-    const int lane = threadIdx.x & 31;
-    // 2^(lane/32), correctly rounded constants
-    const double T[32] = {
+static __device__ __constant__ double DQGP_EXP_T32[32] = {
         0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0, 0x1.172b83c7d517bp+0,
         0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0, 0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0,
         0x1.3dea64c123422p+0, 0x1.44e086061892dp+0, 0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0,
         0x1.6247eb03a5585p+0, 0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
         0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0, 0x1.ae89f995ad3adp+0,
         0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0, 0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0,
-        0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
-    return T[lane];
-}
+        0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};   // 2^(j/32), correctly rounded
+__device__ __forceinline__ double exp_table_entry() { return DQGP_EXP_T32[threadIdx.x & 31]; }
 
 __device__ __forceinline__ double fast_exp_tab(double x, double tab) {
     const double S = 0x1.71547652b82fep+5;                 // 32 / ln 2

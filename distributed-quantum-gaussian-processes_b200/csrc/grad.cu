@@ -7,9 +7,8 @@
 // kernel and contracting on the fly.  Partial sums go to partial[tile][i]; a second kernel adds them in a
 // fixed order, so the result is bit-reproducible run to run (the reference rounds it to 4 decimals).
 // Bound: FP64 pipe (3m + outer-kernel flops per entry); HBM traffic is one read of A^-1.
-#include "pairwise.cuh"
 #include <cstdlib>
-#include "fastmath.cuh"
+#include "pairwise.cuh"
 
 namespace dqgp {
 
@@ -91,7 +90,6 @@ __global__ void __launch_bounds__(PW_THREADS) grad_projected_kernel(const double
 // direct-difference form (the absolute error of d^2 is ~1e-15, harmless for exp/Matern/ExpSine outer kernels;
 // the unshifted Gram that is *written* keeps direct differences).  CTA = 64x64 tile, 8 warps as 4x2, warp tile
 // 16x32 = 2x4 DMMA blocks; B stays in registers for all 2P sets; feature tiles double-buffered with cp.async.
-constexpr int G2_PITCH = 36;                       // doubles per staged sample row: = 4 (mod 16) -> conflict-free fragments
 constexpr int G2_STAGE_DOUBLES = 2 * PW_TILE * G2_PITCH + 2 * PW_TILE;
 constexpr size_t G2_SMEM = sizeof(double) * 2 * G2_STAGE_DOUBLES;
 
@@ -125,20 +123,6 @@ __device__ __forceinline__ void g2_stage(double* buf, const double* __restrict__
     double* nr = buf + 2 * PW_TILE * G2_PITCH;
     if (threadIdx.x < PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(row0 + threadIdx.x, n - 1)]);
     else if (threadIdx.x < 2 * PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(col0 + threadIdx.x - PW_TILE, n - 1)]);
-}
-
-template <int OUTER>
-__device__ __forceinline__ double outer_from_neg_gd2(double v, const OuterHyp& h, double tab) {
-    // v = -gamma_eff * d^2 (gamma_eff = gamma for the Gaussian, 1 otherwise); warp-collective (table shuffle)
-    if (OUTER == DQGP_OUTER_GAUSSIAN) {
-        return fast_exp_tab(fmax(v, -700.0), tab);
-    } else if (OUTER == DQGP_OUTER_MATERN15) {
-        const double k = sqrt(fmax(-v, 0.0)) * h.a * 1.7320508075688772;
-        return (1.0 + k) * fast_exp_tab(fmax(-k, -700.0), tab);
-    } else {
-        const double sn = sin(sqrt(fmax(-v, 0.0)) * h.b) * h.a;
-        return fast_exp_tab(fmax(-2.0 * (sn * sn), -700.0), tab);
-    }
 }
 
 template <int OUTER, int VEC>

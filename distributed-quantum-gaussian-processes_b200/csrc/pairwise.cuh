@@ -7,6 +7,7 @@
 // columns are one LDS.128 and the row operand is a broadcast.
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace dqgp {
 
@@ -95,5 +96,23 @@ __device__ __forceinline__ void micro_sqdist(const double* __restrict__ FrT, con
             }
     }
 }
+
+// Outer kernel from v = -gamma_eff * d^2 (gamma_eff = gamma for the Gaussian, 1 otherwise), as left in a DMMA
+// accumulator by the Gram identity.  Warp-collective: fast_exp_tab shuffles its table.
+template <int OUTER>
+__device__ __forceinline__ double outer_from_neg_gd2(double v, const OuterHyp& h, double tab) {
+    // v = -gamma_eff * d^2 (gamma_eff = gamma for the Gaussian, 1 otherwise); warp-collective (table shuffle)
+    if (OUTER == DQGP_OUTER_GAUSSIAN) {
+        return fast_exp_tab(fmax(v, -700.0), tab);
+    } else if (OUTER == DQGP_OUTER_MATERN15) {
+        const double k = sqrt(fmax(-v, 0.0)) * h.a * 1.7320508075688772;
+        return (1.0 + k) * fast_exp_tab(fmax(-k, -700.0), tab);
+    } else {
+        const double sn = sin(sqrt(fmax(-v, 0.0)) * h.b) * h.a;
+        return fast_exp_tab(fmax(-2.0 * (sn * sn), -700.0), tab);
+    }
+}
+
+constexpr int G2_PITCH = 36;   // doubles per staged sample row: = 4 (mod 16) -> conflict-free DMMA fragment loads
 
 }  // namespace dqgp
