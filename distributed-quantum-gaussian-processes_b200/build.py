@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdqgp.so")
-SOURCES = ["circuit.cu", "statevec.cu", "gram.cu", "gemm64.cu", "chol.cu", "grad.cu", "admm.cu", "api.cu"]
+SOURCES = ["circuit.cu", "statevec.cu", "gram.cu", "gemm64.cu", "chol.cu", "grad.cu", "fid.cu", "admm.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 

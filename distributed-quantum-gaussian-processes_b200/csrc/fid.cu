@@ -1,0 +1,194 @@
+// Fidelity kernel on the DMMA path: K[j][k] = |<psi2_k | psi1_j>|^2 as a complex tile contraction.
+// A state of 2^q complex128 amplitudes is a real vector u of 2*2^q doubles (re, im interleaved):
+//   Re<psi_k|psi_j> = u_j . u_k          Im<psi_k|psi_j> = J(u_j) . u_k,   J(u)[2i] = u[2i+1], J(u)[2i+1] = -u[2i]
+// so one tile needs two real GEMMs that share the column operand; both run on DMMA.8x8x4 with the J-variant of the
+// row fragment read from the same shared-memory tile at index t^1 with a sign flip (no extra staging, no extra HBM).
+// MODE 0 writes the Gram (FidelityKernel.evaluate, reference main.py:118-124); MODE 1 is the fused central-difference
+// gradient over the 2P shifted state sets (agent_riemannian.py:270-275,431-436), lower tiles only, B = A^-1 - alpha
+// alpha^T in registers, deterministic two-stage reduction.  Operand chunks of 32 doubles stream through a
+// double-buffered cp.async ring.  Replaces the SIMT kernels of gram.cu / grad.cu (kept behind DQGP_FID_SIMT).
+#include <cstdlib>
+#include "pairwise.cuh"
+
+namespace dqgp {
+
+constexpr int FD_KC = 32;                      // doubles per k-chunk (16 complex amplitudes)
+constexpr int FD_PITCH = FD_KC + 4;            // = 4 (mod 16): conflict-free fragment loads
+constexpr int FD_STAGE = 2 * PW_TILE * FD_PITCH;
+constexpr size_t FD_SMEM = sizeof(double) * 2 * FD_STAGE;
+
+__device__ __forceinline__ void fd_stage(double* buf, const double* __restrict__ S1, const double* __restrict__ S2, int row0,
+                                         int col0, int n1, int n2, int d2, int k0, int kc) {
+    const int r = threadIdx.x >> 2, l4 = threadIdx.x & 3;
+    const double* src_r = S1 + (size_t)min(row0 + r, n1 - 1) * d2 + k0;
+    const double* src_c = S2 + (size_t)min(col0 + r, n2 - 1) * d2 + k0;
+    double* dst_r = buf + r * FD_PITCH;
+    double* dst_c = buf + PW_TILE * FD_PITCH + r * FD_PITCH;
+    for (int k = 2 * l4; k < kc; k += 8) {
+        cp_async16(dst_r + k, src_r + k);
+        cp_async16(dst_c + k, src_c + k);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PW_THREADS, 1) fidelity_dmma_kernel(const double* __restrict__ Psi1, int n1,
+                                                                      const double* __restrict__ Psi2, int n2, int d2, int n_sets,
+                                                                      double* __restrict__ K, int ldk,
+                                                                      const double* __restrict__ Ainv, int ld,
+                                                                      const double* __restrict__ alpha, int P,
+                                                                      double* __restrict__ partial) {
+    extern __shared__ __align__(16) double fd_smem[];
+    __shared__ double s_red[2][PW_THREADS / 32];
+    int bi, bj;
+    if (MODE == 1) {
+        bi = int((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+        while ((bi + 1) * (bi + 2) / 2 <= (int)blockIdx.x) ++bi;
+        while (bi * (bi + 1) / 2 > (int)blockIdx.x) --bi;
+        bj = blockIdx.x - bi * (bi + 1) / 2;
+    } else {
+        bi = blockIdx.y; bj = blockIdx.x;
+    }
+    const int row0 = bi * PW_TILE, col0 = bj * PW_TILE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wr = warp >> 1, wc = warp & 1, g = lane >> 2, t = lane & 3;
+    const int kc = d2 < FD_KC ? d2 : FD_KC;
+    const int n_chunks = d2 / kc;
+    const double jsign = (t & 1) ? -1.0 : 1.0;
+
+    double br[2][4][2];
+    if (MODE == 1) {
+        const double weight = (bi == bj) ? 1.0 : 2.0;
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+            const int r = row0 + wr * 16 + rb * 8 + g;
+            const double ar = (r < n1) ? alpha[r] : 0.0;
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                const int c = col0 + wc * 32 + cb * 8 + 2 * t;
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    br[rb][cb][e] = (r < n1 && c + e < n1) ? weight * (Ainv[(size_t)r * ld + c + e] - ar * alpha[c + e]) : 0.0;
+            }
+        }
+    }
+
+    const size_t set_stride1 = (size_t)n1 * d2, set_stride2 = (size_t)n2 * d2;
+    const int first_set = (MODE == 1) ? 1 : 0;
+    const int total = n_sets * n_chunks;
+    fd_stage(fd_smem, Psi1 + first_set * set_stride1, Psi2 + first_set * set_stride2, row0, col0, n1, n2, d2, 0, kc);
+    cp_async_commit();
+    double re[2][4][2], im[2][4][2];
+    double pplus = 0.0;
+    for (int it = 0; it < total; ++it) {
+        const int set = it / n_chunks, ch = it - set * n_chunks;
+        cp_async_wait<0>();
+        __syncthreads();
+        if (MODE == 1 && ch == 0 && set >= 2 && (set & 1) == 0 && threadIdx.x == 0) {
+            const int i = (set >> 1) - 1;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < PW_THREADS / 32; ++w) s += s_red[i & 1][w];
+            partial[(size_t)blockIdx.x * P + i] = s;
+        }
+        if (it + 1 < total) {
+            const int ns = (it + 1) / n_chunks, nch = (it + 1) - ns * n_chunks;
+            fd_stage(fd_smem + ((it + 1) & 1) * FD_STAGE, Psi1 + (size_t)(first_set + ns) * set_stride1,
+                     Psi2 + (size_t)(first_set + ns) * set_stride2, row0, col0, n1, n2, d2, nch * kc, kc);
+        }
+        cp_async_commit();
+        if (ch == 0) {
+#pragma unroll
+            for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) re[rb][cb][0] = re[rb][cb][1] = im[rb][cb][0] = im[rb][cb][1] = 0.0;
+        }
+        const double* buf = fd_smem + (it & 1) * FD_STAGE;
+        const double* fr = buf + (wr * 16 + g) * FD_PITCH;
+        const double* fc = buf + PW_TILE * FD_PITCH + (wc * 32 + g) * FD_PITCH + t;
+        for (int kk = 0; kk < (kc >> 2); ++kk) {
+            const double a0 = fr[kk * 4 + t], a1 = fr[8 * FD_PITCH + kk * 4 + t];
+            const double j0 = jsign * fr[kk * 4 + (t ^ 1)], j1 = jsign * fr[8 * FD_PITCH + kk * 4 + (t ^ 1)];
+            double b[4];
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) b[cb] = fc[cb * 8 * FD_PITCH + kk * 4];
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                dmma884(re[0][cb][0], re[0][cb][1], a0, b[cb]);
+                dmma884(re[1][cb][0], re[1][cb][1], a1, b[cb]);
+                dmma884(im[0][cb][0], im[0][cb][1], j0, b[cb]);
+                dmma884(im[1][cb][0], im[1][cb][1], j1, b[cb]);
+            }
+        }
+        if (ch == n_chunks - 1) {
+            if (MODE == 0) {
+#pragma unroll
+                for (int rb = 0; rb < 2; ++rb) {
+                    const int r = row0 + wr * 16 + rb * 8 + g;
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) {
+                        const int c = col0 + wc * 32 + cb * 8 + 2 * t;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            if (r < n1 && c + e < n2)
+                                K[(size_t)r * ldk + c + e] = fma(re[rb][cb][e], re[rb][cb][e], im[rb][cb][e] * im[rb][cb][e]);
+                    }
+                }
+            } else {
+                double part = 0.0;
+#pragma unroll
+                for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            part = fma(br[rb][cb][e], fma(re[rb][cb][e], re[rb][cb][e], im[rb][cb][e] * im[rb][cb][e]), part);
+                if (set & 1) {
+                    const double v = warp_sum(pplus - part);
+                    if (lane == 0) s_red[(set >> 1) & 1][warp] = v;
+                } else {
+                    pplus = part;
+                }
+            }
+        }
+    }
+    if (MODE == 1) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int i = P - 1;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < PW_THREADS / 32; ++w) s += s_red[i & 1][w];
+            partial[(size_t)blockIdx.x * P + i] = s;
+        }
+    }
+}
+
+static int fd_attr() {
+    static bool done = false;
+    if (!done) {
+        DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
+        DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
+        done = true;
+    }
+    return 0;
+}
+
+int fidelity_gram_dmma(const double* Psi1, int n1, const double* Psi2, int n2, int dim, double* K, int ldk, cudaStream_t st) {
+    int rc = fd_attr();
+    if (rc) return rc;
+    dim3 grid((n2 + PW_TILE - 1) / PW_TILE, (n1 + PW_TILE - 1) / PW_TILE);
+    fidelity_dmma_kernel<0><<<grid, PW_THREADS, FD_SMEM, st>>>(Psi1, n1, Psi2, n2, 2 * dim, 1, K, ldk, nullptr, 0, nullptr, 0, nullptr);
+    DQGP_LAUNCH_CHECK("fidelity_dmma_kernel<0>");
+    return 0;
+}
+
+int fidelity_grad_dmma(const double* Ainv, int ld, const double* alpha, const double* Psi, int n, int dim, int P, double* partial,
+                       int tiles, cudaStream_t st) {
+    int rc = fd_attr();
+    if (rc) return rc;
+    fidelity_dmma_kernel<1><<<tiles, PW_THREADS, FD_SMEM, st>>>(Psi, n, Psi, n, 2 * dim, 2 * P, nullptr, 0, Ainv, ld, alpha, P, partial);
+    DQGP_LAUNCH_CHECK("fidelity_dmma_kernel<1>");
+    return 0;
+}
+
+}  // namespace dqgp

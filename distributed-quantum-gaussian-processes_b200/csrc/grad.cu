@@ -403,8 +403,14 @@ int dqgp_grad_fidelity(const double* d_Ainv, int ld, const double* d_alpha, cons
     const int tiles = grad_tiles(n);
     cudaStream_t st = as_stream(stream);
     double* partial = static_cast<double*>(d_work);
-    grad_fidelity_kernel<<<tiles, PW_THREADS, 0, st>>>(d_Ainv, ld, d_alpha, reinterpret_cast<const double2*>(d_Psi), n, dim, P, partial);
-    DQGP_LAUNCH_CHECK("grad_fidelity_kernel");
+    static const bool use_simt = getenv("DQGP_FID_SIMT") != nullptr;      // v1 SIMT kernel, kept for A/B checks
+    if (!use_simt && dim >= 2 && (reinterpret_cast<uintptr_t>(d_Psi) & 15) == 0) {
+        int rc = fidelity_grad_dmma(d_Ainv, ld, d_alpha, d_Psi, n, dim, P, partial, tiles, st);
+        if (rc) return rc;
+    } else {
+        grad_fidelity_kernel<<<tiles, PW_THREADS, 0, st>>>(d_Ainv, ld, d_alpha, reinterpret_cast<const double2*>(d_Psi), n, dim, P, partial);
+        DQGP_LAUNCH_CHECK("grad_fidelity_kernel");
+    }
     grad_reduce_kernel<<<P, 256, 0, st>>>(partial, tiles, P, 0.5 / (2.0 * h), d_grad);
     DQGP_LAUNCH_CHECK("grad_reduce_kernel");
     return 0;

@@ -260,6 +260,9 @@ int dqgp_gram_fidelity(const double* d_Psi1, int n1, const double* d_Psi2, int n
     DQGP_REQUIRE(d_Psi1 && d_Psi2 && d_K, "dqgp_gram_fidelity: NULL argument");
     DQGP_REQUIRE(dim >= 1 && n1 >= 0 && n2 >= 0 && ldk >= n2, "dqgp_gram_fidelity: bad shape");
     if (n1 == 0 || n2 == 0) return 0;
+    static const bool use_simt = getenv("DQGP_FID_SIMT") != nullptr;      // v1 SIMT kernel, kept for A/B checks
+    if (!use_simt && dim >= 2 && ((reinterpret_cast<uintptr_t>(d_Psi1) | reinterpret_cast<uintptr_t>(d_Psi2)) & 15) == 0)
+        return fidelity_gram_dmma(d_Psi1, n1, d_Psi2, n2, dim, d_K, ldk, as_stream(stream));
     dim3 grid((n2 + PW_TILE - 1) / PW_TILE, (n1 + PW_TILE - 1) / PW_TILE);
     gram_fidelity_kernel<<<grid, PW_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const double2*>(d_Psi1), n1,
                                                                     reinterpret_cast<const double2*>(d_Psi2), n2, dim, d_K, ldk);

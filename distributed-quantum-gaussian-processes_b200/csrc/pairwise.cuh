@@ -113,6 +113,11 @@ __device__ __forceinline__ double outer_from_neg_gd2(double v, const OuterHyp& h
     }
 }
 
+// DMMA fidelity kernels (fid.cu)
+int fidelity_gram_dmma(const double* Psi1, int n1, const double* Psi2, int n2, int dim, double* K, int ldk, cudaStream_t st);
+int fidelity_grad_dmma(const double* Ainv, int ld, const double* alpha, const double* Psi, int n, int dim, int P, double* partial,
+                       int tiles, cudaStream_t st);
+
 constexpr int G2_PITCH = 36;   // doubles per staged sample row: = 4 (mod 16) -> conflict-free DMMA fragment loads
 
 }  // namespace dqgp
