@@ -173,7 +173,8 @@ def test_cv_nlpd_matches_reference_main(d):
     assert abs(out["mean_nlpd"] - cv["mean_nlpd"]) < 1e-7
 
 
-@pytest.mark.parametrize("enc,ktype,q,layers,dd,n", [("yz_cx", "projected", 8, 3, 4, 700), ("hubregtsen", "fidelity", 5, 2, 2, 520)])
+@pytest.mark.parametrize("enc,ktype,q,layers,dd,n", [("yz_cx", "projected", 8, 3, 4, 700), ("hubregtsen", "fidelity", 5, 2, 2, 520),
+                                                   ("kyriienko", "projected", 6, 2, 3, 400), ("chebyshev", "fidelity", 4, 2, 2, 330)])
 def test_agent_step_medium_size_against_oracle(d, enc, ktype, q, layers, dd, n):
     from oracle import agent_step, circuits, driver
     x, y = driver.synthetic_dataset(n, dd, enc)
