@@ -139,8 +139,13 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_fn = eng.iteration
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1 and n_i <= 2048)
+    if use_graph:
+        eng.capture()                            # launch-bound shards: replay the whole iteration as one CUDA graph
+        step_fn = eng.replay
     for _ in range(args.warmup):
-        eng.iteration()
+        step_fn()
     barrier()
     for a in eng.agents:
         a.check_info()
@@ -151,7 +156,7 @@ def run_ours(args, w):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        eng.iteration()
+        step_fn()
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -231,7 +236,7 @@ def run_ours(args, w):
                        "parameter_sets": S, "entries_per_iteration": entries_per_iter, "agents_per_gpu": w["agents"] // world,
                        "training_outer_kernel": "gaussian" if not w["honour_outer"] else w["outer"],
                        "cache": "per-agent working set (3 x n_pad^2 fp64 = %.1f GB) exceeds the 126 MB L2; no flush needed" % (3 * 8 * np_pad ** 2 / 1e9),
-                       "noise_std": NOISE_STD, "rho": RHO, "L": LIP, "shift": "pi/8"},
+                       "noise_std": NOISE_STD, "rho": RHO, "L": LIP, "shift": "pi/8", "cuda_graph": bool(use_graph)},
             "gpu_launches": launches * args.steps, "clocks": clocks, "e2e": e2e,
             "phases_ms_one_agent": phases, "roofline": primary, "rooflines": roof, "cpu_baseline": cpu_base,
             "final_nll_rank0": [float(v) for v in nll], "final_z_head": [float(v) for v in z_final[:4]],
@@ -365,6 +370,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="replay the iteration as a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 1)

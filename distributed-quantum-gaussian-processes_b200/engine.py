@@ -288,6 +288,23 @@ class AdmmEngine:
         exchange_rows(self.theta, self.local_theta, self.pg, self.world)
         exchange_rows(self.psi, self.local_psi, self.pg, self.world)
 
+    def capture(self):
+        """Capture one iteration (all local agents, their streams and the solver's internal look-ahead streams) into a
+        CUDA graph; `replay()` then costs one launch.  Worth it when the iteration is launch-bound (small shards:
+        hundreds of short kernels per agent); single-rank only (the NCCL exchange stays outside the graph)."""
+        if self.world != 1:
+            raise DqgpError("graph capture is implemented for the single-rank engine only")
+        self.iteration()                         # warm-up: lazy uploads and function attributes must be set before capture
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.iteration()
+        self._graph = graph
+        return graph
+
+    def replay(self):
+        self._graph.replay()
+
     def state(self):
         """(z, theta, psi, per-agent NLL) on the host (synchronises)."""
         nll = np.array([float(a.d_nll[3].item()) for a in self.agents])

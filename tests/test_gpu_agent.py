@@ -88,6 +88,26 @@ def test_cholesky_panel_width_does_not_change_results(d, outer_blocks):
     assert abs(res[0][1][3] - res[1][1][3]) < 1e-9 * abs(res[0][1][3])
 
 
+def test_cuda_graph_replay_equals_eager_iterations(d):
+    """AdmmEngine.capture()/replay() (whole iteration, all agent streams and the solver's look-ahead streams in one CUDA
+    graph) walks exactly the same trajectory as eager iteration() calls."""
+    from oracle import driver
+    x, y = driver.synthetic_dataset(4 * 150, 2, "chebyshev")
+    shards = [(x[a * 150:(a + 1) * 150], y[a * 150:(a + 1) * 150]) for a in range(4)]
+    rs = np.random.RandomState(42)
+    theta0, psi0 = np.round(rs.rand(4, 12), 4), np.round(rs.rand(4, 12), 4)
+    kw = dict(rho=100.0, L=100.0, encoding_type="chebyshev", kernel_type="projected", num_qubits=3, num_layers=1, noise_std=0.1)
+    eager = d.AdmmEngine(shards, theta0, psi0, **kw)
+    for _ in range(4):
+        eager.iteration()
+    graph = d.AdmmEngine(shards, theta0, psi0, **kw)
+    graph.capture()                      # runs one eager iteration as warm-up
+    for _ in range(3):
+        graph.replay()
+    for a, b in zip(eager.state(), graph.state()):
+        assert np.array_equal(a, b)
+
+
 def test_wrong_parameter_count_raises(d):
     g = load_golden("agent_step_yzcx_fid_q2.npz")
     with pytest.raises(ValueError):
