@@ -140,10 +140,15 @@ def run_ours(args, w):
         torch.cuda.synchronize()
 
     step_fn = eng.iteration
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1 and n_i <= 2048)
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
     if use_graph:
-        eng.capture()                            # launch-bound shards: replay the whole iteration as one CUDA graph
-        step_fn = eng.replay
+        try:
+            eng.capture()                        # replay the whole iteration (all agent / look-ahead streams) as one CUDA graph
+            step_fn = eng.replay
+        except Exception as exc:                 # capture is an optimisation, not a requirement
+            print(f"[bench] CUDA graph capture failed ({exc!r}); running eagerly", file=sys.stderr)
+            use_graph = False
+            torch.cuda.synchronize()
     for _ in range(args.warmup):
         step_fn()
     barrier()
