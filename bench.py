@@ -130,6 +130,8 @@ def run_ours(args, w):
     shards, theta0, psi0, n_i, P = make_problem(w, world, rank)
     kw = dict(encoding_type=w["encoding"], kernel_type=w["kernel"], num_qubits=w["q"], num_layers=w["layers"], noise_std=NOISE_STD,
               outer_kernel=w["outer"], shift_value=H, training_ignores_outer_kernel=not w["honour_outer"])
+    if args.outer_blocks > 0:
+        kw["cholesky_outer_blocks"] = args.outer_blocks
     eng = d.AdmmEngine(shards, theta0, psi0, rho=RHO, L=LIP, process_group=pg, rank=rank, world_size=world, **kw)
     S = 2 * P + 1
     entries_per_iter = w["agents"] * S * n_i * n_i
@@ -375,6 +377,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--outer-blocks", type=int, default=0, help="Cholesky outer panel width in 128-blocks (0 = engine default)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"], help="replay the iteration as a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

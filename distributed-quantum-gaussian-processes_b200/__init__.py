@@ -14,6 +14,7 @@ from .kernels import (EncodingCircuit, Executor, FidelityKernel, ProjectedQuantu
 from .agent import RiemannianAgent, process_agent_training, train_agents  # noqa: F401
 from .engine import AgentEngine, AdmmEngine, agent_block, exchange_rows, synthetic_dataset  # noqa: F401
 from .datagen import generate_quantum_gp_data  # noqa: F401
+from .driver import run_admm  # noqa: F401
 from .predict import k_fold_cross_validation_consensus, nlpd, predict_quantum_gp  # noqa: F401
 
 __version__ = "0.1.0"
