@@ -127,6 +127,8 @@ __global__ void __launch_bounds__(PW_THREADS) gram_projected_dmma_kernel(const d
                 x = (x > snap[rb][cb][e]) ? 0.0 : x;                 // |gamma d^2| below rounding level (or negative d^2) -> 0
                 if (SYM && r == cc + e) x = 0.0;
                 v[e] = outer_from_neg_gd2<OUTER>(x, hyp, tab);
+                // NaN features (arccos outside [-1,1]) must propagate as in NumPy: the clamps above would swallow them
+                if (snap[rb][cb][e] != snap[rb][cb][e]) v[e] = snap[rb][cb][e];
             }
             if (r < n1) {
                 double* dst = K + (size_t)r * ldk + cc;

@@ -236,6 +236,73 @@ def test_agent_step_medium_size_against_oracle(d, enc, ktype, q, layers, dd, n):
     assert abs(nll - ref.nll) < 1e-8 * max(1.0, abs(ref.nll))
 
 
+def test_nan_inputs_propagate_and_are_reported(d):
+    """arccos of |x| > 1 (chebyshev / kyriienko without clipping): NaNs propagate through features and K as in
+    the reference; dataset generation reports them like main.py:248-249."""
+    x = np.array([[0.1, 0.2], [1.5, 0.3], [0.4, -0.2]])
+    qk = d.create_quantum_kernel(3, 2, 1, True, "kyriienko", "projected")
+    qk.assign_parameters(np.full(qk.encoding_circuit.num_parameters, 0.3))
+    K = qk.evaluate(x, x)
+    assert np.isnan(K[1]).all() and np.isnan(K[:, 1]).all() and np.isfinite(K[0, 2]) and K[0, 0] == 1.0
+    with pytest.raises(ValueError, match="NaN"):
+        d.generate_quantum_gp_data(20, 2, 3, 1, (-2.0, 2.0), 0.1, True, None, "kyriienko", "projected", data_seed=1)
+
+
+def test_duplicate_samples_match_oracle(d):
+    """Collisions: repeated inputs give identical Gram rows (exact ones off the diagonal); K + sigma^2 I stays SPD."""
+    from oracle import agent_step, driver
+    x, y = driver.synthetic_dataset(90, 3, "hubregtsen")
+    x[10:20] = x[0:10]
+    x[50] = x[51]
+    cfg = agent_step.KernelConfig("hubregtsen", "projected", 4, 2, "gaussian")
+    rs = np.random.RandomState(3)
+    z, psi = np.round(rs.rand(16), 4), np.round(rs.rand(16), 4)
+    ref = agent_step.train_and_update(cfg, x, y, z, psi, 0.1, 100.0, 100.0, want_cond=False, keep_k=True)
+    ag = d.RiemannianAgent("dup", x, y, 4, 0.1, 100.0, 100.0, use_parameter_shift=True, num_layers=2, encoding_type="hubregtsen",
+                           kernel_type="projected")
+    theta, psi_new, nll, _, _ = ag.train_and_update(z, psi)
+    assert ref.K[0, 10] == 1.0
+    assert np.max(np.abs(ag.last_gradient - ref.grad)) < 1e-8 * max(1.0, np.abs(ref.grad).max())
+    assert np.max(np.abs(theta - ref.theta)) < 1e-12 and abs(nll - ref.nll) < 1e-8 * max(1.0, abs(ref.nll))
+
+
+@pytest.mark.parametrize("enc,ktype,q,layers,dd,n,outer", [("hubregtsen", "fidelity", 5, 2, 2, 2048, "gaussian"),
+                                                          ("kyriienko", "projected", 10, 4, 6, 8192, "matern")])
+def test_full_size_properties_other_configs(d, enc, ktype, q, layers, dd, n, outer):
+    """BASELINE.json configs[2] and configs[4] shard sizes: A * A^-1 = I, alpha solves the system, the fused gradient is
+    reproducible bit for bit, and agrees with a materialised torch fp64 contraction for one parameter."""
+    x, y = d.synthetic_dataset(n, dd, enc)
+    eng = d.AgentEngine(x, y, encoding_type=enc, kernel_type=ktype, num_qubits=q, num_layers=layers, noise_std=0.1, rho=100.0,
+                        L=100.0, outer_kernel=outer, training_ignores_outer_kernel=False)
+    z = d.kernels.dev_f64(np.round(np.random.RandomState(42).rand(eng.P), 4))
+    eng.simulate(z); eng.gram()
+    K = eng.solver.matrix().clone()
+    K = torch.tril(K) + torch.tril(K, -1).T
+    assert torch.allclose(torch.diagonal(K), torch.full((n,), 1.01, dtype=torch.float64, device="cuda"), rtol=0, atol=1e-13)
+    eng.factor(); eng.gradient()
+    torch.cuda.synchronize(); eng.check_info()
+    Ainv = torch.tril(eng.solver.inverse()); Ainv = Ainv + Ainv.T - torch.diag(torch.diagonal(Ainv))
+    assert (K @ Ainv - torch.eye(n, dtype=torch.float64, device="cuda")).abs().max().item() < 1e-8
+    yy = torch.from_numpy(y).cuda()
+    assert ((K @ eng.d_alpha - yy).abs().max() / yy.abs().max()).item() < 1e-9
+    g1 = eng.d_grad.clone()
+    eng.gradient(); torch.cuda.synchronize()
+    assert torch.equal(g1, eng.d_grad)
+    B = Ainv - torch.outer(eng.d_alpha, eng.d_alpha)
+    i = eng.P // 2
+    def gram(s):
+        f = eng.d_feat[s]
+        if ktype == "fidelity":
+            c = torch.view_as_complex(f.reshape(n, -1, 2).contiguous())
+            return (c @ c.conj().T).abs() ** 2
+        dist = torch.cdist(f, f)
+        k = dist * 3 ** 0.5
+        return (1 + k) * torch.exp(-k)
+    dK = (gram(1 + 2 * i) - gram(2 + 2 * i)) / (2 * eng.h)
+    ref = 0.5 * (B * dK).sum().item()
+    assert abs(g1[i].item() - ref) < 1e-6 * max(1.0, abs(ref))
+
+
 def test_full_size_properties_config4_shard(d):
     """BASELINE.json configs[3] shard size (n = 8192, yz_cx q=8 L=3 projected-gaussian): size-independent
     properties — K symmetric with unit diagonal in [0,1]; A * A^-1 = I; alpha solves A alpha = y; the fused
