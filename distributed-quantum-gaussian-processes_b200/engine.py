@@ -101,8 +101,6 @@ class AgentEngine:
         self.d_work = torch.empty(max(1, self._lib.dqgp_grad_workspace_bytes(self.n, self.P) // 8), **f64)
         self.entries_per_step = self.S * self.n * self.n    # full squares, all 2P+1 sets
         self.share_prefix = True
-        self.overlap_sim = False
-        self._side = None
 
     def load_data(self, X, Y):
         """Refresh the resident shard from host arrays (the e2e path does this every call, like the
@@ -161,28 +159,12 @@ class AgentEngine:
                                         PERIOD, d_theta_out.data_ptr(), d_psi_out.data_ptr(), stream_ptr()), "admm local")
 
     def step(self, d_z, d_psi, d_theta_out, d_psi_out):
-        """One agent step.  With `overlap_sim` (one agent per GPU) the 2P shifted simulations are enqueued on a side
-        stream AFTER the factorisation's launches: K only needs the unshifted set, and the simulator's CTAs then fill
-        the SMs the Cholesky leaves idle on its latency-bound critical path.  (Enqueued before the factorisation they
-        just delay its GEMMs — measured, no gain.)"""
-        if not self.overlap_sim:
-            self.simulate(d_z)
-            self.gram()
-            self.factor()
-        else:
-            main = torch.cuda.current_stream()
-            if self._side is None:
-                self._side = torch.cuda.Stream()
-                self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
-            self.simulate(d_z, 0, 1)
-            self._ev_fork.record(main)
-            self.gram()
-            self.factor()
-            self._side.wait_event(self._ev_fork)
-            with torch.cuda.stream(self._side):
-                self.simulate(d_z, 1, self.S - 1)
-                self._ev_join.record(self._side)
-            main.wait_event(self._ev_join)
+        # Overlapping the 2P shifted simulations with the factorisation (side streams at equal or lower priority, before
+        # or after the factorisation's launches) was measured three ways and always lost 1-3%: both want the FP64 pipe,
+        # and resident simulator CTAs take the register / shared-memory slots of the trailing-update GEMMs.
+        self.simulate(d_z)
+        self.gram()
+        self.factor()
         self.gradient()
         self.update(d_psi, d_theta_out, d_psi_out)
 
