@@ -96,10 +96,14 @@ void dqgp_solver_destroy(dqgp_solver* s);
 int dqgp_solver_n(const dqgp_solver* s);
 int dqgp_solver_ld(const dqgp_solver* s);
 double* dqgp_solver_matrix(dqgp_solver* s);  /* (n, ld): write A here (lower triangle is what is read) */
-double* dqgp_solver_inverse(dqgp_solver* s); /* (n, ld): A^-1 after dqgp_potrf_solve_inv               */
+double* dqgp_solver_inverse(dqgp_solver* s); /* (n, ld): A^-1 after dqgp_potrf_solve_inv: want_inverse=1 fills the
+                                              * lower 128x128 tiles (what the fused gradient reads), =2 the full matrix */
 double* dqgp_solver_factor(dqgp_solver* s);  /* (n, ld): L (lower) after the call                      */
 size_t dqgp_solver_bytes(const dqgp_solver* s);
 int dqgp_add_diagonal(double* d_A, int n, int lda, double value, void* stream);
+/* want_inverse: <0 factor only, 0 factor + alpha + logdet, 1 + A^-1 (lower tiles), 2 + A^-1 (full symmetric).
+ * Enqueues on `stream` and on the solver's internal high-priority stream (joined back before returning control of
+ * `stream`); graph-capturable. */
 int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, double* d_logdet, int* d_info,
                          int want_inverse, void* stream);
 /* want_inverse < 0 in dqgp_potrf_solve_inv = factor only (d_y, d_alpha may be NULL).
@@ -110,7 +114,8 @@ int dqgp_solver_quadform_rows(dqgp_solver* s, const double* d_B, int nb, int ldb
 
 /* fp64 GEMM building block on the DMMA tensor path (used by the factorisation; exposed for tests):
  * C(MxN) = alpha*A*B + beta*C; A is [m][k] if a_k_contig else [k][m]; B is [n][k] if b_k_contig else [k][n].
- * M, N multiples of 128; K multiple of 16; even leading dimensions; 16-byte aligned pointers. */
+ * M, N multiples of 128; K multiple of 16; even leading dimensions; 16-byte aligned pointers.
+ * Test utility: allocates its one-entry task table with cudaMallocAsync and synchronises `stream` once. */
 int dqgp_dgemm(int a_k_contig, int b_k_contig, int M, int N, int K, double alpha, const double* d_A, int lda,
                const double* d_B, int ldb, double beta, double* d_C, int ldc, void* stream);
 
