@@ -77,8 +77,16 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise DqgpError(f"{LIB_PATH} not found: build it with `python {os.path.join(HERE, 'build.py')}` "
-                        "(nvcc, sm_100a). dqgp_b200 has no CPU fallback.")
+        # not a fallback: the same CUDA sources are compiled on the spot when the toolkit is present
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_dqgp_build", os.path.join(HERE, "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        except Exception as exc:
+            raise DqgpError(f"{LIB_PATH} not found and building it failed ({exc}); build it with "
+                            f"`python {os.path.join(HERE, 'build.py')}` (nvcc, sm_100a). dqgp_b200 has no CPU fallback.") from exc
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)      # AttributeError here = header / library drift
