@@ -53,6 +53,7 @@ SIGNATURES = {
     "dqgp_solver_inverse": (_vp, [_vp]),
     "dqgp_solver_factor": (_vp, [_vp]),
     "dqgp_solver_bytes": (_sz, [_vp]),
+    "dqgp_solver_potrf_launches": (_i, [_vp]),
     "dqgp_add_diagonal": (_i, [_vp, _i, _i, _d, _vp]),
     "dqgp_potrf_solve_inv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "dqgp_solver_quadform_rows": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

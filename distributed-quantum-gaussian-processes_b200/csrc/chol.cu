@@ -9,6 +9,7 @@
 //   solve   alpha = W^T (W y);  logdet = 2 sum log Lii (accumulated by the leaves)
 // The matrix is padded to a multiple of 128 with an identity block, so no kernel has edge cases.
 #include <cmath>
+#include <cstdlib>
 #include "gemm64.cuh"
 
 namespace dqgp {
@@ -29,6 +30,14 @@ struct dqgp_solver {
     cudaStream_t helper;                              // HIGH-priority stream carrying the critical path (leaf, panel solve, next column)
     cudaEvent_t ev_fork, ev_join;
     std::vector<cudaEvent_t> ev_trsm, ev_rest;
+    // look-ahead scheme (default): three dependency classes, see dqgp_potrf_solve_inv
+    std::vector<Group> trsmA, updA, trsmB, updB;      // per 128-column step: critical block row / everything else
+    std::vector<Group> next1, next2, rest;            // per outer panel: rank-(OB*128) updates by distance from the panel
+    cudaStream_t mid;                                 // second internal stream (panel work off the leaf chain)
+    std::vector<cudaEvent_t> ev_leaf, ev_a, ev_b, ev_n1, ev_n2;
+    cudaEvent_t ev_join2;
+    int legacy;                                       // DQGP_POTRF_LEGACY=1: the round-1 two-stream schedule
+    int potrf_launches;
     std::vector<Group> tri_t, tri_w;       // per trtri level
     Group lauum, quad;
     size_t bytes;
@@ -44,13 +53,75 @@ namespace dqgp {
 // run the update loop over half of the k range each (per k: 1 conflict-free LDS + 4 broadcast LDS.128 for 8 DFMA),
 // the helper hands its partial sums over through shared memory, and the primary thread factors the 8x8 diagonal
 // block redundantly in registers (no cross-lane chain) and forward-substitutes its row.
-// Phase 2 inverts L column by column in panels of 8 rows; column j is owned by two ADJACENT lanes that split the k
-// range and combine with one shuffle, so warps never wait for each other (no block barrier in the whole phase).
-// Measured with clock64 (round 1): v3 (128 threads) spent 32K cycles in the phase-1 k-loops, 50K in the per-panel
-// serial part, 51K in the phase-2 k-loops of the slowest thread, 19K in its serial part, 9K storing W = 164K cycles.
+// Phase 2 inverts L by recursive doubling (leaf_join): 8x8 diagonal blocks by substitution, then four levels of
+// W21 = -W22 (L21 W11) as 8x8 DMMA tiles, 8 strips per level = 8 warps (round 1's column-substitution phase took 70K
+// of the leaf's 155K cycles; measured with clock64: v3 spent 32K cycles in the phase-1 k-loops, 50K in the per-panel
+// serial part).
 constexpr int LEAF_THREADS = 256;
 constexpr int LP = 130;
 constexpr size_t LEAF_SMEM_V2 = sizeof(double) * (NB * LP + 2 * NB + 8 * NB);
+
+// One level of the triangular inverse inside the leaf: every pair of inverted BxB diagonal blocks (W11, W22) of the
+// 128x128 factor is joined into a 2Bx2B inverse, W21 = -W22 (L21 W11), as 8x8 DMMA tiles.  M holds L transposed in its
+// strict upper triangle and W in its strict lower triangle (diagonals in s_diag / rdiag), so operand fragments
+// that straddle the diagonal are masked.  Each level has exactly 8 strips of tiles = 8 warps: product 1 (P = L21 W11,
+// written where W21 will live) by row strips, product 2 by column strips - a warp only overwrites P tiles it alone reads.
+template <int B>
+__device__ __forceinline__ void leaf_join(double* __restrict__ M, const double* __restrict__ rdiag, int warp, int lane) {
+    constexpr int NT = B / 8;
+    const int pair = warp / NT, strip = warp % NT;
+    const int r0 = pair * 2 * B;
+    const int g = lane >> 2, t = lane & 3;
+    {
+        const int i0 = r0 + B + 8 * strip;
+        double acc[NT][2];
+#pragma unroll
+        for (int x = 0; x < NT; ++x) acc[x][0] = acc[x][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < B / 4; ++ks) {
+            const int kr = r0 + 4 * ks + t;
+            const double a = M[kr * LP + i0 + g];                    // L[i0+g][kr]
+#pragma unroll
+            for (int tj = 0; tj < NT; ++tj) {
+                if (4 * ks >= 8 * tj) {                              // W11 is lower-triangular: k >= j0
+                    const int jc = r0 + 8 * tj + g;
+                    double b = M[kr * LP + jc];                      // W[kr][jc]
+                    if (4 * ks < 8 * tj + 8) b = (jc < kr) ? b : (jc == kr ? rdiag[kr] : 0.0);
+                    dmma884(acc[tj][0], acc[tj][1], a, b);
+                }
+            }
+        }
+#pragma unroll
+        for (int tj = 0; tj < NT; ++tj)
+            *reinterpret_cast<double2*>(&M[(i0 + g) * LP + r0 + 8 * tj + 2 * t]) = make_double2(acc[tj][0], acc[tj][1]);
+    }
+    __syncthreads();
+    {
+        const int j0 = r0 + 8 * strip;
+        double acc[NT][2];
+#pragma unroll
+        for (int x = 0; x < NT; ++x) acc[x][0] = acc[x][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < B / 4; ++ks) {
+            const int kc = r0 + B + 4 * ks + t;
+            const double b = M[kc * LP + j0 + g];                    // P[kc][j0+g]
+#pragma unroll
+            for (int ti = 0; ti < NT; ++ti) {
+                if (4 * ks < 8 * ti + 8) {                           // W22 is lower-triangular: k <= i
+                    const int ir = r0 + B + 8 * ti + g;
+                    double a = M[ir * LP + kc];                      // W[ir][kc]
+                    if (4 * ks >= 8 * ti) a = (kc < ir) ? a : (kc == ir ? rdiag[ir] : 0.0);
+                    dmma884(acc[ti][0], acc[ti][1], a, b);
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ti = 0; ti < NT; ++ti)
+            *reinterpret_cast<double2*>(&M[(r0 + B + 8 * ti + g) * LP + j0 + 2 * t]) = make_double2(-acc[ti][0], -acc[ti][1]);
+    }
+    __syncthreads();
+}
 
 __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __restrict__ A, int ld, double* __restrict__ W,
                                                                       int blk, double* logdet, int* info, int n_real) {
@@ -183,53 +254,40 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
         }
     }
 
-    // ---------------- phase 2: W = L^-1; column j is owned by lanes (2*(j%16), 2*(j%16)+1) of warp j/16 ----------------
-    const int j = warp * 16 + (lane >> 1);
-    const int h = lane & 1;
-    for (int i0 = 0; i0 < NB; i0 += 8) {
-        if (warp * 16 > i0 + 7) continue;         // whole warp is right of this row panel (warp-uniform)
-        double acc[8];
+    // ---------------- phase 2: W = L^-1 by recursive doubling on the DMMA pipe ----------------
+    // level 0: the 16 diagonal 8x8 blocks by substitution, one thread per column
+    if (tid < NB) {
+        const int j = tid, b0 = j & ~7;
+        double w[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = 0.0;
-        if (j < i0) {
-            // k = j .. i0-1 (W[j][j] = 1/L[j][j], W[k][j] = M[k][j] for k > j); the two lanes take alternate k
-            for (int k = j + h; k < i0; k += 2) {
-                const double w = (k == j) ? s_rdiag[j] : M[k * LP + j];
-                const double2* row = reinterpret_cast<const double2*>(&M[k * LP + i0]);
-                const double2 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
-                acc[0] = fma(w, v0.x, acc[0]); acc[1] = fma(w, v0.y, acc[1]);
-                acc[2] = fma(w, v1.x, acc[2]); acc[3] = fma(w, v1.y, acc[3]);
-                acc[4] = fma(w, v2.x, acc[4]); acc[5] = fma(w, v2.y, acc[5]);
-                acc[6] = fma(w, v3.x, acc[6]); acc[7] = fma(w, v3.y, acc[7]);
+        for (int r = 0; r < 8; ++r) {
+            const int row = b0 + r;
+            double v = 0.0;
+            if (row == j) v = s_rdiag[j];
+            else if (row > j) {
+                double sres = 0.0;
+#pragma unroll
+                for (int r2 = 0; r2 < r; ++r2)
+                    if (b0 + r2 >= j) sres = fma(M[(b0 + r2) * LP + row], w[r2], sres);
+                v = -sres * s_rdiag[row];
             }
+            w[r] = v;
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
-        if (h == 0 && j <= i0 + 7) {
-            double wv[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int row = i0 + r;
-                double w = 0.0;
-                if (row == j) w = s_rdiag[j];
-                else if (row > j) {
-                    double sres = acc[r];
-#pragma unroll
-                    for (int r2 = 0; r2 < r; ++r2)
-                        if (i0 + r2 >= j) sres = fma(M[(i0 + r2) * LP + row], wv[r2], sres);
-                    w = -sres * s_rdiag[row];
-                    M[row * LP + j] = w;
-                }
-                wv[r] = w;
-            }
-        }
-        __syncwarp();
+        for (int r = 0; r < 8; ++r)
+            if (b0 + r > j) M[(b0 + r) * LP + j] = w[r];
     }
     __syncthreads();
+    leaf_join<8>(M, s_rdiag, warp, lane);
+    leaf_join<16>(M, s_rdiag, warp, lane);
+    leaf_join<32>(M, s_rdiag, warp, lane);
+    leaf_join<64>(M, s_rdiag, warp, lane);
+    // lower triangle only: the strict upper triangle of W's diagonal blocks is zeroed once, at solver creation
     for (int e = tid; e < NB * NB / 2; e += LEAF_THREADS) {
         const int r = e >> 6, c = (e & 63) * 2;
+        if (c > r) continue;
         double2 v;
-        v.x = (c < r) ? M[r * LP + c] : (c == r ? s_rdiag[r] : 0.0);
+        v.x = (c < r) ? M[r * LP + c] : s_rdiag[r];
         v.y = (c + 1 < r) ? M[r * LP + c + 1] : (c + 1 == r ? s_rdiag[r] : 0.0);
         *reinterpret_cast<double2*>(Wblk + (size_t)r * ld + c) = v;
     }
@@ -325,6 +383,137 @@ static GemmTask make_task(const double* A, const double* B, double* C, int M, in
 
 }  // namespace dqgp
 
+static int potrf_legacy(dqgp_solver* s, double* d_logdet, int* d_info, cudaStream_t st) {
+    using namespace dqgp;
+    const int ld = s->ld, nblk = s->nblk;
+    // Two-level right-looking Cholesky with look-ahead.  The critical path (leaves, panel solves, updates inside the
+    // current 512-column outer panel, and the rank-512 update of the NEXT panel's columns) runs on the solver's
+    // HIGH-priority stream; the bulk rank-512 update of everything further right stays on the caller's stream and
+    // overlaps the next panel's factorisation.  Priority matters: a leaf CTA needs 133 KB of shared
+    // memory and only fits beside ONE resident GEMM CTA, so it must win the slot a retiring GEMM CTA frees.
+    cudaStream_t crit = s->helper;
+    DQGP_CUDA(cudaEventRecord(s->ev_fork, st));
+    DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_fork, 0));
+    int last_rest = -1;
+    const int OB = s->ob;
+    for (int k = 0; k < nblk; ++k) {
+        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, crit>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
+        DQGP_LAUNCH_CHECK("potrf_leaf_kernel");
+        if (k + 1 >= nblk) break;
+        int rc = launch_gemm_group(s->d_tasks + s->trsm[k].first, s->trsm[k].count, s->trsm[k].tiles, crit);
+        if (rc) return rc;
+        rc = launch_gemm_group(s->d_tasks + s->inner[k].first, s->inner[k].count, s->inner[k].tiles, crit);
+        if (rc) return rc;
+        if ((k + 1) % OB == 0) {                       // an outer panel is complete: rank-(OB*128) trailing update
+            const int p = k / OB;
+            const bool has_rest = s->syrk_rest[p].tiles > 0;
+            if (has_rest) DQGP_CUDA(cudaEventRecord(s->ev_trsm[p], crit));
+            if (last_rest >= 0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_rest[last_rest], 0));   // earlier bulk updates hit these columns
+            rc = launch_gemm_group(s->d_tasks + s->syrk_next[p].first, s->syrk_next[p].count, s->syrk_next[p].tiles, crit);
+            if (rc) return rc;
+            if (has_rest) {
+                DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_trsm[p], 0));
+                rc = launch_gemm_group(s->d_tasks + s->syrk_rest[p].first, s->syrk_rest[p].count, s->syrk_rest[p].tiles, st);
+                if (rc) return rc;
+                DQGP_CUDA(cudaEventRecord(s->ev_rest[p], st));
+                last_rest = p;
+            }
+        }
+    }
+    DQGP_CUDA(cudaEventRecord(s->ev_join, crit));
+    DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+    return 0;
+}
+
+// Right-looking blocked Cholesky as three dependency classes on three streams.
+//   crit (highest priority): leaf_k -> trsmA_k -> updA_k -> leaf_{k+1}: the chain that bounds a lone factorisation.
+//        A leaf needs 133 KB of shared memory and only fits beside ONE resident GEMM CTA, so it must win the slot a
+//        retiring GEMM CTA frees.
+//   mid: the rest of step k (solve of the rows below, rank-128 updates of the panel's own columns and of the FIRST
+//        column of the next panel), then, at a panel end, the rank-(OB*128) update of the next OB columns.
+//   st (caller): the bulk rank-(OB*128) update of everything further right, one panel behind.
+// Every block receives its updates in the same order as in the sequential algorithm (events order all writers of a
+// block), so the factor does not depend on timing.
+static int potrf_lookahead(dqgp_solver* s, double* d_logdet, int* d_info, cudaStream_t st) {
+    using namespace dqgp;
+    const int ld = s->ld, nblk = s->nblk, OB = s->ob;
+    cudaStream_t crit = s->helper, mid = s->mid;
+    auto run = [&](const dqgp_solver::Group& g, cudaStream_t on) { return launch_gemm_group(s->d_tasks + g.first, g.count, g.tiles, on); };
+    DQGP_CUDA(cudaEventRecord(s->ev_fork, st));
+    DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_fork, 0));
+    DQGP_CUDA(cudaStreamWaitEvent(mid, s->ev_fork, 0));
+    // DQGP_POTRF_TRACE=1: time stamps on the critical stream (diagnostics; synchronises and prints to stderr)
+    static const bool trace = getenv("DQGP_POTRF_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto stamp = [&]() { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, crit); tev.push_back(e); } };
+    int last_rest = -1;
+    for (int k = 0; k < nblk; ++k) {
+        const int p = k / OB, p0 = p * OB, pend = std::min(p0 + OB, nblk);
+        stamp();
+        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, crit>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
+        DQGP_LAUNCH_CHECK("potrf_leaf_kernel");
+        stamp();
+        if (k + 1 >= nblk) break;
+        DQGP_CUDA(cudaEventRecord(s->ev_leaf[k], crit));
+        // critical block row
+        if (k > 0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_b[k - 1], 0));            // A(k+1,k) has all its updates
+        int rc = run(s->trsmA[k], crit);
+        if (rc) return rc;
+        DQGP_CUDA(cudaEventRecord(s->ev_a[k], crit));
+        stamp();
+        if (p > 0 && k == p0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_n1[p - 1], 0));     // column p0+1 got the previous panel
+        if (p > 0 && k == p0 + 1) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_n2[p - 1], 0)); // columns p0+2.. likewise
+        rc = run(s->updA[k], crit);
+        if (rc) return rc;
+        stamp();
+        // the rest of the step
+        DQGP_CUDA(cudaStreamWaitEvent(mid, s->ev_leaf[k], 0));
+        rc = run(s->trsmB[k], mid);
+        if (rc) return rc;
+        DQGP_CUDA(cudaStreamWaitEvent(mid, s->ev_a[k], 0));
+        rc = run(s->updB[k], mid);
+        if (rc) return rc;
+        DQGP_CUDA(cudaEventRecord(s->ev_b[k], mid));
+        if (k + 1 == pend && pend < nblk) {            // the panel's columns of L are complete
+            if (last_rest >= 0) DQGP_CUDA(cudaStreamWaitEvent(mid, s->ev_rest[last_rest], 0));   // bulk updates hit these columns
+            rc = run(s->next1[p], mid);
+            if (rc) return rc;
+            DQGP_CUDA(cudaEventRecord(s->ev_n1[p], mid));
+            rc = run(s->next2[p], mid);
+            if (rc) return rc;
+            DQGP_CUDA(cudaEventRecord(s->ev_n2[p], mid));
+            if (s->rest[p].tiles > 0) {
+                DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_b[k], 0));
+                rc = run(s->rest[p], st);
+                if (rc) return rc;
+                DQGP_CUDA(cudaEventRecord(s->ev_rest[p], st));
+                last_rest = p;
+            }
+        }
+    }
+    DQGP_CUDA(cudaEventRecord(s->ev_join, crit));
+    DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
+    DQGP_CUDA(cudaEventRecord(s->ev_join2, mid));
+    DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_join2, 0));
+    if (trace) {
+        cudaStreamSynchronize(st);
+        // per step: [start, leaf end, trsmA end, updA end]
+        double t_leaf = 0, t_trsm = 0, t_upd = 0, t_gap = 0;
+        for (int k = 0; k + 1 < nblk; ++k) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, tev[4 * k], tev[4 * k + 1]);
+            cudaEventElapsedTime(&b, tev[4 * k + 1], tev[4 * k + 2]);
+            cudaEventElapsedTime(&c, tev[4 * k + 2], tev[4 * k + 3]);
+            cudaEventElapsedTime(&d, tev[4 * k + 3], tev[4 * k + 4]);
+            t_leaf += a; t_trsm += b; t_upd += c; t_gap += d;
+            if (k % 8 == 0 || k + 2 >= nblk) fprintf(stderr, "  step %3d: leaf %.1f us  (wait evB +) trsmA %.1f  (wait next +) updA %.1f  gap %.1f\n", k, a * 1e3, b * 1e3, c * 1e3, d * 1e3);
+        }
+        fprintf(stderr, "potrf trace n=%d OB=%d: leaf %.2f ms  trsmA %.2f  updA %.2f  gaps %.2f\n", s->n, OB, t_leaf, t_trsm, t_upd, t_gap);
+        for (auto e : tev) cudaEventDestroy(e);
+    }
+    return 0;
+}
+
 extern "C" {
 
 int dqgp_solver_create(int n, dqgp_solver** out) { return dqgp_solver_create_ex(n, 0, out); }
@@ -342,12 +531,17 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
     s->ld = s->np;
     s->A = s->W = s->T = s->y_pad = s->w = s->partial = s->strip = s->V = nullptr;
     s->d_tasks = nullptr;
-    s->helper = nullptr; s->ev_fork = nullptr; s->ev_join = nullptr;
+    s->helper = nullptr; s->mid = nullptr; s->ev_fork = nullptr; s->ev_join = nullptr; s->ev_join2 = nullptr;
+    {
+        const char* env = getenv("DQGP_POTRF_LEGACY");
+        s->legacy = (env && env[0] == '1') ? 1 : 0;
+    }
     cudaError_t e = cudaGetDevice(&s->device);
     const size_t mat = sizeof(double) * (size_t)s->np * s->ld;
     s->bytes = 3 * mat;
     if (e == cudaSuccess) e = cudaMalloc(&s->A, mat);
     if (e == cudaSuccess) e = cudaMalloc(&s->W, mat);
+    if (e == cudaSuccess) e = cudaMemset(s->W, 0, mat);   // the leaves write only the lower triangle of W's diagonal blocks
     if (e == cudaSuccess) e = cudaMalloc(&s->T, mat);
     if (e == cudaSuccess) e = cudaMalloc(&s->y_pad, sizeof(double) * s->np);
     if (e == cudaSuccess) e = cudaMalloc(&s->w, sizeof(double) * s->np);
@@ -394,6 +588,42 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
             grp.push_back(make_task(at(s->T, c1, p0), at(s->T, c1, p0), at(s->A, c1, c1), np - c1 * NB, np - c1 * NB, w * NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
         s->syrk_rest.push_back(push_group(grp));
     }
+    // ---- look-ahead schedule.  Step k (panel p = k / OB, columns [p0, pend)):
+    //   trsmA[k]  T(k+1,k)   = A(k+1,k) Wkk^T                       (one block row: what the next leaf waits for)
+    //   updA[k]   A(k+1,k+1) -= T(k+1,k) T(k+1,k)^T
+    //   trsmB[k]  T(k+2..,k) = A(k+2..,k) Wkk^T
+    //   updB[k]   columns k+1 .. pend (INCLUDING the first column of the next panel) -= rank-128 terms of column k
+    // Panel p, once its last column is solved (K = w*128):
+    //   next1[p]  column pend+1;  next2[p]  columns pend+2 .. pend+OB;  rest[p]  columns > pend+OB (lower tiles)
+    for (int k = 0; k + 1 < nblk; ++k) {
+        const int p0 = (k / OB) * OB, pend = std::min(p0 + OB, nblk);
+        grp.push_back(make_task(at(s->A, k + 1, k), at(s->W, k, k), at(s->T, k + 1, k), NB, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
+        s->trsmA.push_back(push_group(grp));
+        grp.push_back(make_task(at(s->T, k + 1, k), at(s->T, k + 1, k), at(s->A, k + 1, k + 1), NB, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+        s->updA.push_back(push_group(grp));
+        const int below = np - (k + 2) * NB;
+        if (below > 0)
+            grp.push_back(make_task(at(s->A, k + 2, k), at(s->W, k, k), at(s->T, k + 2, k), below, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
+        s->trsmB.push_back(push_group(grp));
+        if (below > 0)     // column k+1 below its diagonal block
+            grp.push_back(make_task(at(s->T, k + 2, k), at(s->T, k + 1, k), at(s->A, k + 2, k + 1), below, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+        for (int c = k + 2; c <= std::min(pend, nblk - 1); ++c)
+            grp.push_back(make_task(at(s->T, c, k), at(s->T, c, k), at(s->A, c, c), np - c * NB, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+        s->updB.push_back(push_group(grp));
+    }
+    for (int p0 = 0; p0 < nblk; p0 += OB) {
+        const int w = std::min(OB, nblk - p0), pend = p0 + w;
+        const int c1 = pend + 1, c2 = pend + 2, c2e = std::min(pend + OB, nblk - 1), c3 = pend + OB + 1;
+        if (c1 < nblk)
+            grp.push_back(make_task(at(s->T, c1, p0), at(s->T, c1, p0), at(s->A, c1, c1), np - c1 * NB, NB, w * NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+        s->next1.push_back(push_group(grp));
+        if (c2 <= c2e)
+            grp.push_back(make_task(at(s->T, c2, p0), at(s->T, c2, p0), at(s->A, c2, c2), np - c2 * NB, (c2e - c2 + 1) * NB, w * NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+        s->next2.push_back(push_group(grp));
+        if (c3 < nblk)
+            grp.push_back(make_task(at(s->T, c3, p0), at(s->T, c3, p0), at(s->A, c3, c3), np - c3 * NB, np - c3 * NB, w * NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
+        s->rest.push_back(push_group(grp));
+    }
     // trtri levels: spans of `span` blocks are already inverted; join neighbours pairwise
     for (int span = 1; span < nblk; span *= 2) {
         std::vector<GemmTask> gt, gw;
@@ -424,6 +654,24 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         e = cudaStreamCreateWithPriority(&s->helper, cudaStreamNonBlocking, hi);
+        // panel work: above the caller's bulk updates, below the leaf chain when the device has a level in between
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->mid, cudaStreamNonBlocking, (hi + 1 < lo) ? hi + 1 : hi);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join2, cudaEventDisableTiming);
+    auto make_events = [&](std::vector<cudaEvent_t>& v, int count) {
+        for (int i = 0; i < count && e == cudaSuccess; ++i) {
+            cudaEvent_t ev;
+            e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e == cudaSuccess) v.push_back(ev);
+        }
+    };
+    make_events(s->ev_leaf, nblk); make_events(s->ev_a, nblk); make_events(s->ev_b, nblk);
+    make_events(s->ev_n1, (nblk + s->ob - 1) / s->ob); make_events(s->ev_n2, (nblk + s->ob - 1) / s->ob);
+    {
+        int cnt = nblk;
+        for (int k = 0; k + 1 < nblk; ++k) cnt += 2 + (s->trsmB[k].tiles > 0) + (s->updB[k].tiles > 0);
+        for (size_t p = 0; p < s->rest.size(); ++p) cnt += (s->next1[p].tiles > 0) + (s->next2[p].tiles > 0) + (s->rest[p].tiles > 0);
+        s->potrf_launches = cnt;
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
@@ -445,6 +693,10 @@ void dqgp_solver_destroy(dqgp_solver* s) {
     if (!s) return;
     for (auto ev : s->ev_trsm) cudaEventDestroy(ev);
     for (auto ev : s->ev_rest) cudaEventDestroy(ev);
+    for (auto* v : {&s->ev_leaf, &s->ev_a, &s->ev_b, &s->ev_n1, &s->ev_n2})
+        for (auto ev : *v) cudaEventDestroy(ev);
+    if (s->ev_join2) cudaEventDestroy(s->ev_join2);
+    if (s->mid) cudaStreamDestroy(s->mid);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->helper) cudaStreamDestroy(s->helper);
@@ -457,6 +709,7 @@ double* dqgp_solver_matrix(dqgp_solver* s) { return s ? s->A : nullptr; }
 double* dqgp_solver_inverse(dqgp_solver* s) { return s ? s->T : nullptr; }
 double* dqgp_solver_factor(dqgp_solver* s) { return s ? s->A : nullptr; }
 size_t dqgp_solver_bytes(const dqgp_solver* s) { return s ? s->bytes : 0; }
+int dqgp_solver_potrf_launches(const dqgp_solver* s) { return s ? s->potrf_launches : -1; }
 
 int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, double* d_logdet, int* d_info, int want_inverse,
                          void* stream) {
@@ -468,42 +721,13 @@ int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, dou
     pad_vector_kernel<<<(np + 255) / 256, 256, 0, st>>>(factor_only ? nullptr : d_y, s->n, np, s->y_pad, d_logdet, d_info);
     if (np != s->n) pad_identity_kernel<<<np, 256, 0, st>>>(s->A, s->n, np, ld);
     DQGP_LAUNCH_CHECK("pad kernels");
-    // Two-level right-looking Cholesky with look-ahead.  The critical path (leaves, panel solves, updates inside the
-    // current 512-column outer panel, and the rank-512 update of the NEXT panel's columns) runs on the solver's
-    // HIGH-priority stream; the bulk rank-512 update of everything further right stays on the caller's stream and
-    // overlaps the next panel's factorisation.  Priority matters: a leaf CTA needs 133 KB of shared
-    // memory and only fits beside ONE resident GEMM CTA, so it must win the slot a retiring GEMM CTA frees.
-    cudaStream_t crit = s->helper;
-    DQGP_CUDA(cudaEventRecord(s->ev_fork, st));
-    DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_fork, 0));
-    int last_rest = -1;
-    const int OB = s->ob;
-    for (int k = 0; k < nblk; ++k) {
-        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, crit>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
-        DQGP_LAUNCH_CHECK("potrf_leaf_kernel");
-        if (k + 1 >= nblk) break;
-        int rc = launch_gemm_group(s->d_tasks + s->trsm[k].first, s->trsm[k].count, s->trsm[k].tiles, crit);
+    if (s->legacy) {
+        int rc = potrf_legacy(s, d_logdet, d_info, st);
         if (rc) return rc;
-        rc = launch_gemm_group(s->d_tasks + s->inner[k].first, s->inner[k].count, s->inner[k].tiles, crit);
+    } else {
+        int rc = potrf_lookahead(s, d_logdet, d_info, st);
         if (rc) return rc;
-        if ((k + 1) % OB == 0) {                       // an outer panel is complete: rank-(OB*128) trailing update
-            const int p = k / OB;
-            const bool has_rest = s->syrk_rest[p].tiles > 0;
-            if (has_rest) DQGP_CUDA(cudaEventRecord(s->ev_trsm[p], crit));
-            if (last_rest >= 0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_rest[last_rest], 0));   // earlier bulk updates hit these columns
-            rc = launch_gemm_group(s->d_tasks + s->syrk_next[p].first, s->syrk_next[p].count, s->syrk_next[p].tiles, crit);
-            if (rc) return rc;
-            if (has_rest) {
-                DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_trsm[p], 0));
-                rc = launch_gemm_group(s->d_tasks + s->syrk_rest[p].first, s->syrk_rest[p].count, s->syrk_rest[p].tiles, st);
-                if (rc) return rc;
-                DQGP_CUDA(cudaEventRecord(s->ev_rest[p], st));
-                last_rest = p;
-            }
-        }
     }
-    DQGP_CUDA(cudaEventRecord(s->ev_join, crit));
-    DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
     if (nblk > 1) {
         copy_lower_blocks_kernel<<<dim3(nblk - 1, nblk - 1), 256, 0, st>>>(s->T, s->A, ld);
         DQGP_LAUNCH_CHECK("copy_lower_blocks_kernel");

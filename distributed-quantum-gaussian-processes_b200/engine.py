@@ -171,11 +171,8 @@ class AgentEngine:
     def launches_per_step(self):
         """Kernel launches of one step() (counted from the launch structure of csrc/chol.cu and friends)."""
         nblk = (self.n + 127) // 128
-        ob = self.cholesky_outer_blocks if self.cholesky_outer_blocks > 0 else 4
-        panels = (nblk + ob - 1) // ob
-        inner = sum(1 for k in range(nblk - 1) if k + 1 < min((k // ob + 1) * ob, nblk))
         levels = int(np.ceil(np.log2(nblk))) if nblk > 1 else 0
-        potrf = nblk + (nblk - 1) + inner + max(panels - 1, 0) + max(panels - 2, 0) + (1 if nblk > 1 else 0)
+        potrf = self._lib.dqgp_solver_potrf_launches(self.solver.handle) + (1 if nblk > 1 else 0)   # + copy of the panels
         pad = 1 + (1 if self.n % 128 else 0)
         return (2 + 2 + pad + potrf + 2 * levels + 3 + 1        # sets, sim, gram, diag, pad, potrf, trtri, solve, lauum
                 + (3 if self.kernel_type == "projected" else 2) + 1 + 1)   # (norms) grad reduce, nll, local update

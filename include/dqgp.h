@@ -100,6 +100,7 @@ double* dqgp_solver_inverse(dqgp_solver* s); /* (n, ld): A^-1 after dqgp_potrf_s
                                               * lower 128x128 tiles (what the fused gradient reads), =2 the full matrix */
 double* dqgp_solver_factor(dqgp_solver* s);  /* (n, ld): L (lower) after the call                      */
 size_t dqgp_solver_bytes(const dqgp_solver* s);
+int dqgp_solver_potrf_launches(const dqgp_solver* s); /* kernel launches of the Cholesky stage (bench launch accounting) */
 int dqgp_add_diagonal(double* d_A, int n, int lda, double value, void* stream);
 /* want_inverse: <0 factor only, 0 factor + alpha + logdet, 1 + A^-1 (lower tiles), 2 + A^-1 (full symmetric).
  * Enqueues on `stream` and on the solver's internal high-priority stream (joined back before returning control of
