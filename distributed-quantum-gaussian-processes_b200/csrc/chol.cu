@@ -2,7 +2,8 @@
 // Replaces the LAPACK sequence of RiemannianAgent.train_and_update (reference agent_riemannian.py:410-418:
 // cholesky, 4x general solve incl. an explicit inverse against eye(n); :442 slogdet) with
 //   potrf   right-looking, nb = 128: [leaf: factor + invert the diagonal block] -> [panel = panel * inv(Lkk)^T]
-//           -> [trailing -= panel panel^T]           (trailing update on DMMA, n^3/3 flops)
+//           -> [trailing -= panel panel^T]           (trailing update on DMMA, n^3/3 flops), scheduled as three
+//           dependency classes on three streams (potrf_lookahead): the leaf chain runs at 68 us per 128 columns
 //   trtri   W = L^-1 by recursive halving: W21 = -W22 (L21 W11), all products of one level in ONE grouped
 //           launch (2 launches per level, log2(n/128) levels, n^3/3 flops on DMMA)
 //   lauum   A^-1 = W^T W, lower tiles only, contraction range clipped to the triangular support (n^3/3)
@@ -24,19 +25,16 @@ struct dqgp_solver {
     dqgp::GemmTask* d_tasks;
     // launch groups: [first task, task count, tiles]
     struct Group { int first, count, tiles; };
-    std::vector<Group> trsm, inner;                   // per 128-column step: panel solve, update inside the outer panel
-    std::vector<Group> syrk_next, syrk_rest;          // per outer panel (512 columns): next panel's columns / the bulk
     int ob;                                           // outer panel width in 128-blocks (1 = single-level)
     cudaStream_t helper;                              // HIGH-priority stream carrying the critical path (leaf, panel solve, next column)
     cudaEvent_t ev_fork, ev_join;
-    std::vector<cudaEvent_t> ev_trsm, ev_rest;
-    // look-ahead scheme (default): three dependency classes, see dqgp_potrf_solve_inv
+    std::vector<cudaEvent_t> ev_rest;
+    // potrf launch groups: three dependency classes, see potrf_lookahead
     std::vector<Group> trsmA, updA, trsmB, updB;      // per 128-column step: critical block row / everything else
     std::vector<Group> next1, next2, rest;            // per outer panel: rank-(OB*128) updates by distance from the panel
     cudaStream_t mid;                                 // second internal stream (panel work off the leaf chain)
     std::vector<cudaEvent_t> ev_leaf, ev_a, ev_b, ev_n1, ev_n2;
     cudaEvent_t ev_join2;
-    int legacy;                                       // DQGP_POTRF_LEGACY=1: the round-1 two-stream schedule
     int potrf_launches;
     std::vector<Group> tri_t, tri_w;       // per trtri level
     Group lauum, quad;
@@ -383,48 +381,6 @@ static GemmTask make_task(const double* A, const double* B, double* C, int M, in
 
 }  // namespace dqgp
 
-static int potrf_legacy(dqgp_solver* s, double* d_logdet, int* d_info, cudaStream_t st) {
-    using namespace dqgp;
-    const int ld = s->ld, nblk = s->nblk;
-    // Two-level right-looking Cholesky with look-ahead.  The critical path (leaves, panel solves, updates inside the
-    // current 512-column outer panel, and the rank-512 update of the NEXT panel's columns) runs on the solver's
-    // HIGH-priority stream; the bulk rank-512 update of everything further right stays on the caller's stream and
-    // overlaps the next panel's factorisation.  Priority matters: a leaf CTA needs 133 KB of shared
-    // memory and only fits beside ONE resident GEMM CTA, so it must win the slot a retiring GEMM CTA frees.
-    cudaStream_t crit = s->helper;
-    DQGP_CUDA(cudaEventRecord(s->ev_fork, st));
-    DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_fork, 0));
-    int last_rest = -1;
-    const int OB = s->ob;
-    for (int k = 0; k < nblk; ++k) {
-        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, crit>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
-        DQGP_LAUNCH_CHECK("potrf_leaf_kernel");
-        if (k + 1 >= nblk) break;
-        int rc = launch_gemm_group(s->d_tasks + s->trsm[k].first, s->trsm[k].count, s->trsm[k].tiles, crit);
-        if (rc) return rc;
-        rc = launch_gemm_group(s->d_tasks + s->inner[k].first, s->inner[k].count, s->inner[k].tiles, crit);
-        if (rc) return rc;
-        if ((k + 1) % OB == 0) {                       // an outer panel is complete: rank-(OB*128) trailing update
-            const int p = k / OB;
-            const bool has_rest = s->syrk_rest[p].tiles > 0;
-            if (has_rest) DQGP_CUDA(cudaEventRecord(s->ev_trsm[p], crit));
-            if (last_rest >= 0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_rest[last_rest], 0));   // earlier bulk updates hit these columns
-            rc = launch_gemm_group(s->d_tasks + s->syrk_next[p].first, s->syrk_next[p].count, s->syrk_next[p].tiles, crit);
-            if (rc) return rc;
-            if (has_rest) {
-                DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_trsm[p], 0));
-                rc = launch_gemm_group(s->d_tasks + s->syrk_rest[p].first, s->syrk_rest[p].count, s->syrk_rest[p].tiles, st);
-                if (rc) return rc;
-                DQGP_CUDA(cudaEventRecord(s->ev_rest[p], st));
-                last_rest = p;
-            }
-        }
-    }
-    DQGP_CUDA(cudaEventRecord(s->ev_join, crit));
-    DQGP_CUDA(cudaStreamWaitEvent(st, s->ev_join, 0));
-    return 0;
-}
-
 // Right-looking blocked Cholesky as three dependency classes on three streams.
 //   crit (highest priority): leaf_k -> trsmA_k -> updA_k -> leaf_{k+1}: the chain that bounds a lone factorisation.
 //        A leaf needs 133 KB of shared memory and only fits beside ONE resident GEMM CTA, so it must win the slot a
@@ -439,6 +395,7 @@ static int potrf_lookahead(dqgp_solver* s, double* d_logdet, int* d_info, cudaSt
     const int ld = s->ld, nblk = s->nblk, OB = s->ob;
     cudaStream_t crit = s->helper, mid = s->mid;
     auto run = [&](const dqgp_solver::Group& g, cudaStream_t on) { return launch_gemm_group(s->d_tasks + g.first, g.count, g.tiles, on); };
+    auto run_small = [&](const dqgp_solver::Group& g, cudaStream_t on) { return launch_gemm_group_small(s->d_tasks + g.first, g.count, g.tiles, on); };
     DQGP_CUDA(cudaEventRecord(s->ev_fork, st));
     DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_fork, 0));
     DQGP_CUDA(cudaStreamWaitEvent(mid, s->ev_fork, 0));
@@ -457,13 +414,13 @@ static int potrf_lookahead(dqgp_solver* s, double* d_logdet, int* d_info, cudaSt
         DQGP_CUDA(cudaEventRecord(s->ev_leaf[k], crit));
         // critical block row
         if (k > 0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_b[k - 1], 0));            // A(k+1,k) has all its updates
-        int rc = run(s->trsmA[k], crit);
+        int rc = run_small(s->trsmA[k], crit);
         if (rc) return rc;
         DQGP_CUDA(cudaEventRecord(s->ev_a[k], crit));
         stamp();
         if (p > 0 && k == p0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_n1[p - 1], 0));     // column p0+1 got the previous panel
         if (p > 0 && k == p0 + 1) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_n2[p - 1], 0)); // columns p0+2.. likewise
-        rc = run(s->updA[k], crit);
+        rc = run_small(s->updA[k], crit);
         if (rc) return rc;
         stamp();
         // the rest of the step
@@ -506,7 +463,7 @@ static int potrf_lookahead(dqgp_solver* s, double* d_logdet, int* d_info, cudaSt
             cudaEventElapsedTime(&c, tev[4 * k + 2], tev[4 * k + 3]);
             cudaEventElapsedTime(&d, tev[4 * k + 3], tev[4 * k + 4]);
             t_leaf += a; t_trsm += b; t_upd += c; t_gap += d;
-            if (k % 8 == 0 || k + 2 >= nblk) fprintf(stderr, "  step %3d: leaf %.1f us  (wait evB +) trsmA %.1f  (wait next +) updA %.1f  gap %.1f\n", k, a * 1e3, b * 1e3, c * 1e3, d * 1e3);
+            if (k % 2 == 0 || k + 2 >= nblk) fprintf(stderr, "  step %3d: leaf %.1f us  (wait evB +) trsmA %.1f  (wait next +) updA %.1f  gap %.1f\n", k, a * 1e3, b * 1e3, c * 1e3, d * 1e3);
         }
         fprintf(stderr, "potrf trace n=%d OB=%d: leaf %.2f ms  trsmA %.2f  updA %.2f  gaps %.2f\n", s->n, OB, t_leaf, t_trsm, t_upd, t_gap);
         for (auto e : tev) cudaEventDestroy(e);
@@ -532,10 +489,6 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
     s->A = s->W = s->T = s->y_pad = s->w = s->partial = s->strip = s->V = nullptr;
     s->d_tasks = nullptr;
     s->helper = nullptr; s->mid = nullptr; s->ev_fork = nullptr; s->ev_join = nullptr; s->ev_join2 = nullptr;
-    {
-        const char* env = getenv("DQGP_POTRF_LEGACY");
-        s->legacy = (env && env[0] == '1') ? 1 : 0;
-    }
     cudaError_t e = cudaGetDevice(&s->device);
     const size_t mat = sizeof(double) * (size_t)s->np * s->ld;
     s->bytes = 3 * mat;
@@ -561,33 +514,8 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
     const int ld = s->ld, np = s->np, nblk = s->nblk;
     auto at = [&](double* base, int rb, int cb) { return base + (size_t)rb * NB * ld + (size_t)cb * NB; };
     std::vector<GemmTask> grp;
-    // potrf: two-level blocking.  Outer panels of OB = 4 block columns (512); inside a panel the 128-wide steps
-    // update only the panel's own columns (K = 128, little work); the trailing matrix gets ONE rank-512 update per
-    // outer panel (K = 512: the GEMM runs near its long-K efficiency instead of the 60% of K = 128 updates).
+    auto small = [](GemmTask t) { t.tiles = gemm_task_tiles_small(t); return t; };
     const int OB = s->ob;
-    for (int k = 0; k + 1 < nblk; ++k) {
-        const int rest = np - (k + 1) * NB;
-        // panel solve out of place (A -> T): two 64-column tiles share the same input rows, so in place would race;
-        // the strictly-lower blocks of L are copied back T -> A once, after the last step
-        grp.push_back(make_task(at(s->A, k + 1, k), at(s->W, k, k), at(s->T, k + 1, k), rest, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
-        s->trsm.push_back(push_group(grp));
-        const int pend = std::min(((k / OB) + 1) * OB, nblk);     // first block column after this outer panel
-        for (int c = k + 1; c < pend; ++c)                         // block column c of the panel, rows c..end
-            grp.push_back(make_task(at(s->T, c, k), at(s->T, c, k), at(s->A, c, c), np - c * NB, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
-        s->inner.push_back(push_group(grp));
-    }
-    for (int p0 = 0; p0 < nblk; p0 += OB) {
-        const int w = std::min(OB, nblk - p0);                    // panel width in blocks
-        const int c0 = p0 + w;                                    // first trailing block column
-        const int wn = std::min(OB, nblk - c0);                   // width of the next panel
-        if (wn > 0)   // columns of the next outer panel, all rows below: on the critical path
-            grp.push_back(make_task(at(s->T, c0, p0), at(s->T, c0, p0), at(s->A, c0, c0), np - c0 * NB, wn * NB, w * NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
-        s->syrk_next.push_back(push_group(grp));
-        const int c1 = c0 + wn;
-        if (wn > 0 && c1 < nblk)   // everything further right: the bulk, overlapped with the next panel's factorisation
-            grp.push_back(make_task(at(s->T, c1, p0), at(s->T, c1, p0), at(s->A, c1, c1), np - c1 * NB, np - c1 * NB, w * NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
-        s->syrk_rest.push_back(push_group(grp));
-    }
     // ---- look-ahead schedule.  Step k (panel p = k / OB, columns [p0, pend)):
     //   trsmA[k]  T(k+1,k)   = A(k+1,k) Wkk^T                       (one block row: what the next leaf waits for)
     //   updA[k]   A(k+1,k+1) -= T(k+1,k) T(k+1,k)^T
@@ -597,9 +525,10 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
     //   next1[p]  column pend+1;  next2[p]  columns pend+2 .. pend+OB;  rest[p]  columns > pend+OB (lower tiles)
     for (int k = 0; k + 1 < nblk; ++k) {
         const int p0 = (k / OB) * OB, pend = std::min(p0 + OB, nblk);
-        grp.push_back(make_task(at(s->A, k + 1, k), at(s->W, k, k), at(s->T, k + 1, k), NB, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
+        // the two products on the leaf chain run on the small-tile kernel: 16 (10 for the symmetric update) CTAs of 32x32
+        grp.push_back(small(make_task(at(s->A, k + 1, k), at(s->W, k, k), at(s->T, k + 1, k), NB, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0)));
         s->trsmA.push_back(push_group(grp));
-        grp.push_back(make_task(at(s->T, k + 1, k), at(s->T, k + 1, k), at(s->A, k + 1, k + 1), NB, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+        grp.push_back(small(make_task(at(s->T, k + 1, k), at(s->T, k + 1, k), at(s->A, k + 1, k + 1), NB, NB, NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0)));
         s->updA.push_back(push_group(grp));
         const int below = np - (k + 2) * NB;
         if (below > 0)
@@ -675,12 +604,7 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
-    for (int k = 0; k < (nblk + s->ob - 1) / s->ob && e == cudaSuccess; ++k) {
-        cudaEvent_t a, b;
-        e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
-        if (e == cudaSuccess) { s->ev_trsm.push_back(a); s->ev_rest.push_back(b); }
-    }
+    make_events(s->ev_rest, (nblk + s->ob - 1) / s->ob);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM_V2);
     if (e != cudaSuccess) { dqgp_solver_destroy(s); return cuda_fail(e, "dqgp_solver_create (task table)"); }
     int rc = gemm_init();
@@ -691,9 +615,7 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
 
 void dqgp_solver_destroy(dqgp_solver* s) {
     if (!s) return;
-    for (auto ev : s->ev_trsm) cudaEventDestroy(ev);
-    for (auto ev : s->ev_rest) cudaEventDestroy(ev);
-    for (auto* v : {&s->ev_leaf, &s->ev_a, &s->ev_b, &s->ev_n1, &s->ev_n2})
+    for (auto* v : {&s->ev_leaf, &s->ev_a, &s->ev_b, &s->ev_n1, &s->ev_n2, &s->ev_rest})
         for (auto ev : *v) cudaEventDestroy(ev);
     if (s->ev_join2) cudaEventDestroy(s->ev_join2);
     if (s->mid) cudaStreamDestroy(s->mid);
@@ -721,10 +643,7 @@ int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, dou
     pad_vector_kernel<<<(np + 255) / 256, 256, 0, st>>>(factor_only ? nullptr : d_y, s->n, np, s->y_pad, d_logdet, d_info);
     if (np != s->n) pad_identity_kernel<<<np, 256, 0, st>>>(s->A, s->n, np, ld);
     DQGP_LAUNCH_CHECK("pad kernels");
-    if (s->legacy) {
-        int rc = potrf_legacy(s, d_logdet, d_info, st);
-        if (rc) return rc;
-    } else {
+    {
         int rc = potrf_lookahead(s, d_logdet, d_info, st);
         if (rc) return rc;
     }

@@ -10,55 +10,66 @@
 
 namespace dqgp {
 
-template <int ROWS, int PITCH_R>
+template <int ROWS, int PITCH_R, int THREADS>
 __device__ __forceinline__ void gm_load_operand(double* sm, const double* __restrict__ g, int ld, int row0, int k0, int k_contig) {
     // ROWS rows x 16 k doubles as 16-byte chunks
     constexpr int CHUNKS = ROWS * GM_KC / 2;
+    static_assert(CHUNKS % THREADS == 0, "operand chunks must divide over the CTA");
     if (k_contig) {
 #pragma unroll
-        for (int i = 0; i < CHUNKS / GM_THREADS; ++i) {
-            const int c = threadIdx.x + GM_THREADS * i;
+        for (int i = 0; i < CHUNKS / THREADS; ++i) {
+            const int c = threadIdx.x + THREADS * i;
             const int row = c >> 3, kc = (c & 7) * 2;
             cp_async16(sm + row * GM_PITCH_K + kc, g + (size_t)(row0 + row) * ld + k0 + kc);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < CHUNKS / GM_THREADS; ++i) {
-            const int c = threadIdx.x + GM_THREADS * i;
+        for (int i = 0; i < CHUNKS / THREADS; ++i) {
+            const int c = threadIdx.x + THREADS * i;
             const int k = c / (ROWS / 2), mc = (c % (ROWS / 2)) * 2;
             cp_async16(sm + k * PITCH_R + mc, g + (size_t)(k0 + k) * ld + row0 + mc);
         }
     }
 }
 
-template <int AK, int BK>
+template <typename S, int AK, int BK>
 __device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* gm_smem);
 
-__global__ void __launch_bounds__(GM_THREADS, 2) gemm_group_kernel(const GemmTask* __restrict__ tasks, int n_tasks) {
-    extern __shared__ __align__(16) double gm_smem[];
-    // locate the task that owns this tile (tables are short: <= a few hundred entries)
-    int ti = 0;
-    {
-        int lo = 0, hi = n_tasks - 1;
-        const int tile = blockIdx.x;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tasks[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
-        }
-        ti = lo;
+__device__ __forceinline__ int gm_find_task(const GemmTask* __restrict__ tasks, int n_tasks, int tile) {
+    int lo = 0, hi = n_tasks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tasks[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
     }
-    const GemmTask T = tasks[ti];
+    return lo;
+}
+
+template <typename S>
+__device__ __forceinline__ void gm_dispatch(const GemmTask* __restrict__ tasks, int n_tasks, double* gm_smem) {
+    // locate the task that owns this tile (tables are short: <= a few hundred entries)
+    const GemmTask T = tasks[gm_find_task(tasks, n_tasks, blockIdx.x)];
     const int local = blockIdx.x - T.tile_begin;
     // operand layouts are compile-time inside the tile routine (no predicated duplicate fragment loads)
     if (T.a_k_contig) {
-        if (T.b_k_contig) gemm_tile<1, 1>(T, local, gm_smem); else gemm_tile<1, 0>(T, local, gm_smem);
+        if (T.b_k_contig) gemm_tile<S, 1, 1>(T, local, gm_smem); else gemm_tile<S, 1, 0>(T, local, gm_smem);
     } else {
-        if (T.b_k_contig) gemm_tile<0, 1>(T, local, gm_smem); else gemm_tile<0, 0>(T, local, gm_smem);
+        if (T.b_k_contig) gemm_tile<S, 0, 1>(T, local, gm_smem); else gemm_tile<S, 0, 0>(T, local, gm_smem);
     }
 }
 
-template <int AK, int BK>
+__global__ void __launch_bounds__(GemmBig::THREADS, 2) gemm_group_kernel(const GemmTask* __restrict__ tasks, int n_tasks) {
+    extern __shared__ __align__(16) double gm_smem[];
+    gm_dispatch<GemmBig>(tasks, n_tasks, gm_smem);
+}
+__global__ void __launch_bounds__(GemmSmall::THREADS, 4) gemm_small_kernel(const GemmTask* __restrict__ tasks, int n_tasks) {
+    extern __shared__ __align__(16) double gm_smem[];
+    gm_dispatch<GemmSmall>(tasks, n_tasks, gm_smem);
+}
+
+template <typename S, int AK, int BK>
 __device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* gm_smem) {
+    constexpr int GM_BM = S::BM, GM_BN = S::BN, MI = S::MI, NI = S::NI;
+    constexpr int GM_PITCH_M = S::PITCH_M, GM_PITCH_N = S::PITCH_N, GM_STAGE_DOUBLES = S::STAGE_DOUBLES, GM_A_DOUBLES = S::A_DOUBLES;
     constexpr int R = GM_BM / GM_BN;
     int tm, tn;
     if (T.lower_tiles) {
@@ -91,14 +102,15 @@ __device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* 
     const int n_chunks = (ke - kb) / GM_KC;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = warp >> 1, wn = warp & 1;     // 4 x 2 warps, 32 x 32 each
+    const int wm = warp / S::WC, wn = warp % S::WC;     // WR x WC warps, (8 MI) x (8 NI) each
     const int g = lane >> 2, t = lane & 3;
+    constexpr int WROWS = 8 * MI, WCOLS = 8 * NI;
 
-    double acc[4][4][2];
+    double acc[MI][NI][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto stage_a = [&](int s) { return gm_smem + (size_t)s * GM_STAGE_DOUBLES; };
     auto stage_b = [&](int s) { return gm_smem + (size_t)s * GM_STAGE_DOUBLES + GM_A_DOUBLES; };
@@ -106,8 +118,8 @@ __device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* 
 #pragma unroll
     for (int s = 0; s < GM_STAGES - 1; ++s) {
         if (s < n_chunks) {
-            gm_load_operand<GM_BM, GM_PITCH_M>(stage_a(s), T.A, T.lda, m0, kb + s * GM_KC, AK);
-            gm_load_operand<GM_BN, GM_PITCH_N>(stage_b(s), T.B, T.ldb, n0, kb + s * GM_KC, BK);
+            gm_load_operand<GM_BM, GM_PITCH_M, S::THREADS>(stage_a(s), T.A, T.lda, m0, kb + s * GM_KC, AK);
+            gm_load_operand<GM_BN, GM_PITCH_N, S::THREADS>(stage_b(s), T.B, T.ldb, n0, kb + s * GM_KC, BK);
         }
         cp_async_commit();
     }
@@ -118,8 +130,8 @@ __device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* 
             const int nx = ch + GM_STAGES - 1;
             if (nx < n_chunks) {
                 const int s = nx % GM_STAGES;
-                gm_load_operand<GM_BM, GM_PITCH_M>(stage_a(s), T.A, T.lda, m0, kb + nx * GM_KC, AK);
-                gm_load_operand<GM_BN, GM_PITCH_N>(stage_b(s), T.B, T.ldb, n0, kb + nx * GM_KC, BK);
+                gm_load_operand<GM_BM, GM_PITCH_M, S::THREADS>(stage_a(s), T.A, T.lda, m0, kb + nx * GM_KC, AK);
+                gm_load_operand<GM_BN, GM_PITCH_N, S::THREADS>(stage_b(s), T.B, T.ldb, n0, kb + nx * GM_KC, BK);
             }
             cp_async_commit();
         }
@@ -127,36 +139,36 @@ __device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* 
         const double* Bs = stage_b(ch % GM_STAGES);
 #pragma unroll
         for (int kk = 0; kk < GM_KC / 4; ++kk) {
-            double a[4], b[4];
+            double a[MI], b[NI];
             if (AK) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = As[(wm * 32 + i * 8 + g) * GM_PITCH_K + kk * 4 + t];
+                for (int i = 0; i < MI; ++i) a[i] = As[(wm * WROWS + i * 8 + g) * GM_PITCH_K + kk * 4 + t];
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = As[(kk * 4 + t) * GM_PITCH_M + wm * 32 + i * 8 + g];
+                for (int i = 0; i < MI; ++i) a[i] = As[(kk * 4 + t) * GM_PITCH_M + wm * WROWS + i * 8 + g];
             }
             if (BK) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Bs[(wn * 32 + j * 8 + g) * GM_PITCH_K + kk * 4 + t];
+                for (int j = 0; j < NI; ++j) b[j] = Bs[(wn * WCOLS + j * 8 + g) * GM_PITCH_K + kk * 4 + t];
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = Bs[(kk * 4 + t) * GM_PITCH_N + wn * 32 + j * 8 + g];
+                for (int j = 0; j < NI; ++j) b[j] = Bs[(kk * 4 + t) * GM_PITCH_N + wn * WCOLS + j * 8 + g];
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     cp_async_wait<0>();
 
     // epilogue: each lane owns 2 adjacent doubles per 8x8 block -> 16-byte accesses
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = m0 + wm * 32 + i * 8 + g;
+    for (int i = 0; i < MI; ++i) {
+        const int r = m0 + wm * WROWS + i * 8 + g;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = n0 + wn * 32 + j * 8 + 2 * t;
+        for (int j = 0; j < NI; ++j) {
+            const int c = n0 + wn * WCOLS + j * 8 + 2 * t;
             double2* dst = reinterpret_cast<double2*>(T.C + (size_t)r * T.ldc + c);
             double2 v = make_double2(T.alpha * acc[i][j][0], T.alpha * acc[i][j][1]);
             if (T.beta != 0.0) {
@@ -174,7 +186,8 @@ int gemm_init() {
     int dev = 0;
     DQGP_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && done[dev]) return 0;
-    DQGP_CUDA(cudaFuncSetAttribute(gemm_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM_BYTES));
+    DQGP_CUDA(cudaFuncSetAttribute(gemm_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmBig::SMEM_BYTES));
+    DQGP_CUDA(cudaFuncSetAttribute(gemm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmall::SMEM_BYTES));
     if (dev >= 0 && dev < 64) done[dev] = true;
     return 0;
 }
@@ -183,8 +196,17 @@ int launch_gemm_group(const GemmTask* d_tasks, int n_tasks, int total_tiles, cud
     if (n_tasks <= 0 || total_tiles <= 0) return 0;
     int rc = gemm_init();
     if (rc) return rc;
-    gemm_group_kernel<<<total_tiles, GM_THREADS, GM_SMEM_BYTES, st>>>(d_tasks, n_tasks);
+    gemm_group_kernel<<<total_tiles, GemmBig::THREADS, GemmBig::SMEM_BYTES, st>>>(d_tasks, n_tasks);
     DQGP_LAUNCH_CHECK("gemm_group_kernel");
+    return 0;
+}
+
+int launch_gemm_group_small(const GemmTask* d_tasks, int n_tasks, int total_tiles, cudaStream_t st) {
+    if (n_tasks <= 0 || total_tiles <= 0) return 0;
+    int rc = gemm_init();
+    if (rc) return rc;
+    gemm_small_kernel<<<total_tiles, GemmSmall::THREADS, GemmSmall::SMEM_BYTES, st>>>(d_tasks, n_tasks);
+    DQGP_LAUNCH_CHECK("gemm_small_kernel");
     return 0;
 }
 

@@ -11,7 +11,7 @@ from dqgp_b200.engine import Solver  # noqa: E402
 
 lib = d.load()
 for n in [int(a) for a in sys.argv[1:]] or [1024, 2048, 4096, 8192]:
-    for ob in (1, 4):
+    for ob in [int(o) for o in os.environ.get("OBS", "1,4").split(",")]:
         s = Solver(n, ob)
         g = torch.Generator(device="cuda").manual_seed(1)
         B = torch.randn((n, 64), dtype=torch.float64, device="cuda", generator=g)
