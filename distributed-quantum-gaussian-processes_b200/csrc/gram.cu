@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(PW_THREADS) gram_projected_kernel(const double
 // exactly outer(0).  d^2 below 4e-15*(|f|^2+|g|^2) snaps to 0 so exact duplicates give exactly outer(0) = 1, as
 // the direct-difference form (kept below as gram_projected_kernel for odd cases) and SciPy's cdist do.
 // v1 (direct differences, libm exp) ran at 22% of the HBM write roofline: 72 FP64 instructions per entry.
-template <int OUTER, bool SYM>
+template <int OUTER, int SYM>   // 0 rectangular, 1 lower tiles + mirror, 2 lower tiles only (what the factorisation reads)
 __global__ void __launch_bounds__(PW_THREADS) gram_projected_dmma_kernel(const double* __restrict__ F1, int n1,
                                                                          const double* __restrict__ F2, int n2, int m,
                                                                          OuterHyp hyp, double* __restrict__ K, int ldk) {
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(PW_THREADS) gram_projected_dmma_kernel(const d
                 if (vec_ok && cc + 1 < n2) *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
                 else { if (cc < n2) dst[0] = v[0]; if (cc + 1 < n2) dst[1] = v[1]; }
             }
-            if (SYM && bi != bj) {                                    // mirror: K[c][r]
+            if (SYM == 1 && bi != bj) {                               // mirror: K[c][r]
                 if (cc < n1 && r < n2) K[(size_t)cc * ldk + r] = v[0];
                 if (cc + 1 < n1 && r < n2) K[(size_t)(cc + 1) * ldk + r] = v[1];
             }
@@ -241,8 +241,9 @@ int dqgp_gram_projected(int outer, const double* h_hyp, const double* d_F1, int 
 #define DQGP_GRAM(OUT)                                                                                                     \
     do {                                                                                                                   \
         if (use_direct) gram_projected_kernel<OUT><<<grid, PW_THREADS, 0, st>>>(d_F1, n1, d_F2, n2, m, hyp, d_K, ldk);      \
-        else if (sym) gram_projected_dmma_kernel<OUT, true><<<tsym, PW_THREADS, 0, st>>>(d_F1, n1, d_F2, n2, m, hyp, d_K, ldk); \
-        else gram_projected_dmma_kernel<OUT, false><<<grid, PW_THREADS, 0, st>>>(d_F1, n1, d_F2, n2, m, hyp, d_K, ldk);     \
+        else if (sym && same == 2) gram_projected_dmma_kernel<OUT, 2><<<tsym, PW_THREADS, 0, st>>>(d_F1, n1, d_F2, n2, m, hyp, d_K, ldk); \
+        else if (sym) gram_projected_dmma_kernel<OUT, 1><<<tsym, PW_THREADS, 0, st>>>(d_F1, n1, d_F2, n2, m, hyp, d_K, ldk); \
+        else gram_projected_dmma_kernel<OUT, 0><<<grid, PW_THREADS, 0, st>>>(d_F1, n1, d_F2, n2, m, hyp, d_K, ldk);        \
     } while (0)
     switch (outer) {
         case DQGP_OUTER_GAUSSIAN: DQGP_GRAM(DQGP_OUTER_GAUSSIAN); break;

@@ -130,7 +130,7 @@ class AgentEngine:
         lib, st, s = self._lib, stream_ptr(), self.solver
         base = self.d_feat.data_ptr()          # set 0 = unshifted parameters
         if self.kernel_type == "projected":
-            check(lib.dqgp_gram_projected(self._outer_id, self._hyp, base, self.n, base, self.n, self.m, s.matrix_ptr, s.ld, 1, st),
+            check(lib.dqgp_gram_projected(self._outer_id, self._hyp, base, self.n, base, self.n, self.m, s.matrix_ptr, s.ld, 2, st),   # lower tiles only
                   "gram projected")
         else:
             check(lib.dqgp_gram_fidelity(base, self.n, base, self.n, 1 << self.q, s.matrix_ptr, s.ld, 1, st), "gram fidelity")

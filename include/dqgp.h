@@ -77,7 +77,9 @@ int dqgp_states_shifted(const dqgp_circuit* c, const double* d_X, int n, const d
  *      projected: K = outer(f1_j, f2_k); hyp = {gamma} | {length_scale} | {length_scale, periodicity}
  *      (ProjectedQuantumKernel.evaluate, main.py:130-137);  fidelity: K = |<psi2_k|psi1_j>|^2
  *      (FidelityKernel.evaluate, main.py:118-124). `same` != 0 promises the two operands are the same
- *      array so the diagonal is exactly outer(0) / the mirror is exact. */
+ *      array so the diagonal is exactly outer(0) / the mirror is exact; `same` == 2 (projected kernel) writes
+ *      only the 64x64 tiles that intersect the lower triangle - all dqgp_potrf_solve_inv reads - and leaves
+ *      the rest of d_K untouched. */
 int dqgp_gram_projected(int outer, const double* h_hyp, const double* d_F1, int n1, const double* d_F2, int n2, int m,
                         double* d_K, int ldk, int same, void* stream);
 int dqgp_gram_fidelity(const double* d_Psi1, int n1, const double* d_Psi2, int n2, int dim, double* d_K, int ldk,

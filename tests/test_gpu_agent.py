@@ -1,5 +1,6 @@
 """GPU parity, agent / trajectory level: the drop-in Python surface against golden vectors produced by the
 REAL reference code (tests/golden/make_golden.py) and against the oracle at larger sizes."""
+import ctypes as C
 import json
 import os
 
@@ -313,8 +314,15 @@ def test_full_size_properties_config4_shard(d):
                         rho=100.0, L=100.0)
     z = d.kernels.dev_f64(np.round(np.random.RandomState(42).rand(eng.P), 4))
     eng.simulate(z); eng.gram()
-    K = eng.solver.matrix().clone()
-    assert torch.equal(K, K.T)
+    K = eng.solver.matrix().clone()          # the training Gram fills the lower tiles only (all the factorisation reads)
+    K = torch.tril(K) + torch.tril(K, -1).T
+    f0 = eng.d_feat[0]
+    full = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    hyp = (C.c_double * 1)(1.0)
+    assert d.load().dqgp_gram_projected(0, hyp, f0.data_ptr(), n, f0.data_ptr(), n, 3 * q, full.data_ptr(), n, 1,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    assert torch.equal(full, full.T)         # mirrored mode: exactly symmetric
+    assert torch.equal(torch.tril(full, -1), torch.tril(K, -1))
     assert torch.all(torch.diagonal(K) == 1.0 + 0.1 ** 2)
     off = K - torch.diag(torch.diagonal(K))
     assert off.min() >= 0.0 and off.max() <= 1.0
