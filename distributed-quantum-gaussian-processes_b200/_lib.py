@@ -46,6 +46,8 @@ SIGNATURES = {
     "dqgp_gram_fidelity": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
     "dqgp_solver_create": (_i, [_i, C.POINTER(_vp)]),
     "dqgp_solver_create_ex": (_i, [_i, _i, C.POINTER(_vp)]),
+    "dqgp_solver_create_lean": (_i, [_i, _i, C.POINTER(_vp)]),
+    "dqgp_solver_is_lean": (_i, [_vp]),
     "dqgp_solver_destroy": (None, [_vp]),
     "dqgp_solver_n": (_i, [_vp]),
     "dqgp_solver_ld": (_i, [_vp]),
@@ -57,6 +59,7 @@ SIGNATURES = {
     "dqgp_add_diagonal": (_i, [_vp, _i, _i, _d, _vp]),
     "dqgp_potrf_solve_inv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "dqgp_solver_quadform_rows": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "dqgp_solver_quadform_rows_inplace": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "dqgp_solver_apply_factor": (_i, [_vp, _vp, _vp, _vp]),
     "dqgp_dgemm": (_i, [_i, _i, _i, _i, _i, _d, _vp, _i, _vp, _i, _d, _vp, _i, _vp]),
     "dqgp_shift_parameter_sets": (_i, [_vp, _i, _d, _d, _vp, _vp]),
@@ -66,6 +69,7 @@ SIGNATURES = {
     "dqgp_nll_terms": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "dqgp_admm_local": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp]),
     "dqgp_admm_consensus": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp]),
+    "dqgp_predict_mean": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "dqgp_predict_finish": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

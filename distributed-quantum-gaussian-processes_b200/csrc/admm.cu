@@ -87,9 +87,14 @@ __global__ void predict_finish_kernel(const double* __restrict__ Kst, int nt, in
     const int lane = threadIdx.x & 31;
     if (row >= nt) return;
     double acc = 0.0;
-    for (int k = lane; k < n; k += 32) acc = fma(Kst[(size_t)row * ldk + k], alpha[k], acc);
-    acc = warp_sum(acc);
+    if (Kst != nullptr) {
+        for (int k = lane; k < n; k += 32) acc = fma(Kst[(size_t)row * ldk + k], alpha[k], acc);
+        acc = warp_sum(acc);
+    } else {
+        acc = mean[row];                  // precomputed by dqgp_predict_mean
+    }
     if (lane == 0) {
+        if (kss == nullptr) { mean[row] = acc; return; }     // mean-only launch
         const double v = fmax(kss[row] - quad[row], 1e-10);
         mean[row] = acc;
         var[row] = v;
@@ -150,11 +155,19 @@ int dqgp_nll_terms(const double* d_logdet, const double* d_y, const double* d_al
     return 0;
 }
 
+int dqgp_predict_mean(const double* d_Kst, int nt, int n, int ldk, const double* d_alpha, double* d_mean, void* stream) {
+    using namespace dqgp;
+    DQGP_REQUIRE(d_Kst && d_alpha && d_mean && nt >= 1 && n >= 1 && ldk >= n, "dqgp_predict_mean: bad arguments");
+    predict_finish_kernel<<<(nt + 7) / 8, 256, 0, as_stream(stream)>>>(d_Kst, nt, n, ldk, d_alpha, nullptr, nullptr, nullptr, d_mean, nullptr, nullptr);
+    DQGP_LAUNCH_CHECK("predict_mean kernel");
+    return 0;
+}
+
 int dqgp_predict_finish(const double* d_Kst, int nt, int n, int ldk, const double* d_alpha, const double* d_kss_diag,
                         const double* d_quad, const double* d_ytest, double* d_mean, double* d_var, double* d_nlpd,
                         void* stream) {
     using namespace dqgp;
-    DQGP_REQUIRE(d_Kst && d_alpha && d_kss_diag && d_quad && d_mean && d_var && nt >= 1 && n >= 1 && ldk >= n, "dqgp_predict_finish: bad arguments");
+    DQGP_REQUIRE(d_alpha && d_kss_diag && d_quad && d_mean && d_var && nt >= 1 && n >= 1 && (d_Kst == nullptr || ldk >= n), "dqgp_predict_finish: bad arguments");
     DQGP_REQUIRE((d_nlpd == nullptr) == (d_ytest == nullptr), "dqgp_predict_finish: d_ytest and d_nlpd go together");
     cudaStream_t st = as_stream(stream);
     double* terms = d_nlpd ? d_nlpd + 1 : nullptr;   // d_nlpd: [mean NLPD, per-point terms ...] (1 + nt doubles)

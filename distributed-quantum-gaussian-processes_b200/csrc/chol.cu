@@ -19,7 +19,20 @@ constexpr int NB = 128;
 
 struct dqgp_solver {
     int n, np, ld, nblk, device;
-    double *A, *W, *T;            // factor (in place), L^-1, scratch / A^-1
+    // full mode: A factor (in place), W = L^-1, T scratch / A^-1 - three padded squares.
+    // lean mode (prediction at sizes where three squares do not fit): A only; W holds just the nblk inverted diagonal
+    // blocks (128 x 128 each, ldw = 128) and T two rotating outer-panel buffers (np x OB*128 each).
+    int lean, ldw, ldt;
+    double *A, *W, *T;
+    double* w_block(int k) const { return lean ? W + (size_t)k * 128 * 128 : W + (size_t)k * 128 * ld + (size_t)k * 128; }
+    double* t_block(int r, int k) const {   // block (r, k) of the panel storage
+        return lean ? T + (size_t)((k / ob) & 1) * np * ldt + (size_t)r * 128 * ldt + (size_t)(k % ob) * 128
+                    : T + (size_t)r * 128 * ld + (size_t)k * 128;
+    }
+    dqgp::GemmTask* d_dyn;        // per-call task table of the in-place substitution (dqgp_solver_quadform_rows_inplace)
+    int dyn_capacity;
+    double* tmp;                  // (rows x 128) product buffer of the substitution, grown on demand
+    size_t tmp_rows;
     double *y_pad, *w, *partial;  // padded rhs, W y, column partial sums
     double *strip, *V;            // prediction: padded 128-row strip of K(test,train), V = W strip^T
     dqgp::GemmTask* d_tasks;
@@ -121,8 +134,8 @@ __device__ __forceinline__ void leaf_join(double* __restrict__ M, const double* 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __restrict__ A, int ld, double* __restrict__ W,
-                                                                      int blk, double* logdet, int* info, int n_real) {
+__global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __restrict__ A, int ld, double* __restrict__ Wblk,
+                                                                      int ldw, int blk, double* logdet, int* info, int n_real) {
     extern __shared__ __align__(16) double leaf_smem[];
     double* M = leaf_smem;
     double* s_diag = M + NB * LP;
@@ -135,7 +148,6 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
     const int i = tid & (NB - 1);             // row owned in phase 1
     const bool helper = tid >= NB;
     double* Ablk = A + (size_t)blk * NB * ld + (size_t)blk * NB;
-    double* Wblk = W + (size_t)blk * NB * ld + (size_t)blk * NB;
     if (tid == 0) s_bad = 0;
     __syncthreads();
 
@@ -287,7 +299,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
         double2 v;
         v.x = (c < r) ? M[r * LP + c] : s_rdiag[r];
         v.y = (c + 1 < r) ? M[r * LP + c + 1] : (c + 1 == r ? s_rdiag[r] : 0.0);
-        *reinterpret_cast<double2*>(Wblk + (size_t)r * ld + c) = v;
+        *reinterpret_cast<double2*>(Wblk + (size_t)r * ldw + c) = v;
     }
 }
 
@@ -370,6 +382,80 @@ __global__ void copy_pad_rows_kernel(const double* __restrict__ B, int nb, int n
     for (int c = threadIdx.x; c < np; c += blockDim.x) out[(size_t)r * ldo + c] = (r < nb && c < n) ? B[(size_t)r * ldb + c] : 0.0;
 }
 
+
+// ---- lean mode: copy one solved block column of the panel storage back over its (dead) input, A(k+1.., k) <- T(k+1.., k)
+__global__ void copy_panel_column_kernel(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd, int rows) {
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)rows * (NB / 2); e += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = e / (NB / 2), c = e % (NB / 2);
+        d2[r * (ldd / 2) + c] = s2[r * (lds / 2) + c];
+    }
+}
+// ---- lean mode, vector solves with L (blocked substitution; the diagonal blocks are applied through their inverses)
+// out[0..127] = Wkk in  (trans = 0)  or  Wkk^T in  (trans = 1); in == out allowed
+__global__ void diag_block_mv_kernel(const double* __restrict__ Wk, int ldw, const double* in, double* out, int trans) {
+    __shared__ double x[NB];
+    const int i = threadIdx.x;
+    x[i] = in[i];
+    __syncthreads();
+    double acc = 0.0;
+    if (!trans) { for (int j = 0; j <= i; ++j) acc = fma(Wk[(size_t)i * ldw + j], x[j], acc); }
+    else        { for (int j = i; j < NB; ++j) acc = fma(Wk[(size_t)j * ldw + i], x[j], acc); }
+    out[i] = acc;
+}
+// y[r] -= sum_c L[r][k*128 + c] * wk[c]  for the rows below block k (one warp per row)
+__global__ void subst_forward_update_kernel(const double* __restrict__ L, int ld, int k, int np, const double* __restrict__ wk,
+                                            double* __restrict__ y) {
+    const int row = (k + 1) * NB + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= np) return;
+    const double* lr = L + (size_t)row * ld + (size_t)k * NB;
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < NB / 32; ++c) acc = fma(lr[lane + 32 * c], wk[lane + 32 * c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[row] -= acc;
+}
+// w[j] -= sum_r L[k*128 + r][j] * xk[r]  for the columns left of block k (one thread per column)
+__global__ void subst_backward_update_kernel(const double* __restrict__ L, int ld, int k, const double* __restrict__ xk, double* __restrict__ w) {
+    __shared__ double x[NB];
+    if (threadIdx.x < NB) x[threadIdx.x] = xk[threadIdx.x];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k * NB) return;
+    const double* lc = L + (size_t)k * NB * ld + j;
+    double acc = 0.0;
+    for (int r = 0; r < NB; ++r) acc = fma(lc[(size_t)r * ld], x[r], acc);
+    w[j] -= acc;
+}
+// in-place substitution on row-major right-hand sides: B[:, k-block] <- tmp, out[i] += sum_c tmp[i][c]^2 (fixed order)
+__global__ void subst_store_sumsq_kernel(const double* __restrict__ tmp, double* __restrict__ B, int ldb, int k, int rows,
+                                         double* __restrict__ out, int first) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const double2* t2 = reinterpret_cast<const double2*>(tmp + (size_t)row * NB);
+    double2* b2 = reinterpret_cast<double2*>(B + (size_t)row * ldb + (size_t)k * NB);
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < NB / 64; ++c) {
+        const double2 v = t2[lane + 32 * c];
+        b2[lane + 32 * c] = v;
+        acc = fma(v.x, v.x, acc); acc = fma(v.y, v.y, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = first ? acc : out[row] + acc;
+}
+
+static GemmTask make_task3(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K, int a_k, int b_k,
+                           int lower, int krule, double alpha, double beta) {
+    GemmTask t;
+    t.A = A; t.B = B; t.C = C; t.M = M; t.N = N; t.K = K; t.lda = lda; t.ldb = ldb; t.ldc = ldc;
+    t.a_k_contig = a_k; t.b_k_contig = b_k; t.lower_tiles = lower; t.krule = krule; t.alpha = alpha; t.beta = beta;
+    t.tile_begin = 0; t.tiles = gemm_task_tiles(t);
+    return t;
+}
 static GemmTask make_task(const double* A, const double* B, double* C, int M, int N, int K, int ld, int a_k, int b_k, int lower,
                           int krule, double alpha, double beta) {
     GemmTask t;
@@ -407,13 +493,15 @@ static int potrf_lookahead(dqgp_solver* s, double* d_logdet, int* d_info, cudaSt
     for (int k = 0; k < nblk; ++k) {
         const int p = k / OB, p0 = p * OB, pend = std::min(p0 + OB, nblk);
         stamp();
-        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, crit>>>(s->A, ld, s->W, k, d_logdet, d_info, s->n);
+        potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, crit>>>(s->A, ld, s->w_block(k), s->ldw, k, d_logdet, d_info, s->n);
         DQGP_LAUNCH_CHECK("potrf_leaf_kernel");
         stamp();
         if (k + 1 >= nblk) break;
         DQGP_CUDA(cudaEventRecord(s->ev_leaf[k], crit));
         // critical block row
         if (k > 0) DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_b[k - 1], 0));            // A(k+1,k) has all its updates
+        if (s->lean && p >= 2 && k == p0 && s->rest[p - 2].tiles > 0)                  // this panel's buffer was panel p-2's:
+            DQGP_CUDA(cudaStreamWaitEvent(crit, s->ev_rest[p - 2], 0));                // its bulk update must have read it
         int rc = run_small(s->trsmA[k], crit);
         if (rc) return rc;
         DQGP_CUDA(cudaEventRecord(s->ev_a[k], crit));
@@ -431,6 +519,11 @@ static int potrf_lookahead(dqgp_solver* s, double* d_logdet, int* d_info, cudaSt
         rc = run(s->updB[k], mid);
         if (rc) return rc;
         DQGP_CUDA(cudaEventRecord(s->ev_b[k], mid));
+        if (s->lean) {    // the panel buffers rotate: L's block column goes back over its own input now
+            const int rows = s->np - (k + 1) * NB;
+            copy_panel_column_kernel<<<std::min(rows, 2048), 256, 0, mid>>>(s->t_block(k + 1, k), s->ldt, s->A + (size_t)(k + 1) * NB * ld + (size_t)k * NB, ld, rows);
+            DQGP_LAUNCH_CHECK("copy_panel_column_kernel");
+        }
         if (k + 1 == pend && pend < nblk) {            // the panel's columns of L are complete
             if (last_rest >= 0) DQGP_CUDA(cudaStreamWaitEvent(mid, s->ev_rest[last_rest], 0));   // bulk updates hit these columns
             rc = run(s->next1[p], mid);
@@ -471,11 +564,18 @@ static int potrf_lookahead(dqgp_solver* s, double* d_logdet, int* d_info, cudaSt
     return 0;
 }
 
+static int solver_create_impl(int n, int outer_blocks, int lean, dqgp_solver** out);
+
 extern "C" {
 
 int dqgp_solver_create(int n, dqgp_solver** out) { return dqgp_solver_create_ex(n, 0, out); }
+int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) { return solver_create_impl(n, outer_blocks, 0, out); }
+int dqgp_solver_create_lean(int n, int outer_blocks, dqgp_solver** out) { return solver_create_impl(n, outer_blocks, 1, out); }
+int dqgp_solver_is_lean(const dqgp_solver* s) { return s ? s->lean : -1; }
 
-int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
+}  // extern "C"
+
+static int solver_create_impl(int n, int outer_blocks, int lean, dqgp_solver** out) {
     using namespace dqgp;
     DQGP_REQUIRE(out != nullptr, "dqgp_solver_create: out is NULL");
     *out = nullptr;
@@ -487,20 +587,29 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
     s->np = s->nblk * NB;
     s->ld = s->np;
     s->A = s->W = s->T = s->y_pad = s->w = s->partial = s->strip = s->V = nullptr;
-    s->d_tasks = nullptr;
+    s->d_tasks = nullptr; s->d_dyn = nullptr; s->dyn_capacity = 0; s->tmp = nullptr; s->tmp_rows = 0;
+    s->lean = lean ? 1 : 0;
+    s->ldw = lean ? NB : s->ld;
+    s->ldt = lean ? s->ob * NB : s->ld;
     s->helper = nullptr; s->mid = nullptr; s->ev_fork = nullptr; s->ev_join = nullptr; s->ev_join2 = nullptr;
     cudaError_t e = cudaGetDevice(&s->device);
     const size_t mat = sizeof(double) * (size_t)s->np * s->ld;
-    s->bytes = 3 * mat;
+    const size_t wbytes = lean ? sizeof(double) * (size_t)s->nblk * NB * NB : mat;
+    const size_t tbytes = lean ? sizeof(double) * 2 * (size_t)s->np * s->ldt : mat;
+    s->bytes = mat + wbytes + tbytes;
     if (e == cudaSuccess) e = cudaMalloc(&s->A, mat);
-    if (e == cudaSuccess) e = cudaMalloc(&s->W, mat);
-    if (e == cudaSuccess) e = cudaMemset(s->W, 0, mat);   // the leaves write only the lower triangle of W's diagonal blocks
-    if (e == cudaSuccess) e = cudaMalloc(&s->T, mat);
+    if (e == cudaSuccess) e = cudaMalloc(&s->W, wbytes);
+    if (e == cudaSuccess) e = cudaMemset(s->W, 0, wbytes);   // the leaves write only the lower triangle of W's diagonal blocks
+    if (e == cudaSuccess) e = cudaMalloc(&s->T, tbytes);
     if (e == cudaSuccess) e = cudaMalloc(&s->y_pad, sizeof(double) * s->np);
     if (e == cudaSuccess) e = cudaMalloc(&s->w, sizeof(double) * s->np);
-    if (e == cudaSuccess) e = cudaMalloc(&s->partial, sizeof(double) * (size_t)s->nblk * s->np);
-    if (e == cudaSuccess) e = cudaMalloc(&s->strip, sizeof(double) * (size_t)NB * s->ld);
-    if (e == cudaSuccess) e = cudaMalloc(&s->V, sizeof(double) * (size_t)s->np * NB);
+    if (!lean) {
+        if (e == cudaSuccess) e = cudaMalloc(&s->partial, sizeof(double) * (size_t)s->nblk * s->np);
+        if (e == cudaSuccess) e = cudaMalloc(&s->strip, sizeof(double) * (size_t)NB * s->ld);
+        if (e == cudaSuccess) e = cudaMalloc(&s->V, sizeof(double) * (size_t)s->np * NB);
+    } else if (e == cudaSuccess) {
+        e = cudaMalloc(&s->partial, sizeof(double) * s->np);     // apply_factor's output staging
+    }
     if (e != cudaSuccess) { dqgp_solver_destroy(s); return cuda_fail(e, "dqgp_solver_create (allocation; this library has no CPU fallback)"); }
 
     std::vector<GemmTask> tasks;
@@ -523,36 +632,40 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
     //   updB[k]   columns k+1 .. pend (INCLUDING the first column of the next panel) -= rank-128 terms of column k
     // Panel p, once its last column is solved (K = w*128):
     //   next1[p]  column pend+1;  next2[p]  columns pend+2 .. pend+OB;  rest[p]  columns > pend+OB (lower tiles)
+    const int ldw = s->ldw, ldt = s->ldt;
+    auto tW = [&](int k) { return s->w_block(k); };
+    auto tT = [&](int r, int k) { return s->t_block(r, k); };
     for (int k = 0; k + 1 < nblk; ++k) {
         const int p0 = (k / OB) * OB, pend = std::min(p0 + OB, nblk);
         // the two products on the leaf chain run on the small-tile kernel: 16 (10 for the symmetric update) CTAs of 32x32
-        grp.push_back(small(make_task(at(s->A, k + 1, k), at(s->W, k, k), at(s->T, k + 1, k), NB, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0)));
+        grp.push_back(small(make_task3(at(s->A, k + 1, k), ld, tW(k), ldw, tT(k + 1, k), ldt, NB, NB, NB, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0)));
         s->trsmA.push_back(push_group(grp));
-        grp.push_back(small(make_task(at(s->T, k + 1, k), at(s->T, k + 1, k), at(s->A, k + 1, k + 1), NB, NB, NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0)));
+        grp.push_back(small(make_task3(tT(k + 1, k), ldt, tT(k + 1, k), ldt, at(s->A, k + 1, k + 1), ld, NB, NB, NB, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0)));
         s->updA.push_back(push_group(grp));
         const int below = np - (k + 2) * NB;
         if (below > 0)
-            grp.push_back(make_task(at(s->A, k + 2, k), at(s->W, k, k), at(s->T, k + 2, k), below, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
+            grp.push_back(make_task3(at(s->A, k + 2, k), ld, tW(k), ldw, tT(k + 2, k), ldt, below, NB, NB, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0));
         s->trsmB.push_back(push_group(grp));
         if (below > 0)     // column k+1 below its diagonal block
-            grp.push_back(make_task(at(s->T, k + 2, k), at(s->T, k + 1, k), at(s->A, k + 2, k + 1), below, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+            grp.push_back(make_task3(tT(k + 2, k), ldt, tT(k + 1, k), ldt, at(s->A, k + 2, k + 1), ld, below, NB, NB, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
         for (int c = k + 2; c <= std::min(pend, nblk - 1); ++c)
-            grp.push_back(make_task(at(s->T, c, k), at(s->T, c, k), at(s->A, c, c), np - c * NB, NB, NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+            grp.push_back(make_task3(tT(c, k), ldt, tT(c, k), ldt, at(s->A, c, c), ld, np - c * NB, NB, NB, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
         s->updB.push_back(push_group(grp));
     }
     for (int p0 = 0; p0 < nblk; p0 += OB) {
         const int w = std::min(OB, nblk - p0), pend = p0 + w;
         const int c1 = pend + 1, c2 = pend + 2, c2e = std::min(pend + OB, nblk - 1), c3 = pend + OB + 1;
         if (c1 < nblk)
-            grp.push_back(make_task(at(s->T, c1, p0), at(s->T, c1, p0), at(s->A, c1, c1), np - c1 * NB, NB, w * NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+            grp.push_back(make_task3(tT(c1, p0), ldt, tT(c1, p0), ldt, at(s->A, c1, c1), ld, np - c1 * NB, NB, w * NB, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
         s->next1.push_back(push_group(grp));
         if (c2 <= c2e)
-            grp.push_back(make_task(at(s->T, c2, p0), at(s->T, c2, p0), at(s->A, c2, c2), np - c2 * NB, (c2e - c2 + 1) * NB, w * NB, ld, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
+            grp.push_back(make_task3(tT(c2, p0), ldt, tT(c2, p0), ldt, at(s->A, c2, c2), ld, np - c2 * NB, (c2e - c2 + 1) * NB, w * NB, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
         s->next2.push_back(push_group(grp));
         if (c3 < nblk)
-            grp.push_back(make_task(at(s->T, c3, p0), at(s->T, c3, p0), at(s->A, c3, c3), np - c3 * NB, np - c3 * NB, w * NB, ld, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
+            grp.push_back(make_task3(tT(c3, p0), ldt, tT(c3, p0), ldt, at(s->A, c3, c3), ld, np - c3 * NB, np - c3 * NB, w * NB, 1, 1, 1, GM_KRULE_ALL, -1.0, 1.0));
         s->rest.push_back(push_group(grp));
     }
+    if (!s->lean) {
     // trtri levels: spans of `span` blocks are already inverted; join neighbours pairwise
     for (int span = 1; span < nblk; span *= 2) {
         std::vector<GemmTask> gt, gw;
@@ -576,6 +689,7 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
         grp.push_back(t);
         s->quad = push_group(grp);
     }
+    }   // !lean
 
     e = cudaMalloc(&s->d_tasks, sizeof(GemmTask) * tasks.size());
     if (e == cudaSuccess) e = cudaMemcpy(s->d_tasks, tasks.data(), sizeof(GemmTask) * tasks.size(), cudaMemcpyHostToDevice);
@@ -613,6 +727,8 @@ int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out) {
     return 0;
 }
 
+extern "C" {
+
 void dqgp_solver_destroy(dqgp_solver* s) {
     if (!s) return;
     for (auto* v : {&s->ev_leaf, &s->ev_a, &s->ev_b, &s->ev_n1, &s->ev_n2, &s->ev_rest})
@@ -622,13 +738,13 @@ void dqgp_solver_destroy(dqgp_solver* s) {
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->helper) cudaStreamDestroy(s->helper);
-    cudaFree(s->A); cudaFree(s->W); cudaFree(s->T); cudaFree(s->y_pad); cudaFree(s->w); cudaFree(s->partial); cudaFree(s->strip); cudaFree(s->V); cudaFree(s->d_tasks);
+    cudaFree(s->A); cudaFree(s->W); cudaFree(s->T); cudaFree(s->y_pad); cudaFree(s->w); cudaFree(s->partial); cudaFree(s->strip); cudaFree(s->V); cudaFree(s->d_tasks); cudaFree(s->d_dyn); cudaFree(s->tmp);
     delete s;
 }
 int dqgp_solver_n(const dqgp_solver* s) { return s ? s->n : -1; }
 int dqgp_solver_ld(const dqgp_solver* s) { return s ? s->ld : -1; }
 double* dqgp_solver_matrix(dqgp_solver* s) { return s ? s->A : nullptr; }
-double* dqgp_solver_inverse(dqgp_solver* s) { return s ? s->T : nullptr; }
+double* dqgp_solver_inverse(dqgp_solver* s) { return (s && !s->lean) ? s->T : nullptr; }
 double* dqgp_solver_factor(dqgp_solver* s) { return s ? s->A : nullptr; }
 size_t dqgp_solver_bytes(const dqgp_solver* s) { return s ? s->bytes : 0; }
 int dqgp_solver_potrf_launches(const dqgp_solver* s) { return s ? s->potrf_launches : -1; }
@@ -646,6 +762,24 @@ int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, dou
     {
         int rc = potrf_lookahead(s, d_logdet, d_info, st);
         if (rc) return rc;
+    }
+    if (s->lean) {
+        // L is already in place.  alpha = L^-T (L^-1 y) by blocked substitution through the inverted diagonal blocks.
+        DQGP_REQUIRE(want_inverse <= 0, "dqgp_potrf_solve_inv: a lean solver holds no triangular inverse / A^-1 (want_inverse must be <= 0)");
+        if (factor_only) return 0;
+        double* y = s->y_pad;
+        for (int k = 0; k < nblk; ++k) {
+            diag_block_mv_kernel<<<1, NB, 0, st>>>(s->w_block(k), s->ldw, y + (size_t)k * NB, y + (size_t)k * NB, 0);
+            const int rows = np - (k + 1) * NB;
+            if (rows > 0) subst_forward_update_kernel<<<(rows + 7) / 8, 256, 0, st>>>(s->A, ld, k, np, y + (size_t)k * NB, y);
+        }
+        for (int k = nblk - 1; k >= 0; --k) {
+            diag_block_mv_kernel<<<1, NB, 0, st>>>(s->w_block(k), s->ldw, y + (size_t)k * NB, y + (size_t)k * NB, 1);
+            if (k > 0) subst_backward_update_kernel<<<(k * NB + 255) / 256, 256, 0, st>>>(s->A, ld, k, y + (size_t)k * NB, y);
+        }
+        DQGP_LAUNCH_CHECK("substitution kernels");
+        DQGP_CUDA(cudaMemcpyAsync(d_alpha, y, sizeof(double) * s->n, cudaMemcpyDeviceToDevice, st));
+        return 0;
     }
     if (nblk > 1) {
         copy_lower_blocks_kernel<<<dim3(nblk - 1, nblk - 1), 256, 0, st>>>(s->T, s->A, ld);
@@ -686,11 +820,58 @@ int dqgp_solver_apply_factor(dqgp_solver* s, const double* d_x, double* d_y, voi
     return 0;
 }
 
+int dqgp_solver_quadform_rows_inplace(dqgp_solver* s, double* d_B, int nb_pad, int ldb, double* d_out, void* stream) {
+    // Row i of B (nb_pad, ldb) is replaced by (L^-1 b_i)^T and d_out[i] = || L^-1 b_i ||^2 (main.py:1462-1463), by blocked
+    // forward substitution on the DMMA GEMM: for every 128-column block k
+    //     B[:, k] -= B[:, 0..k) L[k, 0..k)^T        (contraction over everything already solved)
+    //     B[:, k]  = B[:, k] Wkk^T                  (inverted diagonal block)
+    // Needs only L and the diagonal-block inverses, so it works on a lean solver: the right-hand sides are the only
+    // other large buffer (n^2 nb flops in place, no second square).
+    using namespace dqgp;
+    DQGP_REQUIRE(s && d_B && d_out && nb_pad > 0 && nb_pad % NB == 0 && ldb >= s->np && (ldb & 1) == 0,
+                 "dqgp_solver_quadform_rows_inplace: B must have a multiple of 128 rows and an even leading dimension >= %d "
+                 "(columns n..n_pad zero)", s ? s->np : 0);
+    DQGP_REQUIRE((reinterpret_cast<uintptr_t>(d_B) & 15) == 0, "dqgp_solver_quadform_rows_inplace: B must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const int nblk = s->nblk, ld = s->ld;
+    if ((size_t)nb_pad > s->tmp_rows) {
+        DQGP_CUDA(cudaStreamSynchronize(st));
+        cudaFree(s->tmp); s->tmp = nullptr; s->tmp_rows = 0;
+        DQGP_CUDA(cudaMalloc(&s->tmp, sizeof(double) * (size_t)nb_pad * NB));
+        s->tmp_rows = nb_pad;
+    }
+    if (2 * nblk > s->dyn_capacity) {
+        DQGP_CUDA(cudaStreamSynchronize(st));
+        cudaFree(s->d_dyn); s->d_dyn = nullptr; s->dyn_capacity = 0;
+        DQGP_CUDA(cudaMalloc(&s->d_dyn, sizeof(GemmTask) * 2 * nblk));
+        s->dyn_capacity = 2 * nblk;
+    }
+    std::vector<GemmTask> dyn(2 * nblk);
+    for (int k = 0; k < nblk; ++k) {
+        // [2k]   B[:, k] -= B[:, 0..k) L[k, 0..k)^T ;  [2k+1] tmp = B[:, k] Wkk^T
+        dyn[2 * k] = make_task3(d_B, ldb, s->A + (size_t)k * NB * ld, ld, d_B + (size_t)k * NB, ldb, nb_pad, NB, std::max(k, 1) * NB, 1, 1, 0,
+                                GM_KRULE_ALL, -1.0, 1.0);
+        dyn[2 * k + 1] = make_task3(d_B + (size_t)k * NB, ldb, s->w_block(k), s->ldw, s->tmp, NB, nb_pad, NB, NB, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0);
+    }
+    DQGP_CUDA(cudaMemcpyAsync(s->d_dyn, dyn.data(), sizeof(GemmTask) * dyn.size(), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < nblk; ++k) {
+        int rc = 0;
+        if (k > 0) rc = launch_gemm_group(s->d_dyn + 2 * k, 1, dyn[2 * k].tiles, st);
+        if (rc) return rc;
+        rc = launch_gemm_group(s->d_dyn + 2 * k + 1, 1, dyn[2 * k + 1].tiles, st);
+        if (rc) return rc;
+        subst_store_sumsq_kernel<<<(nb_pad + 7) / 8, 256, 0, st>>>(s->tmp, d_B, ldb, k, nb_pad, d_out, k == 0);
+        DQGP_LAUNCH_CHECK("subst_store_sumsq_kernel");
+    }
+    return 0;
+}
+
 int dqgp_solver_quadform_rows(dqgp_solver* s, const double* d_B, int nb, int ldb, double* d_out, void* stream) {
     // d_out[i] = || L^-1 b_i ||^2 for every row b_i of B (nb, n): V = W B^T in strips of 128 rows of B on the
     // DMMA GEMM, then fixed-order column sums of squares (main.py:1462-1463).
     using namespace dqgp;
     DQGP_REQUIRE(s && d_B && d_out && nb >= 0 && ldb >= s->n, "dqgp_solver_quadform_rows: bad arguments");
+    DQGP_REQUIRE(!s->lean, "dqgp_solver_quadform_rows: a lean solver has no L^-1; use dqgp_solver_quadform_rows_inplace");
     cudaStream_t st = as_stream(stream);
     for (int r0 = 0; r0 < nb; r0 += NB) {
         const int cnt = std::min(NB, nb - r0);

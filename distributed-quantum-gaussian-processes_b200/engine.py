@@ -37,14 +37,18 @@ class _DeviceMatrix:
 class Solver:
     """``dqgp_solver`` handle: padded fp64 workspace + task tables for Cholesky / inverse / solve."""
 
-    def __init__(self, n, outer_blocks=0):
+    def __init__(self, n, outer_blocks=0, lean=False):
+        """``lean``: one padded square instead of three (factor in place, inverted diagonal blocks, rotating panel
+        buffers): no triangular inverse / A^-1, for prediction at sizes where three squares do not fit in HBM."""
         self._lib = _lib.load()
         h = C.c_void_p()
-        check(self._lib.dqgp_solver_create_ex(int(n), int(outer_blocks), C.byref(h)), "dqgp_solver_create")
-        self.handle, self.n = h, int(n)
+        create = self._lib.dqgp_solver_create_lean if lean else self._lib.dqgp_solver_create_ex
+        check(create(int(n), int(outer_blocks), C.byref(h)), "dqgp_solver_create")
+        self.handle, self.n, self.lean = h, int(n), bool(lean)
         self.ld = self._lib.dqgp_solver_ld(h)
         self.matrix_ptr = self._lib.dqgp_solver_matrix(h)
         self.inverse_ptr = self._lib.dqgp_solver_inverse(h)
+        self.bytes = int(self._lib.dqgp_solver_bytes(h))
 
     def _view(self, ptr):
         return torch.as_tensor(_DeviceMatrix(ptr, (self.n, self.n), (self.ld * 8, 8)), device="cuda")

@@ -19,10 +19,14 @@ from .kernels import create_quantum_kernel, dev_f64, stream_ptr
 def predict_quantum_gp(X_train, Y_train, X_test, quantum_kernel_params, num_qubits, num_layers, noise_std,
                        use_parameter_shift=True, encoding_type="yz_cx", kernel_type="fidelity", measurement="XYZ",
                        outer_kernel="gaussian", outer_kernel_params=None, regularization=None, return_kernels=False,
-                       Y_test=None):
+                       Y_test=None, lean=None):
     """-> (mean, var, K_tt, K_st, K_ss); the three matrices are None unless ``return_kernels`` (they are only
     used for plots in the reference).  With ``Y_test`` the mean NLPD is computed on the device and attached as
-    ``predict_quantum_gp.last_nlpd``."""
+    ``predict_quantum_gp.last_nlpd``.
+
+    ``lean`` (None = decide from free HBM): factor K(train,train) in place with ONE padded square, alpha by blocked
+    substitution and the predictive variance by in-place forward substitution on K(test,train) - the path for
+    training sets whose three-square workspace does not fit (config 5: 117964 samples = 112 GB per square)."""
     lib = _lib.load()
     X_train = np.asarray(X_train, dtype=np.float64)
     X_test = np.asarray(X_test, dtype=np.float64)
@@ -39,9 +43,16 @@ def predict_quantum_gp(X_train, Y_train, X_test, quantum_kernel_params, num_qubi
     d_p = dev_f64(np.asarray(quantum_kernel_params, dtype=np.float64).reshape(1, -1))
     d_y = dev_f64(np.asarray(Y_train, dtype=np.float64).reshape(-1))
     st = stream_ptr()
-    solver = Solver(n)
+    if lean is None:
+        npad = -(-n // 128) * 128
+        free, _ = torch.cuda.mem_get_info()
+        lean = 3 * 8 * npad * npad + 8 * nt * n > 0.9 * free
+    if lean and return_kernels:
+        raise ValueError("return_kernels is not available on the lean path (K(test,train) is overwritten in place)")
+    solver = Solver(n, lean=bool(lean))
     k_tt = solver.matrix()
-    qk.evaluate_device(d_xtr, d_xtr, d_p, same=True, out=k_tt, ld=solver.ld)
+    # same=2: only the lower tiles are written (all the factorisation reads) unless the caller wants K back
+    qk.evaluate_device(d_xtr, d_xtr, d_p, same=True if return_kernels else 2, out=k_tt, ld=solver.ld)
     k_tt_host = k_tt.cpu().numpy() if return_kernels else None
     # K + sigma^2 I, then + 1e-6 I as two separate additions (main.py:1434-1438)
     check(lib.dqgp_add_diagonal(solver.matrix_ptr, n, solver.ld, float(noise_std) ** 2, st), "add diagonal")
@@ -51,15 +62,29 @@ def predict_quantum_gp(X_train, Y_train, X_test, quantum_kernel_params, num_qubi
     info = torch.zeros(1, dtype=torch.int32, device=d_xtr.device)
     check(lib.dqgp_potrf_solve_inv(solver.handle, d_y.data_ptr(), alpha.data_ptr(), logdet.data_ptr(), info.data_ptr(), 0, st),
           "potrf")
-    k_st = qk.evaluate_device(d_xte, d_xtr, d_p, same=False)
-    quad = torch.empty(nt, **f64)
-    check(lib.dqgp_solver_quadform_rows(solver.handle, k_st.data_ptr(), nt, n, quad.data_ptr(), st), "quadform")
+    mean, var = torch.empty(nt, **f64), torch.empty(nt, **f64)
+    if lean:
+        # K(test,train) in a padded buffer (rows to a multiple of 128, leading dimension = the solver's), mean first,
+        # then the rows are overwritten by (L^-1 k_i)^T
+        ntp, ldk = -(-nt // 128) * 128, solver.ld
+        k_st = torch.empty((ntp, ldk), **f64)
+        k_st[nt:].zero_()
+        k_st[:, n:].zero_()
+        qk.evaluate_device(d_xte, d_xtr, d_p, same=False, out=k_st, ld=ldk)
+        check(lib.dqgp_predict_mean(k_st.data_ptr(), nt, n, ldk, alpha.data_ptr(), mean.data_ptr(), st), "predict mean")
+        quad = torch.empty(ntp, **f64)
+        check(lib.dqgp_solver_quadform_rows_inplace(solver.handle, k_st.data_ptr(), ntp, ldk, quad.data_ptr(), st), "quadform")
+        kst_ptr, ldk_arg = None, 0
+    else:
+        k_st = qk.evaluate_device(d_xte, d_xtr, d_p, same=False)
+        quad = torch.empty(nt, **f64)
+        check(lib.dqgp_solver_quadform_rows(solver.handle, k_st.data_ptr(), nt, n, quad.data_ptr(), st), "quadform")
+        kst_ptr, ldk_arg = k_st.data_ptr(), n
     # diag K(test,test): each test point against itself (1 x 1 Grams batched as a diagonal extraction)
     kss_diag = _self_kernel_diag(qk, d_xte, d_p)
-    mean, var = torch.empty(nt, **f64), torch.empty(nt, **f64)
     nlpd_buf = torch.empty(1 + nt, **f64) if Y_test is not None else None
     d_yt = dev_f64(np.asarray(Y_test, dtype=np.float64).reshape(-1)) if Y_test is not None else None
-    check(lib.dqgp_predict_finish(k_st.data_ptr(), nt, n, n, alpha.data_ptr(), kss_diag.data_ptr(), quad.data_ptr(),
+    check(lib.dqgp_predict_finish(kst_ptr, nt, n, ldk_arg, alpha.data_ptr(), kss_diag.data_ptr(), quad.data_ptr(),
                                   d_yt.data_ptr() if d_yt is not None else None, mean.data_ptr(), var.data_ptr(),
                                   nlpd_buf.data_ptr() if nlpd_buf is not None else None, st), "predict finish")
     if int(info.item()) != 0:

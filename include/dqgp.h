@@ -94,6 +94,12 @@ int dqgp_solver_create(int n, dqgp_solver** out);
 /* outer_blocks: width of the outer Cholesky panel in 128-column blocks. 4 (default, = 0) gives rank-512 trailing
  * updates (best throughput when several agents share a GPU); 1 is the shortest critical path (one agent per GPU). */
 int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out);
+/* Lean solver for prediction / CV at full-train scale (main.py:1364-1596): ONE padded square (A, factored
+ * in place) + the inverted 128x128 diagonal blocks + two rotating panel buffers, instead of three squares.  Supports
+ * dqgp_potrf_solve_inv with want_inverse <= 0 (alpha by blocked substitution), dqgp_solver_apply_factor and
+ * dqgp_solver_quadform_rows_inplace; no triangular inverse, no A^-1.  n = 117964 (config 5's training set) needs 112 GB. */
+int dqgp_solver_create_lean(int n, int outer_blocks, dqgp_solver** out);
+int dqgp_solver_is_lean(const dqgp_solver* s);
 void dqgp_solver_destroy(dqgp_solver* s);
 int dqgp_solver_n(const dqgp_solver* s);
 int dqgp_solver_ld(const dqgp_solver* s);
@@ -114,6 +120,11 @@ int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, dou
 int dqgp_solver_apply_factor(dqgp_solver* s, const double* d_x, double* d_y, void* stream);
 /* v = L^-1 B^T for B (nb, n): returns column sums of v^2 -> d_out[nb] (main.py:1462-1463) */
 int dqgp_solver_quadform_rows(dqgp_solver* s, const double* d_B, int nb, int ldb, double* d_out, void* stream);
+
+/* Same quantity by in-place blocked forward substitution (works on lean solvers): d_B (nb_pad, ldb) with nb_pad a multiple
+ * of 128, ldb >= n_pad = dqgp_solver_ld() and even, 16-byte aligned, columns n..n_pad zero; rows are OVERWRITTEN by
+ * (L^-1 b_i)^T, d_out[nb_pad] receives the squared norms. */
+int dqgp_solver_quadform_rows_inplace(dqgp_solver* s, double* d_B, int nb_pad, int ldb, double* d_out, void* stream);
 
 /* fp64 GEMM building block on the DMMA tensor path (used by the factorisation; exposed for tests):
  * C(MxN) = alpha*A*B + beta*C; A is [m][k] if a_k_contig else [k][m]; B is [n][k] if b_k_contig else [k][n].
@@ -151,6 +162,9 @@ int dqgp_admm_consensus(const double* d_theta, const double* d_psi, int A, int P
 
 /* ---- GP prediction pieces (main.py:1458-1466, 1546-1552): mean = Kst alpha; var = max(diag - q, 1e-10);
  *      d_nlpd[0] = mean_i(0.5 log 2pi + 0.5 log var_i + 0.5 (y_i-mean_i)^2/var_i). */
+/* mean only: d_mean[i] = sum_k Kst[i][k] alpha[k] (use before dqgp_solver_quadform_rows_inplace overwrites Kst; then call
+ * dqgp_predict_finish with d_Kst = NULL, which keeps d_mean as given). */
+int dqgp_predict_mean(const double* d_Kst, int nt, int n, int ldk, const double* d_alpha, double* d_mean, void* stream);
 int dqgp_predict_finish(const double* d_Kst, int nt, int n, int ldk, const double* d_alpha, const double* d_kss_diag,
                         const double* d_quad, const double* d_ytest, double* d_mean, double* d_var, double* d_nlpd,
                         void* stream);

@@ -169,6 +169,22 @@ def test_predict_matches_reference(d, case):
     assert abs(d.nlpd(g["Y_test"], mean, var) - d.predict_quantum_gp.last_nlpd) < 1e-10
 
 
+@pytest.mark.parametrize("case", ["cheb_proj_matern_q3", "hub_fid_q5", "yzcx_proj_gauss_q4"])
+def test_lean_predict_matches_reference(d, case):
+    """The lean prediction path (one square, substitution solves, in-place K(test,train)) against the reference's
+    predict_quantum_gp outputs, and against the three-square path."""
+    g = load_golden(f"agent_step_{case}.npz")
+    args = (g["X"], g["Y"], g["X_test"], np.mod(g["z"], np.pi), int(g["q"]), int(g["layers"]), 0.1, True, str(g["encoding"]),
+            str(g["kernel_type"]), "XYZ", str(g["outer_kernel"]))
+    mean, var, *_ = d.predict_quantum_gp(*args, Y_test=g["Y_test"], lean=True)
+    nl = d.predict_quantum_gp.last_nlpd
+    assert np.max(np.abs(mean - g["pred_mean"])) < 1e-8 * max(1.0, np.abs(g["pred_mean"]).max())
+    assert np.max(np.abs(var - g["pred_var"])) < 1e-8
+    mean2, var2, *_ = d.predict_quantum_gp(*args, Y_test=g["Y_test"], lean=False)
+    assert np.max(np.abs(mean - mean2)) < 1e-10 and np.max(np.abs(var - var2)) < 1e-10
+    assert abs(nl - d.predict_quantum_gp.last_nlpd) < 1e-9
+
+
 def test_generate_quantum_gp_data_matches_reference_main(d):
     """the dataset main.main() generated for configs[0] (seed 42, data seed 7), regenerated on the GPU
     with the same host RNG stream, split like main.py:2356: X identical, Y equal to the Cholesky-sampling accuracy."""

@@ -247,3 +247,60 @@ def test_shift_parameter_sets_bit_exact(d):
     dz = d.kernels.dev_f64(z)
     assert d.load().dqgp_shift_parameter_sets(dz.data_ptr(), 17, np.pi / 8, np.pi, out.data_ptr(), _sp()) == 0
     assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("n,ob", [(100, 4), (640, 1), (1500, 2), (2100, 4)])
+def test_lean_solver_matches_full_solver(d, n, ob):
+    """Lean solver (one square, rotating panel buffers, substitution solves) == full solver: same factor bit for bit,
+    alpha / logdet to rounding, and the in-place quadratic form == the L^-1-based one."""
+    from dqgp_b200.engine import Solver
+    lib = d.load()
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, 40))
+    A = B @ B.T / 40 + np.eye(n)
+    y = rng.standard_normal(n)
+    rhs = rng.standard_normal((70, n))
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = {}
+    for lean in (False, True):
+        s = Solver(n, ob, lean=lean)
+        assert lib.dqgp_solver_is_lean(s.handle) == int(lean)
+        s.matrix().copy_(torch.from_numpy(A).cuda())
+        alpha = torch.empty(n, dtype=torch.float64, device="cuda")
+        logdet = torch.zeros(1, dtype=torch.float64, device="cuda")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        assert lib.dqgp_potrf_solve_inv(s.handle, torch.from_numpy(y).cuda().data_ptr(), alpha.data_ptr(), logdet.data_ptr(),
+                                        info.data_ptr(), 0, st) == 0
+        torch.cuda.synchronize()
+        assert info.item() == 0
+        L = np.tril(s.matrix().cpu().numpy())
+        nbp, ld = 128, s.ld
+        Bp = torch.zeros((nbp, ld), dtype=torch.float64, device="cuda")
+        Bp[:70, :n] = torch.from_numpy(rhs).cuda()
+        q = torch.empty(nbp, dtype=torch.float64, device="cuda")
+        assert lib.dqgp_solver_quadform_rows_inplace(s.handle, Bp.data_ptr(), nbp, ld, q.data_ptr(), st) == 0
+        torch.cuda.synchronize()
+        out[lean] = (L, alpha.cpu().numpy(), logdet.item(), q.cpu().numpy()[:70], Bp.cpu().numpy()[:70, :n])
+        if not lean:
+            q2 = torch.empty(70, dtype=torch.float64, device="cuda")
+            assert lib.dqgp_solver_quadform_rows(s.handle, torch.from_numpy(rhs).cuda().data_ptr(), 70, n, q2.data_ptr(), st) == 0
+            assert np.max(np.abs(q2.cpu().numpy() - out[lean][3]) / out[lean][3]) < 1e-11
+        else:
+            # a lean solver refuses what it cannot do
+            assert lib.dqgp_potrf_solve_inv(s.handle, torch.from_numpy(y).cuda().data_ptr(), alpha.data_ptr(), logdet.data_ptr(),
+                                            info.data_ptr(), 1, st) < 0
+            assert lib.dqgp_solver_inverse(s.handle) is None
+    Lf, af, ldf, qf, vf = out[False]
+    Ll, al, ldl, ql, vl = out[True]
+    assert np.array_equal(Lf, Ll)
+    assert ldf == ldl
+    Lref = np.linalg.cholesky(A)
+    assert np.max(np.abs(Ll - Lref)) < 1e-11
+    aref = np.linalg.solve(A, y)
+    assert np.max(np.abs(al - aref)) / np.max(np.abs(aref)) < 1e-11
+    assert np.max(np.abs(af - al)) / np.max(np.abs(aref)) < 1e-12
+    import scipy.linalg as sl
+    vref = sl.solve_triangular(Lref, rhs.T, lower=True).T
+    assert np.max(np.abs(vl - vref)) < 1e-10
+    assert np.max(np.abs(ql - (vref ** 2).sum(axis=1)) / ql) < 1e-11
+    assert np.array_equal(vf, vl)
