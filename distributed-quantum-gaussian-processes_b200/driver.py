@@ -48,7 +48,8 @@ def run_admm(shards, *, encoding_type, kernel_type, num_qubits, num_layers, nois
         if cv_data is not None:
             cv = k_fold_cross_validation_consensus(cv_data[0], cv_data[1], z, num_qubits, num_layers, noise_std, k_folds=cv_folds,
                                                    encoding_type=encoding_type, kernel_type=kernel_type, outer_kernel=outer_kernel,
-                                                   random_seed=seed + it)
+                                                   random_seed=seed + it, process_group=process_group, rank=rank,
+                                                   world_size=world_size)     # folds dealt to the ranks, scores gathered
             rec["cv"] = cv
             if cv["mean_nlpd"] < cv_best:
                 cv_best, z_best_cv, patience = cv["mean_nlpd"], z.copy(), 0

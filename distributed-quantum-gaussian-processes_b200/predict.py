@@ -108,6 +108,18 @@ def _self_kernel_diag(qk, d_x, d_p):
     return nrm * nrm
 
 
+def gather_fold_scores(scores, process_group, rank, world_size):
+    """All-gather the (k_folds, 3) score table: row f is taken from its owner, rank f % world_size."""
+    import torch.distributed as dist
+    backend = dist.get_backend(process_group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.from_numpy(np.ascontiguousarray(scores)).to(dev)
+    allr = torch.empty((world_size,) + tuple(mine.shape), dtype=mine.dtype, device=dev)
+    dist.all_gather_into_tensor(allr.view(-1), mine.view(-1), group=process_group)
+    allr = allr.cpu().numpy()
+    return np.stack([allr[f % world_size, f] for f in range(scores.shape[0])])
+
+
 def nlpd(Y_true, y_pred_mean, y_pred_var):
     """Mean negative log predictive density, main.py:1546-1552 (host formula for host arrays)."""
     var = np.maximum(np.asarray(y_pred_var, dtype=np.float64), 1e-10)
@@ -118,26 +130,34 @@ def nlpd(Y_true, y_pred_mean, y_pred_var):
 def k_fold_cross_validation_consensus(X_train, Y_train, consensus_params, num_qubits, num_layers, noise_std, k_folds=5,
                                       use_parameter_shift=True, encoding_type="yz_cx", kernel_type="fidelity",
                                       measurement="XYZ", outer_kernel="gaussian", outer_kernel_params=None,
-                                      regularization=None, random_seed=42):
-    """Same result dict as main.py:1490-1596 (mean/std NLPD, R^2, RMSE over valid folds)."""
+                                      regularization=None, random_seed=42, process_group=None, rank=0, world_size=1,
+                                      _predict=None):
+    """Same result dict as main.py:1490-1596 (mean/std NLPD, R^2, RMSE over valid folds).
+
+    With ``world_size`` > 1 (one process per GPU) the folds - independent factorisations - are dealt round-robin to the
+    ranks (fold f on rank f % world_size) and the three per-fold scores are all-gathered, so every rank returns the
+    same dict as a single process would; no training data crosses NVLink."""
     from sklearn.metrics import mean_squared_error, r2_score
     from sklearn.model_selection import KFold
 
     X_train = np.asarray(X_train, dtype=np.float64)
     Y_train = np.asarray(Y_train, dtype=np.float64)
-    fold_nlpds, fold_r2s, fold_rmses = [], [], []
-    for tr, va in KFold(n_splits=k_folds, shuffle=True, random_state=random_seed).split(X_train):
+    predict = _predict or predict_quantum_gp
+    scores = np.full((k_folds, 3), np.nan)
+    for f, (tr, va) in enumerate(KFold(n_splits=k_folds, shuffle=True, random_state=random_seed).split(X_train)):
+        if f % world_size != rank:
+            continue
         try:
-            mean, var, _, _, _ = predict_quantum_gp(X_train[tr], Y_train[tr], X_train[va], consensus_params, num_qubits,
-                                                    num_layers, noise_std, use_parameter_shift, encoding_type, kernel_type,
-                                                    measurement, outer_kernel, outer_kernel_params, regularization)
-            fold_nlpds.append(nlpd(Y_train[va], mean, var))
-            fold_r2s.append(r2_score(Y_train[va], mean))
-            fold_rmses.append(float(np.sqrt(mean_squared_error(Y_train[va], mean))))
+            mean, var, _, _, _ = predict(X_train[tr], Y_train[tr], X_train[va], consensus_params, num_qubits,
+                                         num_layers, noise_std, use_parameter_shift, encoding_type, kernel_type,
+                                         measurement, outer_kernel, outer_kernel_params, regularization)
+            scores[f] = (nlpd(Y_train[va], mean, var), r2_score(Y_train[va], mean),
+                         float(np.sqrt(mean_squared_error(Y_train[va], mean))))
         except Exception:
-            fold_nlpds.append(float("inf"))
-            fold_r2s.append(-float("inf"))
-            fold_rmses.append(float("inf"))
+            scores[f] = (float("inf"), -float("inf"), float("inf"))
+    if world_size > 1:
+        scores = gather_fold_scores(scores, process_group, rank, world_size)
+    fold_nlpds, fold_r2s, fold_rmses = [list(map(float, scores[:, c])) for c in range(3)]
     valid = [v for v in fold_nlpds if not np.isinf(v)]
     if len(valid) >= k_folds // 2:
         ok = [not np.isinf(v) for v in fold_nlpds]

@@ -78,3 +78,35 @@ def test_agent_block_partition():
     assert list(d.agent_block(7, 8, 16)) == [14, 15]
     with pytest.raises(ValueError):
         d.agent_block(0, 3, 8)
+
+
+def _fake_predict(Xtr, Ytr, Xva, *args, **kw):
+    """Stand-in for the GPU prediction (this test is about fold ownership and the gather): ridge fit on the host."""
+    w = np.linalg.solve(Xtr.T @ Xtr + 1e-3 * np.eye(Xtr.shape[1]), Xtr.T @ Ytr)
+    mean = Xva @ w
+    return mean, np.full(len(Xva), 0.05 + 0.001 * len(Xtr) / 100.0), None, None, None
+
+
+def _cv_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dqgp_b200 import predict
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((203, 3)); Y = X @ np.array([0.5, -1.0, 2.0]) + 0.1 * rng.standard_normal(203)
+    out[rank] = predict.k_fold_cross_validation_consensus(X, Y, None, 3, 1, 0.1, k_folds=5, rank=rank, world_size=world,
+                                                          _predict=_fake_predict)
+    dist.destroy_process_group()
+
+
+def test_cv_folds_sharded_over_two_ranks_equal_single_process():
+    from dqgp_b200 import predict
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_cv_worker, args=(2, port, out), nprocs=2, join=True)
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((203, 3)); Y = X @ np.array([0.5, -1.0, 2.0]) + 0.1 * rng.standard_normal(203)
+    ref = predict.k_fold_cross_validation_consensus(X, Y, None, 3, 1, 0.1, k_folds=5, _predict=_fake_predict)
+    assert ref["valid_folds"] == 5
+    for r in range(2):
+        assert out[r] == ref
