@@ -20,8 +20,9 @@ from .kernels import create_quantum_kernel, dev_f64, stream_ptr
 def generate_quantum_gp_data(num_samples, input_dim, num_qubits, num_layers=2, data_range=(-2.0, 2.0), noise_std=0.1,
                              use_parameter_shift=True, kernel_params=None, encoding_type="yz_cx", kernel_type="fidelity",
                              measurement="XYZ", outer_kernel="gaussian", outer_kernel_params=None, regularization=None,
-                             data_seed=None, param_seed=42):
-    """-> (X, Y, ground_truth_params)."""
+                             data_seed=None, param_seed=42, lean=None):
+    """-> (X, Y, ground_truth_params).  ``lean`` (None = decide from free HBM): factor the N x N Gram in place in one padded
+    square (N = 131072 is 137 GB) instead of the three-square workspace."""
     if input_dim < 1 or input_dim > 6:
         raise ValueError(f"Input dimension must be between 1 and 6, got {input_dim}")
     lib = _lib.load()
@@ -47,10 +48,14 @@ def generate_quantum_gp_data(num_samples, input_dim, num_qubits, num_layers=2, d
     n = num_samples
     d_x = dev_f64(X)
     d_p = dev_f64(np.asarray(qk.parameters, dtype=np.float64).reshape(1, -1))
-    solver = Solver(n)
+    if lean is None:                                                   # three padded squares do not fit: factor in place
+        npad = -(-n // 128) * 128
+        lean = 3 * 8 * npad * npad > 0.9 * torch.cuda.mem_get_info()[0]
+    solver = Solver(n, lean=bool(lean))
     st = stream_ptr()
-    qk.evaluate_device(d_x, d_x, d_p, same=True, out=solver.matrix(), ld=solver.ld)
-    if bool(torch.isnan(solver.matrix()).any()):
+    qk.evaluate_device(d_x, d_x, d_p, same=2, out=solver.matrix(), ld=solver.ld)     # lower tiles: all the factorisation reads
+    # a NaN feature (arccos outside [-1, 1]) makes the whole row and column of that sample NaN, diagonal included
+    if bool(torch.isnan(torch.diagonal(solver.matrix())).any()):
         raise ValueError("Kernel matrix contains NaN or infinite values")   # main.py:248-249 (arccos outside [-1, 1])
     check(lib.dqgp_add_diagonal(solver.matrix_ptr, n, solver.ld, 1e-6, st), "add diagonal")
     logdet = torch.zeros(1, dtype=torch.float64, device=d_x.device)

@@ -185,13 +185,15 @@ def test_lean_predict_matches_reference(d, case):
     assert abs(nl - d.predict_quantum_gp.last_nlpd) < 1e-9
 
 
-def test_generate_quantum_gp_data_matches_reference_main(d):
+@pytest.mark.parametrize("lean", [False, True])
+def test_generate_quantum_gp_data_matches_reference_main(d, lean):
     """the dataset main.main() generated for configs[0] (seed 42, data seed 7), regenerated on the GPU
-    with the same host RNG stream, split like main.py:2356: X identical, Y equal to the Cholesky-sampling accuracy."""
+    with the same host RNG stream, split like main.py:2356: X identical, Y equal to the Cholesky-sampling accuracy;
+    with the three-square workspace and with the in-place (lean) factorisation used at N >= 65536."""
     from sklearn.model_selection import train_test_split
     data = load_golden("trajectory_cfg1_data.npz")
     X, Y, truth = d.generate_quantum_gp_data(1000, 2, 3, 1, (-2.0, 2.0), 0.1, True, None, "chebyshev", "projected", "XYZ", "matern",
-                                             {"length_scale": 1.0, "nu": 1.5}, None, data_seed=7, param_seed=42)
+                                             {"length_scale": 1.0, "nu": 1.5}, None, data_seed=7, param_seed=42, lean=lean)
     Xtr, Xte, Ytr, Yte = train_test_split(X, Y, test_size=0.1, random_state=42, shuffle=True)
     assert np.array_equal(Xtr, data["X_train"])
     assert np.max(np.abs(Ytr - data["Y_train"])) < 1e-6 * max(1.0, np.abs(data["Y_train"]).max())
