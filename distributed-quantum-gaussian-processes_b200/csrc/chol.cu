@@ -140,9 +140,8 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
     double* M = leaf_smem;
     double* s_diag = M + NB * LP;
     double* s_rdiag = s_diag + NB;
-    double* s_part = s_rdiag + NB;            // [8][128] partial sums of the helper threads
+    double* s_part = s_rdiag + NB;            // [8][128] the current panel after its left-looking update
     __shared__ double s_red[LEAF_THREADS / 32];
-    __shared__ double s_blk[64];
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = tid & (NB - 1);             // row owned in phase 1
@@ -151,60 +150,77 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
     if (tid == 0) s_bad = 0;
     __syncthreads();
 
-    // ---------------- phase 1: Cholesky ----------------
-    double a[8];
+    // ---------------- phase 1: Cholesky, left-looking in panels of 8 columns ----------------
+    // (a) all 8 warps: the panel's rows >= j0 minus the contribution of every earlier column, on DMMA: 8x8 tiles
+    //     P = A[rows, j0..j0+8) - L[rows, 0..j0) L[j0..j0+8, 0..j0)^T, four interleaved accumulators per tile so the
+    //     dependent DMMA chain is j0/16 long; the A entries are prefetched one panel ahead.  Result -> s_pan[c][row].
+    // (b) the 128 row threads: every thread factors the 8x8 diagonal block redundantly in registers (no cross-lane
+    //     chain), substitutes its own row, and stores L to M (transposed) and to HBM.
+    const int g = lane >> 2, t = lane & 3;
+    double* s_pan = s_part;                    // [8][128]
+    double2 av[2];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) a[c] = 0.0;
-    if (!helper) {
-        const double2* src = reinterpret_cast<const double2*>(Ablk + (size_t)i * ld);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { const double2 v = src[c]; a[2 * c] = v.x; a[2 * c + 1] = v.y; }
+    for (int x = 0; x < 2; ++x) {
+        const int ti = warp + 8 * x;
+        av[x] = *reinterpret_cast<const double2*>(Ablk + (size_t)(8 * ti + g) * ld + 2 * t);
     }
+#ifdef DQGP_LEAF_TIMING
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tw = 0, t_prev = clock64(), t_begin = t_prev;
+#define LEAF_TICK(slot) do { const long long now__ = clock64(); tk[slot] += now__ - t_prev; t_prev = now__; } while (0)
+#else
+#define LEAF_TICK(slot) do { } while (0)
+#endif
     for (int j0 = 0; j0 < NB; j0 += 8) {
-        double nxt[8];
+        const int tb = j0 >> 3;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) nxt[c] = 0.0;
-        if (!helper && j0 + 8 < NB && i >= j0 + 8) {   // prefetch the next panel's entries of this row
-            const double2* src = reinterpret_cast<const double2*>(Ablk + (size_t)i * ld + j0 + 8);
+        for (int x = 0; x < 2; ++x) {
+            const int ti = tb + warp + 8 * x;
+            if (ti < NB / 8) {                 // warp-uniform
+                const int i0 = 8 * ti;
+                double acc[4][2];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { const double2 v = src[c]; nxt[2 * c] = v.x; nxt[2 * c + 1] = v.y; }
-        }
-        if (i >= j0) {
-            const int kh = (j0 >> 1) & ~3;
-            const int kb = helper ? kh : 0, ke = helper ? j0 : kh;
-#pragma unroll 4
-            for (int k = kb; k < ke; ++k) {
-                const double lik = M[k * LP + i];
-                const double2* row = reinterpret_cast<const double2*>(&M[k * LP + j0]);
-                const double2 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
-                a[0] = fma(-lik, v0.x, a[0]); a[1] = fma(-lik, v0.y, a[1]);
-                a[2] = fma(-lik, v1.x, a[2]); a[3] = fma(-lik, v1.y, a[3]);
-                a[4] = fma(-lik, v2.x, a[4]); a[5] = fma(-lik, v2.y, a[5]);
-                a[6] = fma(-lik, v3.x, a[6]); a[7] = fma(-lik, v3.y, a[7]);
+                for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
+                const double* ma = M + t * LP + i0 + g;      // L[i0+g][k0+t] = M[(k0+t)*LP + i0+g]
+                const double* mb = M + t * LP + j0 + g;      // L[j0+g][k0+t]
+                for (int k0 = 0; k0 < j0; k0 += 16) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int kk = k0 + 4 * u;
+                        if (kk < j0) dmma884(acc[u][0], acc[u][1], ma[kk * LP], mb[kk * LP]);
+                    }
+                }
+                const double s0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+                const double s1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+#ifdef DQGP_LEAF_TIMING
+                if (s0 == 1.2345e300) tk[7] += 1;
+                LEAF_TICK(7);
+                if (av[x].x == 1.2345e300) tk[7] += 1;
+                { const long long now__ = clock64(); tw += now__ - t_prev; t_prev = now__; }
+#endif
+                s_pan[(2 * t) * NB + i0 + g] = av[x].x - s0;
+                s_pan[(2 * t + 1) * NB + i0 + g] = av[x].y - s1;
             }
-            if (helper) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) s_part[c * NB + i] = a[c];
-            }
+            const int tn = tb + 1 + warp + 8 * x;          // this slot's tile in the next panel
+            if (j0 + 8 < NB && tn < NB / 8)
+                av[x] = *reinterpret_cast<const double2*>(Ablk + (size_t)(8 * tn + g) * ld + j0 + 8 + 2 * t);
         }
+        LEAF_TICK(0);
         __syncthreads();
+        LEAF_TICK(1);
         if (!helper && i >= j0) {
+            double a[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) a[c] += s_part[c * NB + i];
-            if (i < j0 + 8) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) s_blk[(i - j0) * 8 + c] = a[c];
-            }
-        }
-        __syncthreads();
-        if (!helper && i >= j0) {
-            // every primary thread factors the 8x8 diagonal block redundantly in registers, then substitutes its row
+            for (int c = 0; c < 8; ++c) a[c] = s_pan[c * NB + i];
             double l[8][8];
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int c = 0; c <= r; ++c) l[r][c] = s_blk[r * 8 + c];
+                for (int c = 0; c <= r; ++c) l[r][c] = s_pan[c * NB + j0 + r];
             double rd[8];
+#ifdef DQGP_LEAF_TIMING
+            if (l[7][7] == 1.2345e300) tk[7] += 1;     // force the loads to complete here
+            LEAF_TICK(2);
+#endif
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const double piv = l[c][c];
@@ -218,6 +234,10 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
 #pragma unroll
                     for (int r = c2; r < 8; ++r) l[r][c2] = fma(-l[r][c], l[c2][c], l[r][c2]);
             }
+#ifdef DQGP_LEAF_TIMING
+            if (l[7][7] == 1.2345e300) tk[7] += 1;
+            LEAF_TICK(3);
+#endif
             if (i < j0 + 8) {
                 const int r0 = i - j0;
 #pragma unroll
@@ -238,6 +258,10 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
                     for (int c2 = c + 1; c2 < 8; ++c2) a[c2] = fma(-x, l[c2][c], a[c2]);
                 }
             }
+#ifdef DQGP_LEAF_TIMING
+            if (a[7] == 1.2345e300) tk[7] += 1;
+            LEAF_TICK(4);
+#endif
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 if (i > j0 + c) M[(j0 + c) * LP + i] = a[c];
@@ -246,10 +270,13 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
             for (int c = 0; c < 4; ++c)
                 dst[c] = make_double2((i >= j0 + 2 * c) ? a[2 * c] : 0.0, (i >= j0 + 2 * c + 1) ? a[2 * c + 1] : 0.0);
         }
+        LEAF_TICK(5);
         __syncthreads();
-#pragma unroll
-        for (int c = 0; c < 8; ++c) a[c] = nxt[c];     // helpers restart from zero
+        LEAF_TICK(6);
     }
+#ifdef DQGP_LEAF_TIMING
+    const long long t_phase1 = clock64();
+#endif
     {
         double v = (tid < NB) ? log(s_diag[tid]) : 0.0;
         v = warp_sum(v);
@@ -292,6 +319,9 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
     leaf_join<16>(M, s_rdiag, warp, lane);
     leaf_join<32>(M, s_rdiag, warp, lane);
     leaf_join<64>(M, s_rdiag, warp, lane);
+#ifdef DQGP_LEAF_TIMING
+    const long long t_phase2 = clock64();
+#endif
     // lower triangle only: the strict upper triangle of W's diagonal blocks is zeroed once, at solver creation
     for (int e = tid; e < NB * NB / 2; e += LEAF_THREADS) {
         const int r = e >> 6, c = (e & 63) * 2;
@@ -301,6 +331,12 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
         v.y = (c + 1 < r) ? M[r * LP + c + 1] : (c + 1 == r ? s_rdiag[r] : 0.0);
         *reinterpret_cast<double2*>(Wblk + (size_t)r * ldw + c) = v;
     }
+#ifdef DQGP_LEAF_TIMING
+    if (tid == NB - 1 && blk == 1)
+        printf("leaf cycles (thread 127): dmma update %lld | sync wait %lld | loads %lld | 8x8 factor %lld | substitution %lld | stores %lld | "
+               "end sync %lld | (a: dmma loops %lld, wait for prefetched A %lld) || phase1 %lld  logdet+phase2 %lld  W store %lld\n", tk[0], tk[1], tk[2], tk[3], tk[4], tk[5], tk[6], tk[7], tw,
+               t_phase1 - t_begin, t_phase2 - t_phase1, clock64() - t_phase2);
+#endif
 }
 
 // ---- padding: rows/cols >= n become the identity ---------------------------------------------------------
