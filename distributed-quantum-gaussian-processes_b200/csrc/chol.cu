@@ -69,8 +69,46 @@ namespace dqgp {
 // of the leaf's 155K cycles; measured with clock64: v3 spent 32K cycles in the phase-1 k-loops, 50K in the per-panel
 // serial part).
 constexpr int LEAF_THREADS = 256;
-constexpr int LP = 130;
+constexpr int LP = 132;     // pitch = 4 mod 16 doubles: the DMMA fragment patterns (t*LP + g and g*LP + t) are bank-conflict-free
 constexpr size_t LEAF_SMEM_V2 = sizeof(double) * (NB * LP + 2 * NB + 8 * NB);
+
+// Left-looking update of one 8-column panel for NT (1 or 2) 8-row tiles of one warp, on DMMA:
+//   s_pan[c][row] = A[row][j0+c] - sum_{k<j0} L[row][k] L[j0+c][k],  with L[i][k] = M[k*LP + i].
+// Four interleaved accumulators per tile keep the dependent DMMA chain j0/16 long; the B fragment is shared by the tiles.
+template <int NT>
+__device__ __forceinline__ void leaf_panel_update(const double* __restrict__ M, double* __restrict__ s_pan, int j0, int r0, int r1, int g,
+                                                  int t, const double2 (&av)[2]) {
+    double acc[NT][4][2];
+#pragma unroll
+    for (int x = 0; x < NT; ++x)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[x][u][0] = acc[x][u][1] = 0.0;
+    const double* mb = M + t * LP + j0 + g;
+    const double* ma[2] = {M + t * LP + r0 + g, M + t * LP + r1 + g};
+    const int full = j0 & ~15;                  // j0 is a multiple of 8: full rounds of 16 columns, then one half round
+    for (int k0 = 0; k0 < full; k0 += 16) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double b = mb[(k0 + 4 * u) * LP];
+#pragma unroll
+            for (int x = 0; x < NT; ++x) dmma884(acc[x][u][0], acc[x][u][1], ma[x][(k0 + 4 * u) * LP], b);
+        }
+    }
+    if (j0 & 8) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const double b = mb[(full + 4 * u) * LP];
+#pragma unroll
+            for (int x = 0; x < NT; ++x) dmma884(acc[x][u][0], acc[x][u][1], ma[x][(full + 4 * u) * LP], b);
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < NT; ++x) {
+        const int r = (x == 0 ? r0 : r1) + g;
+        s_pan[(2 * t) * NB + r] = av[x].x - ((acc[x][0][0] + acc[x][1][0]) + (acc[x][2][0] + acc[x][3][0]));
+        s_pan[(2 * t + 1) * NB + r] = av[x].y - ((acc[x][0][1] + acc[x][1][1]) + (acc[x][2][1] + acc[x][3][1]));
+    }
+}
 
 // One level of the triangular inverse inside the leaf: every pair of inverted BxB diagonal blocks (W11, W22) of the
 // 128x128 factor is joined into a 2Bx2B inverse, W21 = -W22 (L21 W11), as 8x8 DMMA tiles.  M holds L transposed in its
@@ -165,45 +203,29 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
         av[x] = *reinterpret_cast<const double2*>(Ablk + (size_t)(8 * ti + g) * ld + 2 * t);
     }
 #ifdef DQGP_LEAF_TIMING
-    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tw = 0, t_prev = clock64(), t_begin = t_prev;
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ta[16], tw = 0, t_prev = clock64(), t_begin = t_prev;
 #define LEAF_TICK(slot) do { const long long now__ = clock64(); tk[slot] += now__ - t_prev; t_prev = now__; } while (0)
 #else
 #define LEAF_TICK(slot) do { } while (0)
 #endif
     for (int j0 = 0; j0 < NB; j0 += 8) {
         const int tb = j0 >> 3;
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-            const int ti = tb + warp + 8 * x;
-            if (ti < NB / 8) {                 // warp-uniform
-                const int i0 = 8 * ti;
-                double acc[4][2];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
-                const double* ma = M + t * LP + i0 + g;      // L[i0+g][k0+t] = M[(k0+t)*LP + i0+g]
-                const double* mb = M + t * LP + j0 + g;      // L[j0+g][k0+t]
-                for (int k0 = 0; k0 < j0; k0 += 16) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int kk = k0 + 4 * u;
-                        if (kk < j0) dmma884(acc[u][0], acc[u][1], ma[kk * LP], mb[kk * LP]);
-                    }
-                }
-                const double s0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
-                const double s1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
-#ifdef DQGP_LEAF_TIMING
-                if (s0 == 1.2345e300) tk[7] += 1;
-                LEAF_TICK(7);
-                if (av[x].x == 1.2345e300) tk[7] += 1;
-                { const long long now__ = clock64(); tw += now__ - t_prev; t_prev = now__; }
-#endif
-                s_pan[(2 * t) * NB + i0 + g] = av[x].x - s0;
-                s_pan[(2 * t + 1) * NB + i0 + g] = av[x].y - s1;
+        {
+            // this warp's row tiles: tb + warp and tb + warp + 8; the B fragment (rows j0..j0+7 of L) is shared by both
+            const int ti0 = tb + warp, ti1 = ti0 + 8;
+            const bool has0 = ti0 < NB / 8, has1 = ti1 < NB / 8;     // warp-uniform
+            // no predicated mma.sync inside the loops: a predicate makes the compiler fence every DMMA with WARPSYNC
+            // (measured: 180 cycles per DMMA instead of 16), so the one- and two-tile cases are separate instantiations
+            if (has1) leaf_panel_update<2>(M, s_pan, j0, 8 * ti0, 8 * ti1, g, t, av);
+            else if (has0) leaf_panel_update<1>(M, s_pan, j0, 8 * ti0, 8 * ti0, g, t, av);
+            if (j0 + 8 < NB) {                                      // prefetch this warp's tiles of the next panel
+                if (ti0 + 1 < NB / 8) av[0] = *reinterpret_cast<const double2*>(Ablk + (size_t)(8 * (ti0 + 1) + g) * ld + j0 + 8 + 2 * t);
+                if (ti1 + 1 < NB / 8) av[1] = *reinterpret_cast<const double2*>(Ablk + (size_t)(8 * (ti1 + 1) + g) * ld + j0 + 8 + 2 * t);
             }
-            const int tn = tb + 1 + warp + 8 * x;          // this slot's tile in the next panel
-            if (j0 + 8 < NB && tn < NB / 8)
-                av[x] = *reinterpret_cast<const double2*>(Ablk + (size_t)(8 * tn + g) * ld + j0 + 8 + 2 * t);
         }
+#ifdef DQGP_LEAF_TIMING
+        { const long long now__ = clock64(); ta[tb] = now__ - t_prev; }
+#endif
         LEAF_TICK(0);
         __syncthreads();
         LEAF_TICK(1);
@@ -332,6 +354,9 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
         *reinterpret_cast<double2*>(Wblk + (size_t)r * ldw + c) = v;
     }
 #ifdef DQGP_LEAF_TIMING
+    if (tid == NB - 1 && blk == 1)
+        printf("panel update cycles per panel: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", ta[0], ta[1], ta[2],
+               ta[3], ta[4], ta[5], ta[6], ta[7], ta[8], ta[9], ta[10], ta[11], ta[12], ta[13], ta[14], ta[15]);
     if (tid == NB - 1 && blk == 1)
         printf("leaf cycles (thread 127): dmma update %lld | sync wait %lld | loads %lld | 8x8 factor %lld | substitution %lld | stores %lld | "
                "end sync %lld | (a: dmma loops %lld, wait for prefetched A %lld) || phase1 %lld  logdet+phase2 %lld  W store %lld\n", tk[0], tk[1], tk[2], tk[3], tk[4], tk[5], tk[6], tk[7], tw,
