@@ -142,7 +142,7 @@ def run_ours(args, w):
         torch.cuda.synchronize()
 
     step_fn = eng.iteration
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    use_graph = args.graph in ("on", "auto")
     if use_graph:
         try:
             eng.capture()                        # replay the whole iteration (all agent / look-ahead streams) as one CUDA graph

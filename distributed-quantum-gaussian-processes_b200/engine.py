@@ -251,7 +251,8 @@ class AdmmEngine:
         check(self._lib.dqgp_admm_consensus(self.theta.data_ptr(), self.psi.data_ptr(), self.A_total, self.P, self.rho, PERIOD,
                                             self.z.data_ptr(), stream_ptr()), "consensus")
 
-    def iteration(self):
+    def _local_part(self):
+        """Consensus z (replicated, from the gathered theta/psi) and every local agent's step: device work only."""
         self.consensus()
         if self.streams is None:
             for i, ag in enumerate(self.agents):
@@ -268,25 +269,30 @@ class AdmmEngine:
                 done = torch.cuda.Event()
                 done.record(s)
                 main.wait_event(done)
+
+    def _exchange(self):
         exchange_rows(self.theta, self.local_theta, self.pg, self.world)
         exchange_rows(self.psi, self.local_psi, self.pg, self.world)
 
+    def iteration(self):
+        self._local_part()
+        self._exchange()
+
     def capture(self):
-        """Capture one iteration (all local agents, their streams and the solver's internal look-ahead streams) into a
-        CUDA graph; `replay()` then costs one launch.  Worth it when the iteration is launch-bound (small shards:
-        hundreds of short kernels per agent); single-rank only (the NCCL exchange stays outside the graph)."""
-        if self.world != 1:
-            raise DqgpError("graph capture is implemented for the single-rank engine only")
+        """Capture the device part of one iteration (consensus, all local agents, their streams and the solver's internal
+        look-ahead streams) into a CUDA graph; `replay()` then costs one launch plus the row exchange, which stays
+        outside the graph (an in-place copy on one rank, the NCCL all-gather on several)."""
         self.iteration()                         # warm-up: lazy uploads and function attributes must be set before capture
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.iteration()
+            self._local_part()
         self._graph = graph
         return graph
 
     def replay(self):
         self._graph.replay()
+        self._exchange()
 
     def state(self):
         """(z, theta, psi, per-agent NLL) on the host (synchronises)."""
