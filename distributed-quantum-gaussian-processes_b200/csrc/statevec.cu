@@ -14,6 +14,7 @@
 // angles are computed once, cooperatively, into a per-state table; arccos(x) once per sample.  Only
 // __syncwarp separates passes.  The epilogue reduces <X_k>,<Y_k>,<Z_k> three qubits at a time from registers
 // with group-local shuffles, or streams the state to HBM for the fidelity kernel.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace dqgp {
@@ -199,6 +200,72 @@ __device__ __forceinline__ void features_block(const double2* __restrict__ amp, 
             double t = 0.0;
             for (int w = 0; w < nw; ++w) t += red[(w * 3 + which) * 3 + l];
             if (live) dst[which * Q + k0 + l] = (which == 2) ? t : 2.0 * t;
+        }
+        __syncthreads();
+    }
+}
+
+// Re<psi|O|phi> for O = X_k, Y_k, Z_k, k = k0 .. k0+B-1, of two states held side by side (same layout as features_block;
+// psi = phi gives <X>, <Y>, <Z>).  Used by the linear-combination form of the central-difference sets (statevec_lc_kernel).
+template <int B, int Q>
+__device__ __forceinline__ void features_cross_block(const double2* __restrict__ amp1, const double2* __restrict__ amp2, int k0, int lig,
+                                                     int lps, double* __restrict__ dst, double* __restrict__ red = nullptr) {
+    constexpr int N = 1 << B;
+    const int groups = (1 << Q) >> B;
+    double fx[B], fy[B], fz[B];
+#pragma unroll
+    for (int l = 0; l < B; ++l) fx[l] = fy[l] = fz[l] = 0.0;
+    for (int gi = lig; gi < groups; gi += lps) {
+        int base = gi;
+#pragma unroll
+        for (int l = 0; l < B; ++l) base = insert_zero_bit(base, k0 + l);
+        double2 r[N], s[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            int o = 0;
+#pragma unroll
+            for (int l = 0; l < B; ++l) o += ((j >> l) & 1) << (k0 + l);
+            r[j] = amp1[sv_phys(base + o)];
+            s[j] = amp2[sv_phys(base + o)];
+        }
+#pragma unroll
+        for (int l = 0; l < B; ++l)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                if (j & (1 << l)) continue;
+                const double2 a = r[j], b = r[j | (1 << l)], a2 = s[j], b2 = s[j | (1 << l)];
+                fx[l] += (a.x * b2.x + a.y * b2.y) + (b.x * a2.x + b.y * a2.y);
+                fy[l] += (a.x * b2.y - a.y * b2.x) - (b.x * a2.y - b.y * a2.x);
+                fz[l] += (a.x * a2.x + a.y * a2.y) - (b.x * b2.x + b.y * b2.y);
+            }
+    }
+    if (lps <= 32) {
+#pragma unroll
+        for (int l = 0; l < B; ++l) {
+            for (int o = lps >> 1; o > 0; o >>= 1) {
+                fx[l] += __shfl_xor_sync(0xffffffffu, fx[l], o);
+                fy[l] += __shfl_xor_sync(0xffffffffu, fy[l], o);
+                fz[l] += __shfl_xor_sync(0xffffffffu, fz[l], o);
+            }
+            if (lig == 0) {
+                dst[k0 + l] = fx[l];
+                dst[Q + k0 + l] = fy[l];
+                dst[2 * Q + k0 + l] = fz[l];
+            }
+        }
+    } else {
+        const int warp = lig >> 5, nw = lps >> 5;
+#pragma unroll
+        for (int l = 0; l < B; ++l) {
+            fx[l] = warp_sum(fx[l]); fy[l] = warp_sum(fy[l]); fz[l] = warp_sum(fz[l]);
+            if ((lig & 31) == 0) { red[(warp * 3 + 0) * 3 + l] = fx[l]; red[(warp * 3 + 1) * 3 + l] = fy[l]; red[(warp * 3 + 2) * 3 + l] = fz[l]; }
+        }
+        __syncthreads();
+        if (lig < 3 * B) {
+            const int which = lig / B, l = lig - which * B;
+            double t = 0.0;
+            for (int w = 0; w < nw; ++w) t += red[(w * 3 + which) * 3 + l];
+            dst[which * Q + k0 + l] = t;
         }
         __syncthreads();
     }
@@ -619,6 +686,186 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_shared_kernel(
     }
 }
 
+// ---- central-difference sets by LINEAR COMBINATION --------------------------------------------------------------------
+// For a parameter that enters through ONE rotation R(theta) = exp(-i theta sigma / 2) (RX / RY / RZ: every parameter of yz_cx and
+// kyriienko, the non-CRZ ones of chebyshev and hubregtsen), R(theta + D) = cos(D/2) R(theta) + sin(D/2) R(theta + pi), and the rest
+// of the circuit is linear, so BOTH shifted states of that parameter are combinations of the base state psi and one extra state
+// phi (the circuit with that gate's angle advanced by pi):   psi(D) = cos(D/2) psi + sin(D/2) phi,
+//     <O>(D) = cos^2(D/2) <psi|O|psi> + sin^2(D/2) <phi|O|phi> + sin(D) Re<psi|O|phi>.
+// One fork per parameter instead of two: P suffix simulations instead of 2P (D+ and D- are whatever the wrapped parameter sets of
+// dqgp_shift_parameter_sets give for this sample: they need not be symmetric).  CRZ parameters keep the two-fork path.  Results
+// equal the per-set simulation to rounding (1e-15), not bit for bit.
+template <int Q, bool WANT_STATES>
+__global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc_kernel(
+    const dqgp_gate* __restrict__ gates, int n_gates, const SvPass* __restrict__ passes, int n_passes, const SvOp* __restrict__ ops,
+    const SvMat* __restrict__ mats, int n_mats, const int* __restrict__ mat_gates, int n_mat_gates, const int* __restrict__ share,
+    int d, int P, int uses_acos, const double* __restrict__ X, int n, const double* __restrict__ Pm, double* __restrict__ out) {
+    using T = SvTeam<Q>;
+    constexpr int M3 = 3 * Q, M3P = (M3 + 1) & ~1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t gate_bytes = (sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15);
+    const size_t pass_bytes = (sizeof(SvPass) * n_passes + 15) & ~size_t(15);
+    const size_t op_bytes = (sizeof(SvOp) * n_gates + 15) & ~size_t(15);
+    const size_t mat_bytes = (sizeof(SvMat) * n_mats + sizeof(int) * n_mat_gates + 15) & ~size_t(15);
+    const int n_share = 2 * P + n_passes + 1 + P;
+    const size_t share_bytes = (sizeof(int) * n_share + 15) & ~size_t(15);
+    dqgp_gate* s_gates = reinterpret_cast<dqgp_gate*>(smem_raw);
+    SvPass* s_passes = reinterpret_cast<SvPass*>(smem_raw + gate_bytes);
+    SvOp* s_ops = reinterpret_cast<SvOp*>(smem_raw + gate_bytes + pass_bytes);
+    SvMat* s_mats = reinterpret_cast<SvMat*>(smem_raw + gate_bytes + pass_bytes + op_bytes);
+    int* s_mat_gates = reinterpret_cast<int*>(s_mats + n_mats);
+    int* s_share = reinterpret_cast<int*>(smem_raw + gate_bytes + pass_bytes + op_bytes + mat_bytes);
+    const int* par_gate = s_share;
+    const int* par_mat = s_share + P;
+    const int* pass_par_begin = s_share + 2 * P;
+    const int* pass_params = s_share + 2 * P + n_passes + 1;
+    for (int i = threadIdx.x; i < n_gates; i += blockDim.x) { s_gates[i] = gates[i]; s_ops[i] = ops[i]; }
+    for (int i = threadIdx.x; i < n_passes; i += blockDim.x) s_passes[i] = passes[i];
+    for (int i = threadIdx.x; i < n_mats; i += blockDim.x) s_mats[i] = mats[i];
+    for (int i = threadIdx.x; i < n_mat_gates; i += blockDim.x) s_mat_gates[i] = mat_gates[i];
+    for (int i = threadIdx.x; i < n_share; i += blockDim.x) s_share[i] = share[i];
+    __syncthreads();
+
+    // per-team storage: base | scratch | final base state | cos/sin table | fused matrices | fork matrices | acos | reduction | A,B,C
+    const size_t team_bytes = sizeof(double2) * (3 * T::DIM + n_gates + 4 * n_mats + 4 * T::SLOTS) +
+                              sizeof(double) * (((d + 1) & ~1) + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0) + 3 * M3P);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int team_in_block = T::BLOCK ? 0 : warp * T::PER_WARP + lane / T::SIZE;
+    const int lig = T::BLOCK ? threadIdx.x : lane % T::SIZE;
+    const int teams_per_block = T::BLOCK ? 1 : (blockDim.x >> 5) * T::PER_WARP;
+    unsigned char* my = smem_raw + gate_bytes + pass_bytes + op_bytes + mat_bytes + share_bytes + team_bytes * team_in_block;
+    double2* base = reinterpret_cast<double2*>(my);
+    double2* scr = base + T::DIM;
+    double2* fin = scr + T::DIM;
+    double2* trig = fin + T::DIM;
+    double2* u2 = trig + n_gates;
+    double2* altm = u2 + 4 * n_mats;
+    double* acx = reinterpret_cast<double*>(altm + 4 * T::SLOTS);
+    double* red = acx + ((d + 1) & ~1);
+    double* featA = red + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0);
+    double* featB = featA + M3P;
+    double* featC = featB + M3P;
+    const SvAlt no_alt = SvAlt{-1, -1, nullptr};
+    constexpr int FULL = Q / 3, REM = Q % 3;
+
+    const long long n_rounds = (n + (long long)gridDim.x * teams_per_block - 1) / ((long long)gridDim.x * teams_per_block);
+    for (long long round = 0; round < n_rounds; ++round) {
+        long long j = (round * gridDim.x + blockIdx.x) * teams_per_block + team_in_block;
+        const bool live = j < n;
+        if (!live) j = n - 1;
+        const double* x = X + (size_t)j * d;
+        if (uses_acos) {
+            for (int f = lig; f < d; f += T::SIZE) acx[f] = acos(x[f]);
+            T::sync();
+        }
+        for (int g = lig; g < n_gates; g += T::SIZE) {
+            const dqgp_gate gt = s_gates[g];
+            if (gt.form == DQGP_A_NONE) continue;
+            double sn, cs;
+            sincos(0.5 * gate_angle(gt, gt.pidx >= 0 ? Pm[gt.pidx] : 0.0, x, acx), &sn, &cs);
+            trig[g] = make_double2(cs, sn);
+        }
+        for (int i = lig; i < T::DIM; i += T::SIZE) { base[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0); fin[i] = base[i]; }
+        T::sync();
+        for (int f = lig; f < n_mats; f += T::SIZE) compose_matrix(s_mats[f], s_mat_gates, s_gates, trig, -1, make_double2(0, 0), u2 + 4 * f);
+        T::sync();
+
+        // sweep 1: the final base state (kept for the cross terms) and the base set's output
+        sv_run_passes<Q>(fin, s_passes, 0, n_passes, s_ops, u2, trig, lig, no_alt, 0);
+        if (WANT_STATES) {
+            sv_emit<Q, true>(fin, lig, live, out, j, red);
+        } else {
+#pragma unroll 1
+            for (int b = 0; b < FULL; ++b) features_block<(Q >= 3 ? 3 : 1), Q>(fin, 3 * b, lig, T::SIZE, true, featA, red);
+            if (REM == 2) features_block<(Q >= 2 ? 2 : 1), Q>(fin, 3 * FULL, lig, T::SIZE, true, featA, red);
+            if (REM == 1) features_block<1, Q>(fin, 3 * FULL, lig, T::SIZE, true, featA, red);
+            T::sync();
+            if (live)
+                for (int k = lig; k < M3; k += T::SIZE) out[(size_t)j * M3 + k] = featA[k];
+        }
+        T::sync();
+
+        // sweep 2: advance the base pass by pass; fork every parameter whose op lives in the pass about to run
+        for (int ip = 0; ip < n_passes; ++ip) {
+            const int pb = pass_par_begin[ip], pe = pass_par_begin[ip + 1];
+            for (int f0 = 2 * pb; f0 < 2 * pe; f0 += T::SLOTS) {
+                const int cnt = min(T::SLOTS, 2 * pe - f0);
+                if (lig < cnt) {
+                    const int fk = f0 + lig, i = pass_params[fk >> 1], sg = fk & 1;
+                    const int g = par_gate[i];
+                    if (par_mat[i] >= 0) {
+                        // rotation: one fork with the gate's angle advanced by pi: (cos, sin)(theta/2 + pi/2) = (-sin, cos)(theta/2)
+                        if (sg == 0) compose_matrix(s_mats[par_mat[i]], s_mat_gates, s_gates, trig, g, make_double2(-trig[g].y, trig[g].x), altm + 4 * lig);
+                    } else {
+                        double sn, cs;
+                        sincos(0.5 * gate_angle(s_gates[g], Pm[(size_t)(1 + 2 * i + sg) * P + i], x, acx), &sn, &cs);
+                        altm[4 * lig] = make_double2(cs, sn);
+                    }
+                }
+                T::sync();
+                for (int t = 0; t < cnt; ++t) {
+                    const int fk = f0 + t, i = pass_params[fk >> 1], sg = fk & 1;
+                    const bool rot = par_mat[i] >= 0;
+                    if (rot && sg == 1) continue;                 // both signs come out of the sg = 0 fork
+                    for (int a = lig; a < T::DIM; a += T::SIZE) scr[a] = base[a];
+                    T::sync();
+                    const SvAlt alt = SvAlt{par_mat[i], rot ? -1 : par_gate[i], altm + 4 * t};
+                    sv_run_passes<Q>(scr, s_passes, ip, n_passes, s_ops, u2, trig, lig, alt, 0);
+                    if (!rot) {
+                        sv_emit<Q, WANT_STATES>(scr, lig, live, out, (long long)(1 + 2 * i + sg) * n + j, red);
+                    } else {
+                        const dqgp_gate gt = s_gates[par_gate[i]];
+                        const double th0 = gate_angle(gt, Pm[i], x, acx);
+                        double c[2], sn[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            sincos(0.5 * (gate_angle(gt, Pm[(size_t)(1 + 2 * i + e) * P + i], x, acx) - th0), &sn[e], &c[e]);
+                        if (WANT_STATES) {
+                            if (live) {
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    double2* dst = reinterpret_cast<double2*>(out) + ((size_t)(1 + 2 * i + e) * n + j) * T::DIM;
+                                    for (int a = lig; a < T::DIM; a += T::SIZE) {
+                                        const double2 u = fin[sv_phys(a)], v = scr[sv_phys(a)];
+                                        dst[a] = make_double2(fma(c[e], u.x, sn[e] * v.x), fma(c[e], u.y, sn[e] * v.y));
+                                    }
+                                }
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int b = 0; b < FULL; ++b) {
+                                features_block<(Q >= 3 ? 3 : 1), Q>(scr, 3 * b, lig, T::SIZE, true, featB, red);
+                                features_cross_block<(Q >= 3 ? 3 : 1), Q>(fin, scr, 3 * b, lig, T::SIZE, featC, red);
+                            }
+                            if (REM == 2) {
+                                features_block<(Q >= 2 ? 2 : 1), Q>(scr, 3 * FULL, lig, T::SIZE, true, featB, red);
+                                features_cross_block<(Q >= 2 ? 2 : 1), Q>(fin, scr, 3 * FULL, lig, T::SIZE, featC, red);
+                            }
+                            if (REM == 1) {
+                                features_block<1, Q>(scr, 3 * FULL, lig, T::SIZE, true, featB, red);
+                                features_cross_block<1, Q>(fin, scr, 3 * FULL, lig, T::SIZE, featC, red);
+                            }
+                            T::sync();
+                            if (live) {
+                                for (int k = lig; k < M3; k += T::SIZE) {
+                                    const double A = featA[k], B = featB[k], C = featC[k];
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e)
+                                        out[((size_t)(1 + 2 * i + e) * n + j) * M3 + k] =
+                                            fma(c[e] * c[e], A, fma(sn[e] * sn[e], B, 2.0 * sn[e] * c[e] * C));
+                                }
+                            }
+                        }
+                    }
+                    T::sync();
+                }
+            }
+            sv_run_passes<Q>(base, s_passes, ip, n_passes, s_ops, u2, trig, lig, no_alt, 1);
+        }
+        T::sync();
+    }
+}
+
 template <int Q, bool WANT_STATES>
 static int launch_sv_shared(const dqgp_circuit* c, const double* X, int n, const double* Pm, double* out, cudaStream_t st) {
     using T = SvTeam<Q>;
@@ -628,14 +875,16 @@ static int launch_sv_shared(const dqgp_circuit* c, const double* X, int n, const
     const size_t fixed = ((sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvPass) * n_passes + 15) & ~size_t(15)) +
                          ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvMat) * n_mats + sizeof(int) * n_mat_gates + 15) & ~size_t(15)) +
                          ((sizeof(int) * n_share + 15) & ~size_t(15));
-    const size_t team_bytes = sizeof(double2) * (2 * T::DIM + n_gates + 4 * n_mats + 4 * T::SLOTS) +
-                              sizeof(double) * (((c->d + 1) & ~1) + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0));
+    // linear-combination form (statevec_lc_kernel) unless DQGP_SV_NO_LC is set (A/B checks against the two-fork kernel)
+    const bool use_lc = getenv("DQGP_SV_NO_LC") == nullptr;
+    const size_t team_bytes = sizeof(double2) * ((use_lc ? 3 : 2) * T::DIM + n_gates + 4 * n_mats + 4 * T::SLOTS) +
+                              sizeof(double) * (((c->d + 1) & ~1) + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0) + (use_lc ? 3 * ((3 * Q + 1) & ~1) : 0));
     int warps = T::BLOCK ? T::SIZE / 32 : 4;
     int teams = T::BLOCK ? 1 : warps * T::PER_WARP;
     while (!T::BLOCK && warps > 1 && fixed + team_bytes * teams > 100 * 1024) { warps >>= 1; teams = warps * T::PER_WARP; }
     const size_t smem = fixed + team_bytes * teams;
     DQGP_REQUIRE(smem <= 227 * 1024, "statevector kernel needs %zu bytes of shared memory (q=%d, %d gates)", smem, Q, n_gates);
-    auto kern = statevec_shared_kernel<Q, WANT_STATES>;
+    auto kern = use_lc ? statevec_lc_kernel<Q, WANT_STATES> : statevec_shared_kernel<Q, WANT_STATES>;
     DQGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
@@ -736,7 +985,9 @@ static int dispatch_sv_shared(const dqgp_circuit* c, const double* X, int n, con
     // prefix sharing parallelises over samples only: with few samples (or a parameter feeding several gates) the
     // per-set kernel, which parallelises over samples x sets, fills the machine better
     const long long teams = c->q >= 9 ? n : (long long)n * (c->q > 3 ? (1 << (c->q - 3)) : 1) / 32;
-    if (!c->shareable || teams < (c->q >= 9 ? 600 : 1200)) return dispatch_sv<WANT_STATES>(c, X, n, Pm, 2 * P + 1, out, stream);
+    // DQGP_SV_FORCE_SHARED: tests exercise the sharing kernels at small n
+    if (!c->shareable || (teams < (c->q >= 9 ? 600 : 1200) && getenv("DQGP_SV_FORCE_SHARED") == nullptr))
+        return dispatch_sv<WANT_STATES>(c, X, n, Pm, 2 * P + 1, out, stream);
     int rc = circuit_on_device(c);
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);

@@ -53,9 +53,11 @@ def test_features_and_states_match_oracle(d, enc, q, dd, layers):
 
 @pytest.mark.parametrize("enc,q,dd,layers", [("chebyshev", 3, 2, 1), ("chebyshev", 4, 2, 3), ("hubregtsen", 5, 2, 2), ("yz_cx", 8, 4, 3),
                                             ("yz_cx", 1, 1, 2), ("kyriienko", 10, 6, 2), ("hubregtsen", 9, 3, 1), ("yz_cx", 6, 3, 2)])
-def test_shared_prefix_simulation_is_bit_identical(d, enc, q, dd, layers):
-    """dqgp_features_shifted / dqgp_states_shifted (prefix sharing over the 2P+1 central-difference sets) must equal
-    the per-set kernels bit for bit, including circuits whose parameters sit on CRZ gates."""
+def test_shared_prefix_simulation_matches_per_set_kernels(d, enc, q, dd, layers, monkeypatch):
+    """dqgp_features_shifted / dqgp_states_shifted over the 2P+1 central-difference sets against the per-set kernels:
+    the two-fork prefix-sharing kernel bit for bit; the linear-combination kernel (one fork per rotation parameter, both
+    signs from <psi|O|psi>, <phi|O|phi>, Re<psi|O|phi>) to rounding, including circuits whose parameters sit on CRZ gates
+    (those keep two forks) and parameter sets whose +h / -h shifts wrap differently."""
     from oracle import agent_step, circuits
     rng = np.random.default_rng(7 * q + dd)
     n = 45
@@ -67,12 +69,24 @@ def test_shared_prefix_simulation_is_bit_identical(d, enc, q, dd, layers):
     dx, dpm = d.kernels.dev_f64(x), d.kernels.dev_f64(pm)
     lib = d.load()
     F_ref, S_ref = ec.features(dx, dpm), ec.states(dx, dpm)
-    F = torch.full_like(F_ref, float("nan"))
-    S = torch.full_like(S_ref, float("nan"))
-    assert lib.dqgp_features_shifted(ec.handle, dx.data_ptr(), n, dpm.data_ptr(), P, F.data_ptr(), _sp()) == 0, lib.dqgp_last_error()
-    assert lib.dqgp_states_shifted(ec.handle, dx.data_ptr(), n, dpm.data_ptr(), P, S.data_ptr(), _sp()) == 0, lib.dqgp_last_error()
-    assert torch.equal(F, F_ref)
-    assert torch.equal(S, S_ref)
+    monkeypatch.setenv("DQGP_SV_FORCE_SHARED", "1")      # n = 45 is below the size where the sharing kernels are dispatched
+    for no_lc in (True, False):
+        if no_lc:
+            monkeypatch.setenv("DQGP_SV_NO_LC", "1")
+        else:
+            monkeypatch.delenv("DQGP_SV_NO_LC")
+        F = torch.full_like(F_ref, float("nan"))
+        S = torch.full_like(S_ref, float("nan"))
+        assert lib.dqgp_features_shifted(ec.handle, dx.data_ptr(), n, dpm.data_ptr(), P, F.data_ptr(), _sp()) == 0, lib.dqgp_last_error()
+        assert lib.dqgp_states_shifted(ec.handle, dx.data_ptr(), n, dpm.data_ptr(), P, S.data_ptr(), _sp()) == 0, lib.dqgp_last_error()
+        torch.cuda.synchronize()
+        if no_lc:
+            assert torch.equal(F, F_ref)
+            assert torch.equal(S, S_ref)
+        else:
+            assert (F - F_ref).abs().max().item() < 2e-14
+            assert (S - S_ref).abs().max().item() < 2e-14
+            assert torch.equal(F[0], F_ref[0]) and torch.equal(S[0], S_ref[0])      # the base set is simulated directly
 
 
 def test_features_empty_and_single(d):
