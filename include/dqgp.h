@@ -12,7 +12,9 @@
  *     and nothing synchronises unless stated;
  *   - return value: 0 = ok, <0 = error (dqgp_last_error() gives a thread-local message); nothing throws;
  *   - no global mutable state; handles are immutable after creation and may be shared by streams,
- *     except dqgp_solver (owns scratch: one in-flight use at a time);
+ *     except dqgp_solver (owns scratch and internal streams: one in-flight use at a time);
+ *   - diagnostics read from the environment at call time: DQGP_POTRF_TRACE (time stamps of the Cholesky's leaf chain),
+ *     DQGP_SV_NO_LC / DQGP_SV_FORCE_SHARED (simulator kernel selection), DQGP_GRAM_DIRECT, DQGP_FID_SIMT (v1 kernels);
  *   - there is no CPU fallback anywhere in this library.
  */
 #ifndef DQGP_H
@@ -92,7 +94,7 @@ int dqgp_gram_fidelity(const double* d_Psi1, int n1, const double* d_Psi2, int n
  *      reference's LU -> pinv ladder (agent_riemannian.py:419-428) or raise. */
 int dqgp_solver_create(int n, dqgp_solver** out);
 /* outer_blocks: width of the outer Cholesky panel in 128-column blocks. 4 (default, = 0) gives rank-512 trailing
- * updates (best throughput when several agents share a GPU); 1 is the shortest critical path (one agent per GPU). */
+ * updates (best throughput when several agents share a GPU); 2 is the fastest for one agent per GPU (measured 1..8). */
 int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out);
 /* Lean solver for prediction / CV at full-train scale (main.py:1364-1596): ONE padded square (A, factored
  * in place) + the inverted 128x128 diagonal blocks + two rotating panel buffers, instead of three squares.  Supports
@@ -111,8 +113,9 @@ size_t dqgp_solver_bytes(const dqgp_solver* s);
 int dqgp_solver_potrf_launches(const dqgp_solver* s); /* kernel launches of the Cholesky stage (bench launch accounting) */
 int dqgp_add_diagonal(double* d_A, int n, int lda, double value, void* stream);
 /* want_inverse: <0 factor only, 0 factor + alpha + logdet, 1 + A^-1 (lower tiles), 2 + A^-1 (full symmetric).
- * Enqueues on `stream` and on the solver's internal high-priority stream (joined back before returning control of
- * `stream`); graph-capturable. */
+ * Enqueues on `stream` and on the solver's two internal high-priority streams (the leaf chain and the panel work of the
+ * look-ahead schedule; both are forked from and joined back to `stream`, so the call is graph-capturable and ordered like
+ * any other work on `stream`).  A lean solver accepts want_inverse <= 0 only. */
 int dqgp_potrf_solve_inv(dqgp_solver* s, const double* d_y, double* d_alpha, double* d_logdet, int* d_info,
                          int want_inverse, void* stream);
 /* want_inverse < 0 in dqgp_potrf_solve_inv = factor only (d_y, d_alpha may be NULL).
@@ -123,7 +126,8 @@ int dqgp_solver_quadform_rows(dqgp_solver* s, const double* d_B, int nb, int ldb
 
 /* Same quantity by in-place blocked forward substitution (works on lean solvers): d_B (nb_pad, ldb) with nb_pad a multiple
  * of 128, ldb >= n_pad = dqgp_solver_ld() and even, 16-byte aligned, columns n..n_pad zero; rows are OVERWRITTEN by
- * (L^-1 b_i)^T, d_out[nb_pad] receives the squared norms. */
+ * (L^-1 b_i)^T, d_out[nb_pad] receives the squared norms.  Grows the solver's scratch on first use with a larger nb_pad
+ * (synchronises `stream` then; not graph-capturable at that moment). */
 int dqgp_solver_quadform_rows_inplace(dqgp_solver* s, double* d_B, int nb_pad, int ldb, double* d_out, void* stream);
 
 /* fp64 GEMM building block on the DMMA tensor path (used by the factorisation; exposed for tests):
