@@ -25,8 +25,11 @@ struct dqgp_solver {
     int lean, ldw, ldt;
     double *A, *W, *T;
     double* w_block(int k) const { return lean ? W + (size_t)k * 128 * 128 : W + (size_t)k * 128 * ld + (size_t)k * 128; }
+    // outer panels: panel p covers block columns [pan_lo[p], pan_hi[p]); widths may vary (wide while the trailing updates
+    // bound the factorisation, narrow once the leaf chain does)
+    std::vector<int> pan_of, pan_lo, pan_hi;
     double* t_block(int r, int k) const {   // block (r, k) of the panel storage
-        return lean ? T + (size_t)((k / ob) & 1) * np * ldt + (size_t)r * 128 * ldt + (size_t)(k % ob) * 128
+        return lean ? T + (size_t)(pan_of[k] & 1) * np * ldt + (size_t)r * 128 * ldt + (size_t)(k - pan_lo[pan_of[k]]) * 128
                     : T + (size_t)r * 128 * ld + (size_t)k * 128;
     }
     dqgp::GemmTask* d_dyn;        // per-call task table of the in-place substitution (dqgp_solver_quadform_rows_inplace)
@@ -552,7 +555,7 @@ static int potrf_lookahead(dqgp_solver* s, double* d_logdet, int* d_info, cudaSt
     auto stamp = [&]() { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, crit); tev.push_back(e); } };
     int last_rest = -1;
     for (int k = 0; k < nblk; ++k) {
-        const int p = k / OB, p0 = p * OB, pend = std::min(p0 + OB, nblk);
+        const int p = s->pan_of[k], p0 = s->pan_lo[p], pend = s->pan_hi[p];
         stamp();
         potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM_V2, crit>>>(s->A, ld, s->w_block(k), s->ldw, k, d_logdet, d_info, s->n);
         DQGP_LAUNCH_CHECK("potrf_leaf_kernel");
@@ -643,8 +646,19 @@ static int solver_create_impl(int n, int outer_blocks, int lean, dqgp_solver** o
     DQGP_REQUIRE(n >= 1 && n <= (1 << 17), "dqgp_solver_create: n = %d outside [1, 131072]", n);
     dqgp_solver* s = new dqgp_solver();
     s->n = n;
-    s->ob = outer_blocks > 0 ? (outer_blocks > 16 ? 16 : outer_blocks) : 4;
+    s->ob = outer_blocks > 0 ? (outer_blocks > 16 ? 16 : outer_blocks) : 4;      // widest panel
     s->nblk = (n + NB - 1) / NB;
+    {
+        // outer_blocks < 0: rank-512 panels while more than 28 block columns remain (there the rank-k trailing updates bound
+        // the factorisation and want the long contraction), rank-256 panels afterwards (the leaf chain bounds it)
+        s->pan_of.assign(s->nblk, 0);
+        for (int k0 = 0, p = 0; k0 < s->nblk; ++p) {
+            const int w = std::min(outer_blocks < 0 ? (s->nblk - k0 > 28 ? 4 : 2) : s->ob, s->nblk - k0);
+            s->pan_lo.push_back(k0); s->pan_hi.push_back(k0 + w);
+            for (int k = k0; k < k0 + w; ++k) s->pan_of[k] = p;
+            k0 += w;
+        }
+    }
     s->np = s->nblk * NB;
     s->ld = s->np;
     s->A = s->W = s->T = s->y_pad = s->w = s->partial = s->strip = s->V = nullptr;
@@ -685,7 +699,6 @@ static int solver_create_impl(int n, int outer_blocks, int lean, dqgp_solver** o
     auto at = [&](double* base, int rb, int cb) { return base + (size_t)rb * NB * ld + (size_t)cb * NB; };
     std::vector<GemmTask> grp;
     auto small = [](GemmTask t) { t.tiles = gemm_task_tiles_small(t); return t; };
-    const int OB = s->ob;
     // ---- look-ahead schedule.  Step k (panel p = k / OB, columns [p0, pend)):
     //   trsmA[k]  T(k+1,k)   = A(k+1,k) Wkk^T                       (one block row: what the next leaf waits for)
     //   updA[k]   A(k+1,k+1) -= T(k+1,k) T(k+1,k)^T
@@ -697,7 +710,7 @@ static int solver_create_impl(int n, int outer_blocks, int lean, dqgp_solver** o
     auto tW = [&](int k) { return s->w_block(k); };
     auto tT = [&](int r, int k) { return s->t_block(r, k); };
     for (int k = 0; k + 1 < nblk; ++k) {
-        const int p0 = (k / OB) * OB, pend = std::min(p0 + OB, nblk);
+        const int pend = s->pan_hi[s->pan_of[k]];
         // the two products on the leaf chain run on the small-tile kernel: 16 (10 for the symmetric update) CTAs of 32x32
         grp.push_back(small(make_task3(at(s->A, k + 1, k), ld, tW(k), ldw, tT(k + 1, k), ldt, NB, NB, NB, 1, 1, 0, GM_KRULE_ALL, 1.0, 0.0)));
         s->trsmA.push_back(push_group(grp));
@@ -713,9 +726,10 @@ static int solver_create_impl(int n, int outer_blocks, int lean, dqgp_solver** o
             grp.push_back(make_task3(tT(c, k), ldt, tT(c, k), ldt, at(s->A, c, c), ld, np - c * NB, NB, NB, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
         s->updB.push_back(push_group(grp));
     }
-    for (int p0 = 0; p0 < nblk; p0 += OB) {
-        const int w = std::min(OB, nblk - p0), pend = p0 + w;
-        const int c1 = pend + 1, c2 = pend + 2, c2e = std::min(pend + OB, nblk - 1), c3 = pend + OB + 1;
+    for (size_t p = 0; p < s->pan_lo.size(); ++p) {
+        const int p0 = s->pan_lo[p], pend = s->pan_hi[p], w = pend - p0;
+        const int pnext = p + 1 < s->pan_hi.size() ? s->pan_hi[p + 1] : nblk;      // end of the next panel
+        const int c1 = pend + 1, c2 = pend + 2, c2e = std::min(pnext, nblk - 1), c3 = pnext + 1;
         if (c1 < nblk)
             grp.push_back(make_task3(tT(c1, p0), ldt, tT(c1, p0), ldt, at(s->A, c1, c1), ld, np - c1 * NB, NB, w * NB, 1, 1, 0, GM_KRULE_ALL, -1.0, 1.0));
         s->next1.push_back(push_group(grp));
@@ -770,7 +784,7 @@ static int solver_create_impl(int n, int outer_blocks, int lean, dqgp_solver** o
         }
     };
     make_events(s->ev_leaf, nblk); make_events(s->ev_a, nblk); make_events(s->ev_b, nblk);
-    make_events(s->ev_n1, (nblk + s->ob - 1) / s->ob); make_events(s->ev_n2, (nblk + s->ob - 1) / s->ob);
+    make_events(s->ev_n1, (int)s->pan_lo.size()); make_events(s->ev_n2, (int)s->pan_lo.size());
     {
         int cnt = nblk;
         for (int k = 0; k + 1 < nblk; ++k) cnt += 2 + (s->trsmB[k].tiles > 0) + (s->updB[k].tiles > 0);
@@ -779,7 +793,7 @@ static int solver_create_impl(int n, int outer_blocks, int lean, dqgp_solver** o
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming);
-    make_events(s->ev_rest, (nblk + s->ob - 1) / s->ob);
+    make_events(s->ev_rest, (int)s->pan_lo.size());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEAF_SMEM_V2);
     if (e != cudaSuccess) { dqgp_solver_destroy(s); return cuda_fail(e, "dqgp_solver_create (task table)"); }
     int rc = gemm_init();

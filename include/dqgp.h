@@ -94,7 +94,8 @@ int dqgp_gram_fidelity(const double* d_Psi1, int n1, const double* d_Psi2, int n
  *      reference's LU -> pinv ladder (agent_riemannian.py:419-428) or raise. */
 int dqgp_solver_create(int n, dqgp_solver** out);
 /* outer_blocks: width of the outer Cholesky panel in 128-column blocks. 4 (default, = 0) gives rank-512 trailing
- * updates (best throughput when several agents share a GPU); 2 is the fastest for one agent per GPU (measured 1..8). */
+ * updates (best throughput when several agents share a GPU); < 0 = width 4 while more than 28 block columns remain and 2
+ * afterwards (one agent per GPU: wide while the trailing updates bound the factorisation, narrow once the leaf chain does). */
 int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out);
 /* Lean solver for prediction / CV at full-train scale (main.py:1364-1596): ONE padded square (A, factored
  * in place) + the inverted 128x128 diagonal blocks + two rotating panel buffers, instead of three squares.  Supports

@@ -72,7 +72,7 @@ def test_train_agents_concurrent_equals_sequential(d):
     assert np.max(np.abs(par[0][0] - gs[0]["theta_out"])) < 1e-12
 
 
-@pytest.mark.parametrize("outer_blocks", [1, 2, 4])
+@pytest.mark.parametrize("outer_blocks", [1, 2, 4, -1])
 def test_cholesky_panel_width_does_not_change_results(d, outer_blocks):
     from oracle import driver
     x, y = driver.synthetic_dataset(1100, 4, "yz_cx")

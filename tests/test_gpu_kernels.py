@@ -263,7 +263,7 @@ def test_shift_parameter_sets_bit_exact(d):
     assert np.array_equal(out.cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("n,ob", [(100, 4), (640, 1), (1500, 2), (2100, 4)])
+@pytest.mark.parametrize("n,ob", [(100, 4), (640, 1), (1500, 2), (2100, 4), (4500, -1)])
 def test_lean_solver_matches_full_solver(d, n, ob):
     """Lean solver (one square, rotating panel buffers, substitution solves) == full solver: same factor bit for bit,
     alpha / logdet to rounding, and the in-place quadratic form == the L^-1-based one."""
