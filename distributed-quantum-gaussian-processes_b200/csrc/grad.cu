@@ -333,6 +333,76 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const double* __restri
     if (threadIdx.x == 0) grad[i] = scale * s[0];
 }
 
+// ---- analytic gradient (opt-in; SURVEY 8(f) row 3: NOT the reference's central difference, Q3) -------------------------------
+// For the Gaussian outer kernel K_jk = exp(-gamma |f_j - f_k|^2) and B = A^-1 - alpha alpha^T,
+//   grad_i = 1/2 sum_jk B_jk dK_jk/dp_i = -2 gamma sum_j < df_j/dp_i , G_j >,   G_j = sum_k (B o K)_jk (f_j - f_k),
+// so ONE pass over the n x n entries (one exp per entry instead of 2P) gives G (n x m), and the P parameters only enter
+// through the feature Jacobian (dqgp_features_jacobian) in an O(P n m) contraction.
+// grad_analytic_rows_kernel: thread = row r of a column segment; f_r and the running G_r live in registers (M = 3q at compile
+// time), the segment's f_c stream through shared memory 64 columns at a time, A^-1 is read through its symmetric image
+// A^-1[c][r] so consecutive threads read consecutive addresses.  Fixed summation order: bit-reproducible.
+constexpr int GA_ROWS = 128, GA_CHUNK = 64, GA_SEGMENTS = 16;
+
+template <int M>
+__global__ void __launch_bounds__(GA_ROWS) grad_analytic_rows_kernel(const double* __restrict__ Ainv, int ld, const double* __restrict__ alpha,
+                                                                    const double* __restrict__ F, int n, double gamma, int seg_cols,
+                                                                    double* __restrict__ Gpart) {
+    __shared__ double Fc[GA_CHUNK * M];
+    __shared__ double ac[GA_CHUNK];
+    const int r = blockIdx.x * GA_ROWS + threadIdx.x;
+    const int c_begin = blockIdx.y * seg_cols, c_end = min(n, c_begin + seg_cols);
+    const bool live = r < n;
+    double fr[M], h[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) { fr[k] = live ? F[(size_t)r * M + k] : 0.0; h[k] = 0.0; }
+    const double ar = live ? alpha[r] : 0.0;
+    for (int c0 = c_begin; c0 < c_end; c0 += GA_CHUNK) {
+        const int cnt = min(GA_CHUNK, c_end - c0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * M; e += GA_ROWS) Fc[e] = F[(size_t)c0 * M + e];
+        if (threadIdx.x < cnt) ac[threadIdx.x] = alpha[c0 + threadIdx.x];
+        __syncthreads();
+        if (!live) continue;
+        for (int cc = 0; cc < cnt; ++cc) {
+            const double* fc = Fc + cc * M;
+            double df[M], d2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < M; ++k) { df[k] = fr[k] - fc[k]; d2 = fma(df[k], df[k], d2); }
+            const double q = (Ainv[(size_t)(c0 + cc) * ld + r] - ar * ac[cc]) * fast_exp(-gamma * d2);
+#pragma unroll
+            for (int k = 0; k < M; ++k) h[k] = fma(q, df[k], h[k]);
+        }
+    }
+    if (live) {
+        double* dst = Gpart + ((size_t)blockIdx.y * n + r) * M;
+#pragma unroll
+        for (int k = 0; k < M; ++k) dst[k] = h[k];
+    }
+}
+// G = sum over segments, fixed order
+__global__ void grad_analytic_sum_kernel(const double* __restrict__ Gpart, size_t count, int segments, double* __restrict__ G) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count) return;
+    double acc = 0.0;
+    for (int sgm = 0; sgm < segments; ++sgm) acc += Gpart[(size_t)sgm * count + e];
+    G[e] = acc;
+}
+// grad[i] = scale * <J_i, G>  (n*m products, strided per thread then a fixed tree)
+__global__ void __launch_bounds__(256) grad_analytic_contract_kernel(const double* __restrict__ J, const double* __restrict__ G, size_t count,
+                                                                     double scale, double* __restrict__ grad) {
+    __shared__ double sred[256];
+    const double* Ji = J + (size_t)blockIdx.x * count;
+    double acc = 0.0;
+    for (size_t e = threadIdx.x; e < count; e += 256) acc = fma(Ji[e], G[e], acc);
+    sred[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sred[threadIdx.x] += sred[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) grad[blockIdx.x] = scale * sred[0];
+}
+
 static inline int grad_tiles(int n) {
     const int t = (n + PW_TILE - 1) / PW_TILE;
     return t * (t + 1) / 2;
@@ -392,6 +462,38 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
     DQGP_LAUNCH_CHECK("grad_projected_kernel");
     grad_reduce_kernel<<<P, 256, 0, st>>>(partial, tiles, P, 0.5 / (2.0 * h), d_grad);
     DQGP_LAUNCH_CHECK("grad_reduce_kernel");
+    return 0;
+}
+
+size_t dqgp_grad_analytic_workspace_bytes(int n, int m) {
+    if (n <= 0 || m <= 0) return 0;
+    return sizeof(double) * (size_t)(dqgp::GA_SEGMENTS + 1) * (size_t)n * (size_t)m;
+}
+
+int dqgp_grad_projected_analytic(int outer, const double* h_hyp, const double* d_Ainv, int ld, const double* d_alpha, const double* d_F,
+                                 const double* d_J, int n, int m, int P, double* d_grad, void* d_work, void* stream) {
+    using namespace dqgp;
+    DQGP_REQUIRE(d_Ainv && d_alpha && d_F && d_J && d_grad && d_work && h_hyp, "dqgp_grad_projected_analytic: NULL argument");
+    DQGP_REQUIRE(outer == DQGP_OUTER_GAUSSIAN, "dqgp_grad_projected_analytic: only the Gaussian outer kernel (what the reference trains with, Q1)");
+    DQGP_REQUIRE(n >= 1 && ld >= n && P >= 1 && m >= 3 && m <= 36 && m % 3 == 0, "dqgp_grad_projected_analytic: bad shape (m = 3q, q <= 12)");
+    OuterHyp hyp;
+    if (make_outer_hyp(outer, h_hyp, &hyp)) return -1;
+    cudaStream_t st = as_stream(stream);
+    double* Gpart = static_cast<double*>(d_work);
+    double* G = Gpart + (size_t)GA_SEGMENTS * n * m;
+    const int seg_cols = ((n + GA_SEGMENTS - 1) / GA_SEGMENTS + GA_CHUNK - 1) / GA_CHUNK * GA_CHUNK;
+    const int segments = (n + seg_cols - 1) / seg_cols;
+    dim3 grid((n + GA_ROWS - 1) / GA_ROWS, segments);
+    switch (m / 3) {
+#define DQGP_GA(QQ) case QQ: grad_analytic_rows_kernel<3 * QQ><<<grid, GA_ROWS, 0, st>>>(d_Ainv, ld, d_alpha, d_F, n, hyp.a, seg_cols, Gpart); break;
+        DQGP_GA(1) DQGP_GA(2) DQGP_GA(3) DQGP_GA(4) DQGP_GA(5) DQGP_GA(6) DQGP_GA(7) DQGP_GA(8) DQGP_GA(9) DQGP_GA(10) DQGP_GA(11) DQGP_GA(12)
+#undef DQGP_GA
+    }
+    DQGP_LAUNCH_CHECK("grad_analytic_rows_kernel");
+    const size_t count = (size_t)n * m;
+    grad_analytic_sum_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(Gpart, count, segments, G);
+    grad_analytic_contract_kernel<<<P, 256, 0, st>>>(d_J, G, count, -2.0 * hyp.a, d_grad);
+    DQGP_LAUNCH_CHECK("grad_analytic kernels");
     return 0;
 }
 

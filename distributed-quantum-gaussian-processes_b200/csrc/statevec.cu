@@ -695,11 +695,14 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_shared_kernel(
 // One fork per parameter instead of two: P suffix simulations instead of 2P (D+ and D- are whatever the wrapped parameter sets of
 // dqgp_shift_parameter_sets give for this sample: they need not be symmetric).  CRZ parameters keep the two-fork path.  Results
 // equal the per-set simulation to rounding (1e-15), not bit for bit.
-template <int Q, bool WANT_STATES>
+// JAC: instead of the two shifted sets, emit the exact feature Jacobian  d<O_k>/dp_i = (dtheta/dp_i) Re<psi|O_k|phi>  (the sin D
+// coefficient above is the derivative at D = 0): out = base features (n, 3q), jac = (P, n, 3q); Pm is the single base row.
+template <int Q, bool WANT_STATES, bool JAC = false>
 __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc_kernel(
     const dqgp_gate* __restrict__ gates, int n_gates, const SvPass* __restrict__ passes, int n_passes, const SvOp* __restrict__ ops,
     const SvMat* __restrict__ mats, int n_mats, const int* __restrict__ mat_gates, int n_mat_gates, const int* __restrict__ share,
-    int d, int P, int uses_acos, const double* __restrict__ X, int n, const double* __restrict__ Pm, double* __restrict__ out) {
+    int d, int P, int uses_acos, const double* __restrict__ X, int n, const double* __restrict__ Pm, double* __restrict__ out,
+    double* __restrict__ jac = nullptr) {
     using T = SvTeam<Q>;
     constexpr int M3 = 3 * Q, M3P = (M3 + 1) & ~1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -796,7 +799,7 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc_kernel(
                     if (par_mat[i] >= 0) {
                         // rotation: one fork with the gate's angle advanced by pi: (cos, sin)(theta/2 + pi/2) = (-sin, cos)(theta/2)
                         if (sg == 0) compose_matrix(s_mats[par_mat[i]], s_mat_gates, s_gates, trig, g, make_double2(-trig[g].y, trig[g].x), altm + 4 * lig);
-                    } else {
+                    } else if (!JAC) {
                         double sn, cs;
                         sincos(0.5 * gate_angle(s_gates[g], Pm[(size_t)(1 + 2 * i + sg) * P + i], x, acx), &sn, &cs);
                         altm[4 * lig] = make_double2(cs, sn);
@@ -812,7 +815,18 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc_kernel(
                     const SvAlt alt = SvAlt{par_mat[i], rot ? -1 : par_gate[i], altm + 4 * t};
                     sv_run_passes<Q>(scr, s_passes, ip, n_passes, s_ops, u2, trig, lig, alt, 0);
                     if (!rot) {
-                        sv_emit<Q, WANT_STATES>(scr, lig, live, out, (long long)(1 + 2 * i + sg) * n + j, red);
+                        if (!JAC) sv_emit<Q, WANT_STATES>(scr, lig, live, out, (long long)(1 + 2 * i + sg) * n + j, red);
+                    } else if (JAC) {
+                        // d<O>/dtheta = Re<psi|O|phi>;  dtheta/dp = 1 (p, p + c x) or arccos(x) (p arccos x)
+                        const dqgp_gate gt = s_gates[par_gate[i]];
+                        const double dth = (gt.form == DQGP_A_P_TIMES_ACOS) ? acx[gt.fidx] : 1.0;
+#pragma unroll 1
+                        for (int b = 0; b < FULL; ++b) features_cross_block<(Q >= 3 ? 3 : 1), Q>(fin, scr, 3 * b, lig, T::SIZE, featC, red);
+                        if (REM == 2) features_cross_block<(Q >= 2 ? 2 : 1), Q>(fin, scr, 3 * FULL, lig, T::SIZE, featC, red);
+                        if (REM == 1) features_cross_block<1, Q>(fin, scr, 3 * FULL, lig, T::SIZE, featC, red);
+                        T::sync();
+                        if (live)
+                            for (int k = lig; k < M3; k += T::SIZE) jac[((size_t)i * n + j) * M3 + k] = dth * featC[k];
                     } else {
                         const dqgp_gate gt = s_gates[par_gate[i]];
                         const double th0 = gate_angle(gt, Pm[i], x, acx);
@@ -884,17 +898,27 @@ static int launch_sv_shared(const dqgp_circuit* c, const double* X, int n, const
     while (!T::BLOCK && warps > 1 && fixed + team_bytes * teams > 100 * 1024) { warps >>= 1; teams = warps * T::PER_WARP; }
     const size_t smem = fixed + team_bytes * teams;
     DQGP_REQUIRE(smem <= 227 * 1024, "statevector kernel needs %zu bytes of shared memory (q=%d, %d gates)", smem, Q, n_gates);
-    auto kern = use_lc ? statevec_lc_kernel<Q, WANT_STATES> : statevec_shared_kernel<Q, WANT_STATES>;
-    DQGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto lc_kern = statevec_lc_kernel<Q, WANT_STATES, false>;
+    auto fork_kern = statevec_shared_kernel<Q, WANT_STATES>;
     int per_sm = 0;
-    DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (use_lc) {
+        DQGP_CUDA(cudaFuncSetAttribute(lc_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lc_kern, warps * 32, smem));
+    } else {
+        DQGP_CUDA(cudaFuncSetAttribute(fork_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fork_kern, warps * 32, smem));
+    }
     if (per_sm < 1) per_sm = 1;
     long long blocks = ((long long)n + teams - 1) / teams;
     const long long cap = (long long)sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) return 0;
-    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d_passes, n_passes, c->d_ops, c->d_mats, n_mats, c->d_mat_gates,
-                                                     n_mat_gates, c->d_share, c->d, c->P, c->uses_acos ? 1 : 0, X, n, Pm, out);
+    if (use_lc)
+        lc_kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d_passes, n_passes, c->d_ops, c->d_mats, n_mats, c->d_mat_gates,
+                                                            n_mat_gates, c->d_share, c->d, c->P, c->uses_acos ? 1 : 0, X, n, Pm, out, nullptr);
+    else
+        fork_kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d_passes, n_passes, c->d_ops, c->d_mats, n_mats,
+                                                              c->d_mat_gates, n_mat_gates, c->d_share, c->d, c->P, c->uses_acos ? 1 : 0, X, n, Pm, out);
     DQGP_LAUNCH_CHECK("statevec_shared_kernel");
     return 0;
 }
@@ -955,6 +979,37 @@ static int launch_sv(const dqgp_circuit* c, const double* X, int n, const double
     return 0;
 }
 
+template <int Q>
+static int launch_sv_jac(const dqgp_circuit* c, const double* X, int n, const double* p, double* F, double* J, cudaStream_t st) {
+    using T = SvTeam<Q>;
+    const int n_gates = (int)c->gates.size(), n_passes = (int)c->passes.size();
+    const int n_mats = (int)c->mats.size(), n_mat_gates = (int)c->mat_gates.size();
+    const int n_share = 2 * c->P + n_passes + 1 + c->P;
+    const size_t fixed = ((sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvPass) * n_passes + 15) & ~size_t(15)) +
+                         ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvMat) * n_mats + sizeof(int) * n_mat_gates + 15) & ~size_t(15)) +
+                         ((sizeof(int) * n_share + 15) & ~size_t(15));
+    const size_t team_bytes = sizeof(double2) * (3 * T::DIM + n_gates + 4 * n_mats + 4 * T::SLOTS) +
+                              sizeof(double) * (((c->d + 1) & ~1) + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0) + 3 * ((3 * Q + 1) & ~1));
+    int warps = T::BLOCK ? T::SIZE / 32 : 4;
+    int teams = T::BLOCK ? 1 : warps * T::PER_WARP;
+    while (!T::BLOCK && warps > 1 && fixed + team_bytes * teams > 100 * 1024) { warps >>= 1; teams = warps * T::PER_WARP; }
+    const size_t smem = fixed + team_bytes * teams;
+    DQGP_REQUIRE(smem <= 227 * 1024, "statevector kernel needs %zu bytes of shared memory (q=%d, %d gates)", smem, Q, n_gates);
+    auto kern = statevec_lc_kernel<Q, false, true>;
+    DQGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = ((long long)n + teams - 1) / teams;
+    const long long cap = (long long)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) return 0;
+    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d_passes, n_passes, c->d_ops, c->d_mats, n_mats, c->d_mat_gates,
+                                                     n_mat_gates, c->d_share, c->d, c->P, c->uses_acos ? 1 : 0, X, n, p, F, J);
+    DQGP_LAUNCH_CHECK("statevec_lc_kernel (jacobian)");
+    return 0;
+}
+
 template <bool WANT_STATES>
 static int dispatch_sv(const dqgp_circuit* c, const double* X, int n, const double* Pm, int S, double* out, void* stream) {
     DQGP_REQUIRE(n >= 0 && S >= 0, "statevector: negative size");
@@ -1004,6 +1059,27 @@ static int dispatch_sv_shared(const dqgp_circuit* c, const double* X, int n, con
 }  // namespace dqgp
 
 extern "C" {
+int dqgp_features_jacobian(const dqgp_circuit* c, const double* d_X, int n, const double* d_p, double* d_F, double* d_J, void* stream) {
+    using namespace dqgp;
+    DQGP_REQUIRE(n >= 0, "dqgp_features_jacobian: negative size");
+    if (n == 0) return 0;
+    DQGP_REQUIRE(c && d_X && d_p && d_F && d_J, "dqgp_features_jacobian: NULL argument");
+    DQGP_REQUIRE(c->shareable, "dqgp_features_jacobian: a parameter of this circuit feeds several gates");
+    for (int i = 0; i < c->P; ++i)
+        DQGP_REQUIRE(c->par_mat[i] >= 0, "dqgp_features_jacobian: parameter %d sits on a CRZ gate (two-frequency dependence); only circuits whose "
+                     "parameters enter through RX/RY/RZ are supported (yz_cx, kyriienko)", i);
+    int rc = circuit_on_device(c);
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    switch (c->q) {
+#define DQGP_SV_CASE(QQ) case QQ: return launch_sv_jac<QQ>(c, d_X, n, d_p, d_F, d_J, st);
+        DQGP_SV_CASE(1) DQGP_SV_CASE(2) DQGP_SV_CASE(3) DQGP_SV_CASE(4) DQGP_SV_CASE(5) DQGP_SV_CASE(6)
+        DQGP_SV_CASE(7) DQGP_SV_CASE(8) DQGP_SV_CASE(9) DQGP_SV_CASE(10) DQGP_SV_CASE(11) DQGP_SV_CASE(12)
+#undef DQGP_SV_CASE
+    }
+    set_error("statevector: unsupported qubit count %d", c->q);
+    return -1;
+}
 int dqgp_features_shifted(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int P, double* d_F, void* stream) {
     return dqgp::dispatch_sv_shared<false>(c, d_X, n, d_Pm, P, d_F, stream);
 }

@@ -70,7 +70,13 @@ class Solver:
 
 class AgentEngine:
     def __init__(self, X, Y, *, encoding_type, kernel_type, num_qubits, num_layers, noise_std, rho, L,
-                 outer_kernel="gaussian", shift_value=np.pi / 8, training_ignores_outer_kernel=True, cholesky_outer_blocks=0):
+                 outer_kernel="gaussian", shift_value=np.pi / 8, training_ignores_outer_kernel=True, cholesky_outer_blocks=0,
+                 gradient="central_difference"):
+        """``gradient``: "central_difference" = the reference's rule (dK_i = (K(p + h e_i) - K(p - h e_i)) / 2h, h = pi/8,
+        agent_riemannian.py:275) - the parity path; "analytic" (opt-in) = the exact derivative of the NLL:
+        feature Jacobian from one extra suffix simulation per parameter and ONE pass over the n^2 Gram entries.  The analytic
+        mode does NOT reproduce the reference's trajectories (its h = pi/8 difference is far from the derivative); it needs the
+        projected kernel with the Gaussian outer kernel and a circuit whose parameters all enter through RX/RY/RZ."""
         _require_cuda()
         self._lib = _lib.load()
         X = np.asarray(X, dtype=np.float64)
@@ -93,8 +99,18 @@ class AgentEngine:
         dev = self.d_X.device
         f64 = dict(dtype=torch.float64, device=dev)
         self.m = 3 * self.q if kernel_type == "projected" else 2 * (1 << self.q)   # doubles per sample per set
+        if gradient not in ("central_difference", "analytic"):
+            raise ValueError(f"Unknown gradient mode: {gradient}")
+        self.gradient_mode = gradient
+        if gradient == "analytic" and (kernel_type != "projected" or self.outer_kernel != "gaussian"):
+            raise ValueError("gradient='analytic' needs the projected kernel with the Gaussian outer kernel")
         self.d_Pm = torch.empty((self.S, self.P), **f64)
-        self.d_feat = torch.empty((self.S, self.n, self.m), **f64)
+        if gradient == "analytic":
+            self.d_feat = torch.empty((1, self.n, self.m), **f64)
+            self.d_jac = torch.empty((self.P, self.n, self.m), **f64)
+            self.d_work_a = torch.empty(max(1, self._lib.dqgp_grad_analytic_workspace_bytes(self.n, self.m) // 8), **f64)
+        else:
+            self.d_feat = torch.empty((self.S, self.n, self.m), **f64)
         self.cholesky_outer_blocks = int(cholesky_outer_blocks)
         self.solver = Solver(self.n, cholesky_outer_blocks)
         self.d_alpha = torch.empty(self.n, **f64)
@@ -120,6 +136,10 @@ class AgentEngine:
         if first == 0:
             check(lib.dqgp_shift_parameter_sets(d_z.data_ptr(), self.P, self.h, PERIOD, self.d_Pm.data_ptr(), st), "shift sets")
         count = self.S - first if count is None else count
+        if self.gradient_mode == "analytic":
+            check(lib.dqgp_features_jacobian(self.circuit.handle, self.d_X.data_ptr(), self.n, self.d_Pm.data_ptr(), self.d_feat.data_ptr(),
+                                             self.d_jac.data_ptr(), st), "feature jacobian")
+            return
         if first == 0 and count == self.S and self.share_prefix:
             # all 2P+1 central-difference sets of a sample share the circuit prefix before the shifted gate
             fn = lib.dqgp_features_shifted if self.kernel_type == "projected" else lib.dqgp_states_shifted
@@ -141,12 +161,18 @@ class AgentEngine:
         check(lib.dqgp_add_diagonal(s.matrix_ptr, self.n, s.ld, self.noise_std ** 2, st), "add diagonal")
 
     def factor(self):
+        # the fused central-difference gradient reads the lower tiles of A^-1; the analytic one its full symmetric image
         check(self._lib.dqgp_potrf_solve_inv(self.solver.handle, self.d_Y.data_ptr(), self.d_alpha.data_ptr(),
-                                             self.d_logdet.data_ptr(), self.d_info.data_ptr(), 1, stream_ptr()), "potrf")
+                                             self.d_logdet.data_ptr(), self.d_info.data_ptr(), 2 if self.gradient_mode == "analytic" else 1,
+                                             stream_ptr()), "potrf")
 
     def gradient(self):
         lib, st, s = self._lib, stream_ptr(), self.solver
-        if self.kernel_type == "projected":
+        if self.gradient_mode == "analytic":
+            check(lib.dqgp_grad_projected_analytic(self._outer_id, self._hyp, s.inverse_ptr, s.ld, self.d_alpha.data_ptr(), self.d_feat.data_ptr(),
+                                                   self.d_jac.data_ptr(), self.n, self.m, self.P, self.d_grad.data_ptr(),
+                                                   self.d_work_a.data_ptr(), st), "grad analytic")
+        elif self.kernel_type == "projected":
             check(lib.dqgp_grad_projected(self._outer_id, self._hyp, s.inverse_ptr, s.ld, self.d_alpha.data_ptr(),
                                           self.d_feat.data_ptr(), self.n, self.m, self.P, self.h, self.d_grad.data_ptr(),
                                           self.d_work.data_ptr(), st), "grad projected")

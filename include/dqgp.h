@@ -152,6 +152,18 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
 int dqgp_grad_fidelity(const double* d_Ainv, int ld, const double* d_alpha, const double* d_Psi, int n, int dim, int P,
                        double h, double* d_grad, void* d_work, void* stream);
 
+/* ---- analytic gradient (OPT-IN, SURVEY 8(f) row 3: the true derivative, not the reference's central difference with
+ *      h = pi/8 - trajectories differ from the reference's; replaces the dead evaluate_derivatives branch,
+ *      agent_riemannian.py:402-404).  dqgp_features_jacobian: d_F (n,3q) features at d_p (P) and d_J (P,n,3q) their exact
+ *      derivatives, one extra suffix simulation per parameter (circuits whose parameters all enter through RX/RY/RZ).
+ *      dqgp_grad_projected_analytic: Gaussian outer kernel, d_Ainv the FULL symmetric A^-1 (want_inverse = 2), one pass
+ *      over the n^2 entries (one exp per entry instead of 2P).  d_work: dqgp_grad_analytic_workspace_bytes(n, m). */
+int dqgp_features_jacobian(const dqgp_circuit* c, const double* d_X, int n, const double* d_p, double* d_F, double* d_J, void* stream);
+size_t dqgp_grad_analytic_workspace_bytes(int n, int m);
+int dqgp_grad_projected_analytic(int outer, const double* h_hyp, const double* d_Ainv, int ld, const double* d_alpha,
+                                 const double* d_F, const double* d_J, int n, int m, int P, double* d_grad, void* d_work,
+                                 void* stream);
+
 /* ---- NLL terms (agent_riemannian.py:441-452): d_out[4] = {1/2 logdet, 1/2 y^T alpha, n/2 log 2pi, total} */
 int dqgp_nll_terms(const double* d_logdet, const double* d_y, const double* d_alpha, int n, double* d_out, void* stream);
 

@@ -366,3 +366,38 @@ def test_full_size_properties_config4_shard(d):
         dK = (gram(1 + 2 * i) - gram(2 + 2 * i)) / (2 * eng.h)
         ref = 0.5 * (B * dK).sum().item()
         assert abs(g1[i].item() - ref) < 1e-6 * max(1.0, abs(ref))
+
+
+@pytest.mark.parametrize("enc,q,dd,layers,n", [("yz_cx", 4, 2, 2, 150), ("kyriienko", 3, 2, 1, 200)])
+def test_analytic_gradient_is_the_derivative_of_the_oracle_nll(d, enc, q, dd, layers, n):
+    """AgentEngine(gradient="analytic") (opt-in): the gradient equals the derivative of the NLL computed by
+    the ORACLE (NumPy kernel + LAPACK), by central differences of the NLL itself; and the reference's h = pi/8 rule, which the
+    default mode reproduces, is visibly a different number."""
+    from oracle import qkernels
+    x, y = d.synthetic_dataset(n, dd, enc)
+    z = np.round(np.random.RandomState(5).uniform(0.2, 2.9, d.EncodingCircuit(enc, q, dd, layers).num_parameters), 4)
+    grads = {}
+    for mode in ("analytic", "central_difference"):
+        eng = d.AgentEngine(x, y, encoding_type=enc, kernel_type="projected", num_qubits=q, num_layers=layers, noise_std=0.1, rho=100.0,
+                            L=100.0, gradient=mode)
+        dz = d.kernels.dev_f64(z)
+        eng.simulate(dz); eng.gram(); eng.factor(); eng.gradient()
+        torch.cuda.synchronize(); eng.check_info()
+        grads[mode] = eng.d_grad.cpu().numpy().copy()
+        nll_gpu = float(eng.d_nll[3].item())
+
+    def nll(p):
+        qk = qkernels.create_quantum_kernel(q, dd, layers, enc, "projected", "XYZ", "gaussian")
+        qk.assign_parameters(p)
+        a = qk.evaluate(x, x) + 0.01 * np.eye(n)
+        L = np.linalg.cholesky(a)
+        al = np.linalg.solve(a, y)
+        return np.log(np.diag(L)).sum() + 0.5 * y @ al + 0.5 * n * np.log(2 * np.pi)
+
+    assert abs(nll(z) - nll_gpu) < 1e-8 * abs(nll_gpu)
+    h = 1e-5
+    for i in range(0, len(z), max(1, len(z) // 5)):
+        e = np.zeros_like(z); e[i] = h
+        ref = (nll(z + e) - nll(z - e)) / (2 * h)
+        assert abs(grads["analytic"][i] - ref) < 2e-5 * max(1.0, abs(ref)), (i, grads["analytic"][i], ref)
+    assert np.max(np.abs(grads["analytic"] - grads["central_difference"])) > 1e-3 * np.max(np.abs(grads["analytic"]))
