@@ -18,10 +18,11 @@ from .predict import k_fold_cross_validation_consensus
 def run_admm(shards, *, encoding_type, kernel_type, num_qubits, num_layers, noise_std=0.1, rho=100.0, L=100.0,
              outer_kernel="gaussian", shift_value=np.pi / 8, max_iter=100, tolerance=1e-6, theta0=None, psi0=None,
              n_agents_total=None, cv_data=None, cv_folds=5, cv_patience=50, seed=42, training_ignores_outer_kernel=True,
-             process_group=None, rank=0, world_size=1, callback=None):
+             process_group=None, rank=0, world_size=1, callback=None, gradient="central_difference"):
     """Returns a dict: z (final consensus; the best-CV z on early stop / max_iter as in the reference), iterations,
     history (per iteration: z, theta, psi, nll per local agent, cv), stop_reason.
-    ``cv_data=(X_train, Y_train)`` enables the per-iteration CV of main.py:2650 (seed + iteration as fold seed)."""
+    ``cv_data=(X_train, Y_train)`` enables the per-iteration CV of main.py:2650 (seed + iteration as fold seed).
+    ``gradient="analytic"`` switches the agents to the exact NLL derivative (opt-in, not the reference's trajectories)."""
     import torch
 
     A = n_agents_total if n_agents_total is not None else len(shards) * world_size
@@ -35,7 +36,8 @@ def run_admm(shards, *, encoding_type, kernel_type, num_qubits, num_layers, nois
     eng = AdmmEngine(shards, np.asarray(theta0, dtype=np.float64), np.asarray(psi0, dtype=np.float64), rho=rho, L=L,
                      process_group=process_group, rank=rank, world_size=world_size, encoding_type=encoding_type,
                      kernel_type=kernel_type, num_qubits=num_qubits, num_layers=num_layers, noise_std=noise_std,
-                     outer_kernel=outer_kernel, shift_value=shift_value, training_ignores_outer_kernel=training_ignores_outer_kernel)
+                     outer_kernel=outer_kernel, shift_value=shift_value, training_ignores_outer_kernel=training_ignores_outer_kernel,
+                     gradient=gradient)
     history, z_best_cv, cv_best, patience = [], None, float("inf"), 0
     it, reason = 0, "max_iter"
     while True:
