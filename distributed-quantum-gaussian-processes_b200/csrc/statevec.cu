@@ -1042,7 +1042,7 @@ static int dispatch_sv_shared(const dqgp_circuit* c, const double* X, int n, con
     const long long teams = c->q >= 9 ? n : (long long)n * (c->q > 3 ? (1 << (c->q - 3)) : 1) / 32;
     // DQGP_SV_FORCE_SHARED: tests exercise the sharing kernels at small n
     if (!c->shareable || (teams < (c->q >= 9 ? 600 : 1200) && getenv("DQGP_SV_FORCE_SHARED") == nullptr))
-        return dispatch_sv<WANT_STATES>(c, X, n, Pm, 2 * P + 1, out, stream);
+        return WANT_STATES ? dqgp_states(c, X, n, Pm, 2 * P + 1, out, stream) : dqgp_features(c, X, n, Pm, 2 * P + 1, out, stream);
     int rc = circuit_on_device(c);
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
@@ -1058,7 +1058,13 @@ static int dispatch_sv_shared(const dqgp_circuit* c, const double* X, int n, con
 
 }  // namespace dqgp
 
+// This file is compiled five times (build.py: -DDQGP_SV_PART=1..5), one group of entry points per object, so the twelve qubit
+// counts x kernel variants compile in parallel (one translation unit took 2.6 minutes).
+#ifndef DQGP_SV_PART
+#define DQGP_SV_PART 0      // 0 = everything in one object
+#endif
 extern "C" {
+#if DQGP_SV_PART == 0 || DQGP_SV_PART == 5
 int dqgp_features_jacobian(const dqgp_circuit* c, const double* d_X, int n, const double* d_p, double* d_F, double* d_J, void* stream) {
     using namespace dqgp;
     DQGP_REQUIRE(n >= 0, "dqgp_features_jacobian: negative size");
@@ -1080,16 +1086,25 @@ int dqgp_features_jacobian(const dqgp_circuit* c, const double* d_X, int n, cons
     set_error("statevector: unsupported qubit count %d", c->q);
     return -1;
 }
+#endif
+#if DQGP_SV_PART == 0 || DQGP_SV_PART == 3
 int dqgp_features_shifted(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int P, double* d_F, void* stream) {
     return dqgp::dispatch_sv_shared<false>(c, d_X, n, d_Pm, P, d_F, stream);
 }
+#endif
+#if DQGP_SV_PART == 0 || DQGP_SV_PART == 4
 int dqgp_states_shifted(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int P, double* d_Psi, void* stream) {
     return dqgp::dispatch_sv_shared<true>(c, d_X, n, d_Pm, P, d_Psi, stream);
 }
+#endif
+#if DQGP_SV_PART == 0 || DQGP_SV_PART == 1
 int dqgp_features(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int S, double* d_F, void* stream) {
     return dqgp::dispatch_sv<false>(c, d_X, n, d_Pm, S, d_F, stream);
 }
+#endif
+#if DQGP_SV_PART == 0 || DQGP_SV_PART == 2
 int dqgp_states(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int S, double* d_Psi, void* stream) {
     return dqgp::dispatch_sv<true>(c, d_X, n, d_Pm, S, d_Psi, stream);
 }
+#endif
 }
