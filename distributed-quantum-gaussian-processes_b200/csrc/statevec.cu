@@ -59,7 +59,7 @@ __device__ __forceinline__ void apply_u2(double2 (&r)[N], const double2 u00, con
 }
 // CX (swap) / CRZ (phases e^{-+ i theta/2}) on the pairs whose control bit is set
 template <int N, int L>
-__device__ __forceinline__ void apply_controlled(double2 (&r)[N], int kind, int cloc, bool ext, double c, double s) {
+__device__ __forceinline__ void apply_controlled(double2 (&r)[N], int kind, int cloc, bool ext, double c, double s, bool zero_off = false) {
     constexpr int BIT = 1 << L;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
@@ -74,8 +74,9 @@ __device__ __forceinline__ void apply_controlled(double2 (&r)[N], int kind, int 
             na = make_double2(fma(c, a.x, s * a.y), fma(c, a.y, -s * a.x));
             nb = make_double2(fma(c, b.x, -s * b.y), fma(c, b.y, s * b.x));
         }
-        r[j] = on ? na : a;
-        r[j | BIT] = on ? nb : b;
+        const double2 zero = make_double2(0.0, 0.0);
+        r[j] = on ? na : (zero_off ? zero : a);
+        r[j | BIT] = on ? nb : (zero_off ? zero : b);
     }
 }
 
@@ -84,6 +85,7 @@ struct SvAlt {
     int mat;            // fused-matrix index replaced by u[0..3], or -1
     int gate;           // CRZ gate index whose (cos, sin) is u[0], or -1
     const double2* u;
+    int zero_off;       // that CRZ also ZEROES the amplitudes whose control bit is clear (derivative fork: dCRZ/dtheta = P1 x RZ(theta+pi)/2)
 };
 
 template <int N, int L>
@@ -94,15 +96,16 @@ __device__ __forceinline__ void apply_op(double2 (&r)[N], const SvOp op, int bas
         apply_u2<N, L>(r, u[0], u[1], u[2], u[3]);
     } else {
         const bool ext = (op.cq >= 0) ? (((base >> op.cq) & 1) != 0) : false;
-        const double2 cs = (op.kind == SV_CRZ) ? ((op.idx == alt.gate) ? alt.u[0] : trig[op.idx]) : make_double2(1.0, 0.0);
-        apply_controlled<N, L>(r, op.kind, op.cloc, ext, cs.x, cs.y);
+        const bool is_alt = op.kind == SV_CRZ && op.idx == alt.gate;
+        const double2 cs = (op.kind == SV_CRZ) ? (is_alt ? alt.u[0] : trig[op.idx]) : make_double2(1.0, 0.0);
+        apply_controlled<N, L>(r, op.kind, op.cloc, ext, cs.x, cs.y, is_alt && alt.zero_off != 0);
     }
 }
 
 template <int B>
 __device__ __forceinline__ void run_pass(double2* __restrict__ amp, const SvPass& ps, const SvOp* __restrict__ ops,
                                          const double2* __restrict__ mats, const double2* __restrict__ trig, int lig, int lps,
-                                         int groups, const SvAlt alt = SvAlt{-1, -1, nullptr}) {
+                                         int groups, const SvAlt alt = SvAlt{-1, -1, nullptr, 0}) {
     constexpr int N = 1 << B;
     const int q0 = ps.q[0], q1 = ps.q[1], q2 = ps.q[2];
     int off[N];
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_shared_kernel(
     double2* altm = u2 + 4 * n_mats;
     double* acx = reinterpret_cast<double*>(altm + 4 * T::SLOTS);
     double* red = acx + ((d + 1) & ~1);
-    const SvAlt no_alt = SvAlt{-1, -1, nullptr};
+    const SvAlt no_alt = SvAlt{-1, -1, nullptr, 0};
 
     // lane-group teams of one warp must iterate together (the plan is identical, only the data differ)
     const long long n_rounds = (n + (long long)gridDim.x * teams_per_block - 1) / ((long long)gridDim.x * teams_per_block);
@@ -673,7 +676,7 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_shared_kernel(
                     const int fk = f0 + t, i = pass_params[fk >> 1], sg = fk & 1;
                     for (int a = lig; a < T::DIM; a += T::SIZE) scr[a] = base[a];
                     T::sync();
-                    const SvAlt alt = SvAlt{par_mat[i], par_mat[i] >= 0 ? -1 : par_gate[i], altm + 4 * t};
+                    const SvAlt alt = SvAlt{par_mat[i], par_mat[i] >= 0 ? -1 : par_gate[i], altm + 4 * t, 0};
                     sv_run_passes<Q>(scr, s_passes, ip, n_passes, s_ops, u2, trig, lig, alt, 0);
                     sv_emit<Q, WANT_STATES>(scr, lig, live, out, (long long)(1 + 2 * i + sg) * n + j, red);
                     T::sync();
@@ -748,7 +751,7 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc_kernel(
     double* featA = red + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0);
     double* featB = featA + M3P;
     double* featC = featB + M3P;
-    const SvAlt no_alt = SvAlt{-1, -1, nullptr};
+    const SvAlt no_alt = SvAlt{-1, -1, nullptr, 0};
     constexpr int FULL = Q / 3, REM = Q % 3;
 
     const long long n_rounds = (n + (long long)gridDim.x * teams_per_block - 1) / ((long long)gridDim.x * teams_per_block);
@@ -803,21 +806,24 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc_kernel(
                         double sn, cs;
                         sincos(0.5 * gate_angle(s_gates[g], Pm[(size_t)(1 + 2 * i + sg) * P + i], x, acx), &sn, &cs);
                         altm[4 * lig] = make_double2(cs, sn);
+                    } else if (sg == 0) {
+                        altm[4 * lig] = make_double2(-trig[g].y, trig[g].x);     // CRZ derivative fork: RZ(theta + pi) on the control-on pairs
                     }
                 }
                 T::sync();
                 for (int t = 0; t < cnt; ++t) {
                     const int fk = f0 + t, i = pass_params[fk >> 1], sg = fk & 1;
                     const bool rot = par_mat[i] >= 0;
-                    if (rot && sg == 1) continue;                 // both signs come out of the sg = 0 fork
+                    if ((rot || JAC) && sg == 1) continue;        // both signs (or the derivative) come out of the sg = 0 fork
                     for (int a = lig; a < T::DIM; a += T::SIZE) scr[a] = base[a];
                     T::sync();
-                    const SvAlt alt = SvAlt{par_mat[i], rot ? -1 : par_gate[i], altm + 4 * t};
+                    const SvAlt alt = SvAlt{par_mat[i], rot ? -1 : par_gate[i], altm + 4 * t, (JAC && !rot) ? 1 : 0};
                     sv_run_passes<Q>(scr, s_passes, ip, n_passes, s_ops, u2, trig, lig, alt, 0);
-                    if (!rot) {
-                        if (!JAC) sv_emit<Q, WANT_STATES>(scr, lig, live, out, (long long)(1 + 2 * i + sg) * n + j, red);
+                    if (!rot && !JAC) {
+                        sv_emit<Q, WANT_STATES>(scr, lig, live, out, (long long)(1 + 2 * i + sg) * n + j, red);
                     } else if (JAC) {
-                        // d<O>/dtheta = Re<psi|O|phi>;  dtheta/dp = 1 (p, p + c x) or arccos(x) (p arccos x)
+                        // d<O>/dtheta = Re<psi|O|phi> (phi: the gate's angle advanced by pi; for a CRZ also projected on control = 1);
+                        // dtheta/dp = 1 (p, p + c x) or arccos(x) (p arccos x)
                         const dqgp_gate gt = s_gates[par_gate[i]];
                         const double dth = (gt.form == DQGP_A_P_TIMES_ACOS) ? acx[gt.fidx] : 1.0;
 #pragma unroll 1
@@ -1071,9 +1077,6 @@ int dqgp_features_jacobian(const dqgp_circuit* c, const double* d_X, int n, cons
     if (n == 0) return 0;
     DQGP_REQUIRE(c && d_X && d_p && d_F && d_J, "dqgp_features_jacobian: NULL argument");
     DQGP_REQUIRE(c->shareable, "dqgp_features_jacobian: a parameter of this circuit feeds several gates");
-    for (int i = 0; i < c->P; ++i)
-        DQGP_REQUIRE(c->par_mat[i] >= 0, "dqgp_features_jacobian: parameter %d sits on a CRZ gate (two-frequency dependence); only circuits whose "
-                     "parameters enter through RX/RY/RZ are supported (yz_cx, kyriienko)", i);
     int rc = circuit_on_device(c);
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);

@@ -76,7 +76,7 @@ class AgentEngine:
         agent_riemannian.py:275) - the parity path; "analytic" (opt-in) = the exact derivative of the NLL:
         feature Jacobian from one extra suffix simulation per parameter and ONE pass over the n^2 Gram entries.  The analytic
         mode does NOT reproduce the reference's trajectories (its h = pi/8 difference is far from the derivative); it needs the
-        projected kernel with the Gaussian outer kernel and a circuit whose parameters all enter through RX/RY/RZ."""
+        projected kernel with the Gaussian outer kernel."""
         _require_cuda()
         self._lib = _lib.load()
         X = np.asarray(X, dtype=np.float64)

@@ -155,7 +155,7 @@ int dqgp_grad_fidelity(const double* d_Ainv, int ld, const double* d_alpha, cons
 /* ---- analytic gradient (OPT-IN, SURVEY 8(f) row 3: the true derivative, not the reference's central difference with
  *      h = pi/8 - trajectories differ from the reference's; replaces the dead evaluate_derivatives branch,
  *      agent_riemannian.py:402-404).  dqgp_features_jacobian: d_F (n,3q) features at d_p (P) and d_J (P,n,3q) their exact
- *      derivatives, one extra suffix simulation per parameter (circuits whose parameters all enter through RX/RY/RZ).
+ *      derivatives, one extra suffix simulation per parameter (every parameter must feed exactly one gate).
  *      dqgp_grad_projected_analytic: Gaussian outer kernel, d_Ainv the FULL symmetric A^-1 (want_inverse = 2), one pass
  *      over the n^2 entries (one exp per entry instead of 2P).  d_work: dqgp_grad_analytic_workspace_bytes(n, m). */
 int dqgp_features_jacobian(const dqgp_circuit* c, const double* d_X, int n, const double* d_p, double* d_F, double* d_J, void* stream);

@@ -368,7 +368,7 @@ def test_full_size_properties_config4_shard(d):
         assert abs(g1[i].item() - ref) < 1e-6 * max(1.0, abs(ref))
 
 
-@pytest.mark.parametrize("enc,q,dd,layers,n", [("yz_cx", 4, 2, 2, 150), ("kyriienko", 3, 2, 1, 200)])
+@pytest.mark.parametrize("enc,q,dd,layers,n", [("yz_cx", 4, 2, 2, 150), ("kyriienko", 3, 2, 1, 200), ("chebyshev", 3, 2, 1, 180)])
 def test_analytic_gradient_is_the_derivative_of_the_oracle_nll(d, enc, q, dd, layers, n):
     """AgentEngine(gradient="analytic") (opt-in): the gradient equals the derivative of the NLL computed by
     the ORACLE (NumPy kernel + LAPACK), by central differences of the NLL itself; and the reference's h = pi/8 rule, which the

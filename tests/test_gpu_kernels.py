@@ -320,13 +320,14 @@ def test_lean_solver_matches_full_solver(d, n, ob):
     assert np.array_equal(vf, vl)
 
 
-@pytest.mark.parametrize("enc,q,dd,layers", [("yz_cx", 4, 3, 2), ("kyriienko", 3, 2, 2), ("yz_cx", 9, 3, 1), ("yz_cx", 8, 4, 3)])
+@pytest.mark.parametrize("enc,q,dd,layers", [("yz_cx", 4, 3, 2), ("kyriienko", 3, 2, 2), ("yz_cx", 9, 3, 1), ("yz_cx", 8, 4, 3),
+                                            ("chebyshev", 4, 2, 3), ("hubregtsen", 5, 2, 2), ("chebyshev", 3, 2, 1), ("hubregtsen", 9, 3, 1)])
 def test_feature_jacobian_matches_finite_differences(d, enc, q, dd, layers):
     """dqgp_features_jacobian (exact derivative of every Pauli feature with respect to every circuit parameter, from the
     cross term Re<psi|O|phi> of the linear-combination simulator) against central differences of dqgp_features."""
     rng = np.random.default_rng(3 * q + dd)
     n = 37
-    lo, hi = (-0.99, 0.99) if enc == "kyriienko" else (-2, 2)
+    lo, hi = (-0.99, 0.99) if enc in ("kyriienko", "chebyshev") else (-2, 2)
     x = rng.uniform(lo, hi, (n, dd))
     ec = d.EncodingCircuit(enc, q, dd, layers)
     P = ec.num_parameters
@@ -347,11 +348,3 @@ def test_feature_jacobian_matches_finite_differences(d, enc, q, dd, layers):
     fd = (Fs[1::2] - Fs[2::2]) / (2 * h)
     assert (J - fd).abs().max().item() < 5e-9
     assert J.abs().max().item() > 1e-3
-
-
-def test_feature_jacobian_rejects_crz_parameters(d):
-    ec = d.EncodingCircuit("chebyshev", 3, 2, 1)
-    lib = d.load()
-    buf = torch.zeros(4096, dtype=torch.float64, device="cuda")
-    assert lib.dqgp_features_jacobian(ec.handle, buf.data_ptr(), 4, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), _sp()) < 0
-    assert b"CRZ" in lib.dqgp_last_error()
