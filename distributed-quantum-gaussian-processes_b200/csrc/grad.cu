@@ -125,7 +125,8 @@ __device__ __forceinline__ void g2_stage(double* buf, const double* __restrict__
     else if (threadIdx.x < 2 * PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(col0 + threadIdx.x - PW_TILE, n - 1)]);
 }
 
-template <int OUTER, int VEC>
+// CLAMP: guard the exponent against arguments below -700 (only reachable when gamma * 4m > 700; features lie in [-1, 1])
+template <int OUTER, int VEC, bool CLAMP = true>
 __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(const double* __restrict__ Ainv, int ld,
                                                                            const double* __restrict__ alpha,
                                                                            const double* __restrict__ F,
@@ -219,7 +220,12 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) part = fma(br[rb][cb][e], outer_from_neg_gd2<OUTER>(c[rb][cb][e], hyp, tab), part);
+                for (int e = 0; e < 2; ++e) {
+                    const double kv = (OUTER == DQGP_OUTER_GAUSSIAN)
+                                          ? fast_exp_tab5(CLAMP ? fmax(c[rb][cb][e], -700.0) : c[rb][cb][e], tab)
+                                          : outer_from_neg_gd2<OUTER>(c[rb][cb][e], hyp, tab);
+                    part = fma(br[rb][cb][e], kv, part);
+                }
         if (tt & 1) {
             pminus = part;
             double v = warp_sum(pplus - pminus);
@@ -439,17 +445,21 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
     } else {
         const long long rows = (long long)(2 * P + 1) * n;
         feature_norms_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d_F, rows, m, norms);
+        // Pauli features lie in [-1, 1]: gamma d^2 <= 4 m gamma, so the exponent guard is only needed for large gamma
+        const bool no_clamp = outer == DQGP_OUTER_GAUSSIAN && hyp.a > 0.0 && 4.0 * m * hyp.a < 650.0;
 #define DQGP_G2(OUT)                                                                                                         \
     do {                                                                                                                     \
         static bool attr_done = false;                                                                                       \
         if (!attr_done) {                                                                                                    \
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
+            DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             attr_done = true;                                                                                                \
         }                                                                                                                    \
-        if ((m & 1) == 0 && (reinterpret_cast<uintptr_t>(d_F) & 15) == 0)                                                    \
-            grad_projected_dmma_kernel<OUT, 2><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
-        else                                                                                                                 \
+        if ((m & 1) == 0 && (reinterpret_cast<uintptr_t>(d_F) & 15) == 0) {                                                  \
+            if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+            else grad_projected_dmma_kernel<OUT, 2><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+        } else                                                                                                               \
             grad_projected_dmma_kernel<OUT, 1><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
     } while (0)
         switch (outer) {
