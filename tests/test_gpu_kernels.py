@@ -348,3 +348,32 @@ def test_feature_jacobian_matches_finite_differences(d, enc, q, dd, layers):
     fd = (Fs[1::2] - Fs[2::2]) / (2 * h)
     assert (J - fd).abs().max().item() < 5e-9
     assert J.abs().max().item() > 1e-3
+
+
+@pytest.mark.parametrize("ob", [1, 2, 4, -1])
+def test_lookahead_cholesky_is_deterministic_at_full_size(d, ob):
+    """The three-stream look-ahead schedule orders every writer of a block with events: the factor of an 8192 x 8192 matrix
+    (config 4's shard size, 64 leaves) must be bit-identical run to run, for every outer-panel width, and a solve of it must
+    reproduce the right-hand side."""
+    from dqgp_b200.engine import Solver
+    lib = d.load()
+    n = 8192
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B = torch.randn((n, 96), dtype=torch.float64, device="cuda", generator=g)
+    A = B @ B.T / 96 + 0.05 * torch.eye(n, dtype=torch.float64, device="cuda")
+    y = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    s = Solver(n, ob)
+    alpha = torch.empty(n, dtype=torch.float64, device="cuda")
+    logdet = torch.zeros(1, dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = []
+    for rep in range(3):
+        s.matrix().copy_(A)
+        assert lib.dqgp_potrf_solve_inv(s.handle, y.data_ptr(), alpha.data_ptr(), logdet.data_ptr(), info.data_ptr(), 1, st) == 0
+        torch.cuda.synchronize()
+        assert info.item() == 0
+        outs.append((torch.tril(s.matrix()).clone(), torch.tril(s.inverse()).clone(), alpha.clone(), logdet.item()))
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2]) and o[3] == outs[0][3]
+    assert ((A @ outs[0][2] - y).abs().max() / y.abs().max()).item() < 1e-9
