@@ -895,10 +895,15 @@ static int launch_sv_shared(const dqgp_circuit* c, const double* X, int n, const
     const size_t fixed = ((sizeof(dqgp_gate) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvPass) * n_passes + 15) & ~size_t(15)) +
                          ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvMat) * n_mats + sizeof(int) * n_mat_gates + 15) & ~size_t(15)) +
                          ((sizeof(int) * n_share + 15) & ~size_t(15));
-    // linear-combination form (statevec_lc_kernel) unless DQGP_SV_NO_LC is set (A/B checks against the two-fork kernel)
-    const bool use_lc = getenv("DQGP_SV_NO_LC") == nullptr;
-    const size_t team_bytes = sizeof(double2) * ((use_lc ? 3 : 2) * T::DIM + n_gates + 4 * n_mats + 4 * T::SLOTS) +
-                              sizeof(double) * (((c->d + 1) & ~1) + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0) + (use_lc ? 3 * ((3 * Q + 1) & ~1) : 0));
+    // linear-combination form (statevec_lc_kernel) unless DQGP_SV_NO_LC is set (A/B checks against the two-fork kernel) or its
+    // third copy of the state does not fit in shared memory (q = 12 with a long gate list)
+    bool use_lc = getenv("DQGP_SV_NO_LC") == nullptr;
+    auto team_size = [&](bool lc) {
+        return sizeof(double2) * ((lc ? 3 : 2) * T::DIM + n_gates + 4 * n_mats + 4 * T::SLOTS) +
+               sizeof(double) * (((c->d + 1) & ~1) + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0) + (lc ? 3 * ((3 * Q + 1) & ~1) : 0));
+    };
+    if (use_lc && T::BLOCK && fixed + team_size(true) > 227 * 1024) use_lc = false;
+    const size_t team_bytes = team_size(use_lc);
     int warps = T::BLOCK ? T::SIZE / 32 : 4;
     int teams = T::BLOCK ? 1 : warps * T::PER_WARP;
     while (!T::BLOCK && warps > 1 && fixed + team_bytes * teams > 100 * 1024) { warps >>= 1; teams = warps * T::PER_WARP; }

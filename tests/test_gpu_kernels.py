@@ -52,7 +52,8 @@ def test_features_and_states_match_oracle(d, enc, q, dd, layers):
 
 
 @pytest.mark.parametrize("enc,q,dd,layers", [("chebyshev", 3, 2, 1), ("chebyshev", 4, 2, 3), ("hubregtsen", 5, 2, 2), ("yz_cx", 8, 4, 3),
-                                            ("yz_cx", 1, 1, 2), ("kyriienko", 10, 6, 2), ("hubregtsen", 9, 3, 1), ("yz_cx", 6, 3, 2)])
+                                            ("yz_cx", 1, 1, 2), ("kyriienko", 10, 6, 2), ("hubregtsen", 9, 3, 1), ("yz_cx", 6, 3, 2),
+                                            ("yz_cx", 12, 4, 1), ("kyriienko", 12, 6, 4)])
 def test_shared_prefix_simulation_matches_per_set_kernels(d, enc, q, dd, layers, monkeypatch):
     """dqgp_features_shifted / dqgp_states_shifted over the 2P+1 central-difference sets against the per-set kernels:
     the two-fork prefix-sharing kernel bit for bit; the linear-combination kernel (one fork per rotation parameter, both
@@ -60,7 +61,7 @@ def test_shared_prefix_simulation_matches_per_set_kernels(d, enc, q, dd, layers,
     (those keep two forks) and parameter sets whose +h / -h shifts wrap differently."""
     from oracle import agent_step, circuits
     rng = np.random.default_rng(7 * q + dd)
-    n = 45
+    n = 45 if q < 12 else 5
     lo, hi = (-0.99, 0.99) if enc in ("chebyshev", "kyriienko") else (-2, 2)
     x = rng.uniform(lo, hi, (n, dd))
     P = circuits.num_parameters(enc, q, layers)
