@@ -67,6 +67,9 @@ SIGNATURES = {
     "dqgp_grad_projected": (_i, [_i, _dp, _vp, _i, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp]),
     "dqgp_grad_fidelity": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp]),
     "dqgp_features_jacobian": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "dqgp_states_jacobian": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "dqgp_grad_fidelity_analytic_workspace_bytes": (_sz, [_i, _i]),
+    "dqgp_grad_fidelity_analytic": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "dqgp_grad_analytic_workspace_bytes": (_sz, [_i, _i]),
     "dqgp_grad_projected_analytic": (_i, [_i, _dp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "dqgp_nll_terms": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),

@@ -409,6 +409,61 @@ __global__ void __launch_bounds__(256) grad_analytic_contract_kernel(const doubl
     if (threadIdx.x == 0) grad[blockIdx.x] = scale * sred[0];
 }
 
+// Fidelity kernel, analytic gradient: K_jk = |s_jk|^2, s_jk = <psi_k|psi_j>, and with d_i psi_j from dqgp_states_jacobian
+//   grad_i = 1/2 sum_jk B_jk dK_jk/dp_i = 2 Re sum_j < G_j | d_i psi_j >,   G_j = sum_k B_jk s_jk psi_k.
+// Thread = row j of a column segment; psi_j and the running G_j live in shared memory (one column per thread, [a][thread]),
+// the segment's psi_k stream through shared memory 16 columns at a time.  DIM = 2^q <= 64.
+constexpr int GF_ROWS = 64, GF_CHUNK = 16;
+template <int DIM>
+__global__ void __launch_bounds__(GF_ROWS) grad_fid_analytic_rows_kernel(const double* __restrict__ Ainv, int ld, const double* __restrict__ alpha,
+                                                                        const double2* __restrict__ Psi, int n, int seg_cols,
+                                                                        double2* __restrict__ Gpart) {
+    extern __shared__ __align__(16) double2 gf_smem[];
+    double2* sp = gf_smem;                          // psi_j: [DIM][GF_ROWS]
+    double2* sg = sp + DIM * GF_ROWS;               // G_j:   [DIM][GF_ROWS]
+    double2* sc = sg + DIM * GF_ROWS;               // psi_k chunk: [GF_CHUNK][DIM]
+    __shared__ double ac[GF_CHUNK];
+    const int tid = threadIdx.x;
+    const int j = blockIdx.x * GF_ROWS + tid;
+    const bool live = j < n;
+    const int c_begin = blockIdx.y * seg_cols, c_end = min(n, c_begin + seg_cols);
+    for (int a = 0; a < DIM; ++a) {
+        sp[a * GF_ROWS + tid] = live ? Psi[(size_t)j * DIM + a] : make_double2(0.0, 0.0);
+        sg[a * GF_ROWS + tid] = make_double2(0.0, 0.0);
+    }
+    const double aj = live ? alpha[j] : 0.0;
+    for (int c0 = c_begin; c0 < c_end; c0 += GF_CHUNK) {
+        const int cnt = min(GF_CHUNK, c_end - c0);
+        __syncthreads();
+        for (int e = tid; e < cnt * DIM; e += GF_ROWS) sc[e] = Psi[(size_t)c0 * DIM + e];
+        if (tid < cnt) ac[tid] = alpha[c0 + tid];
+        __syncthreads();
+        if (!live) continue;
+        for (int cc = 0; cc < cnt; ++cc) {
+            const double2* pk = sc + cc * DIM;
+            double sr = 0.0, si = 0.0;              // s = sum_a conj(psi_k[a]) psi_j[a]
+            for (int a = 0; a < DIM; ++a) {
+                const double2 u = pk[a], v = sp[a * GF_ROWS + tid];
+                sr = fma(u.x, v.x, fma(u.y, v.y, sr));
+                si = fma(u.x, v.y, fma(-u.y, v.x, si));
+            }
+            const double b = Ainv[(size_t)(c0 + cc) * ld + j] - aj * ac[cc];
+            const double qr = b * sr, qi = b * si;
+            for (int a = 0; a < DIM; ++a) {
+                const double2 u = pk[a];
+                double2 g = sg[a * GF_ROWS + tid];
+                g.x = fma(qr, u.x, fma(-qi, u.y, g.x));
+                g.y = fma(qr, u.y, fma(qi, u.x, g.y));
+                sg[a * GF_ROWS + tid] = g;
+            }
+        }
+    }
+    if (live) {
+        double2* dst = Gpart + ((size_t)blockIdx.y * n + j) * DIM;
+        for (int a = 0; a < DIM; ++a) dst[a] = sg[a * GF_ROWS + tid];
+    }
+}
+
 static inline int grad_tiles(int n) {
     const int t = (n + PW_TILE - 1) / PW_TILE;
     return t * (t + 1) / 2;
@@ -504,6 +559,43 @@ int dqgp_grad_projected_analytic(int outer, const double* h_hyp, const double* d
     grad_analytic_sum_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(Gpart, count, segments, G);
     grad_analytic_contract_kernel<<<P, 256, 0, st>>>(d_J, G, count, -2.0 * hyp.a, d_grad);
     DQGP_LAUNCH_CHECK("grad_analytic kernels");
+    return 0;
+}
+
+size_t dqgp_grad_fidelity_analytic_workspace_bytes(int n, int dim) {
+    if (n <= 0 || dim <= 0) return 0;
+    return sizeof(double) * 2 * (size_t)(dqgp::GA_SEGMENTS + 1) * (size_t)n * (size_t)dim;
+}
+
+int dqgp_grad_fidelity_analytic(const double* d_Ainv, int ld, const double* d_alpha, const double* d_Psi, const double* d_D, int n, int dim,
+                                int P, double* d_grad, void* d_work, void* stream) {
+    using namespace dqgp;
+    DQGP_REQUIRE(d_Ainv && d_alpha && d_Psi && d_D && d_grad && d_work, "dqgp_grad_fidelity_analytic: NULL argument");
+    DQGP_REQUIRE(n >= 1 && ld >= n && P >= 1, "dqgp_grad_fidelity_analytic: bad shape");
+    DQGP_REQUIRE(dim >= 2 && dim <= 64 && (dim & (dim - 1)) == 0, "dqgp_grad_fidelity_analytic: 2^q amplitudes with q <= 6 (got %d)", dim);
+    cudaStream_t st = as_stream(stream);
+    double2* Gpart = static_cast<double2*>(d_work);
+    double2* G = Gpart + (size_t)GA_SEGMENTS * n * dim;
+    const int seg_cols = ((n + GA_SEGMENTS - 1) / GA_SEGMENTS + GF_CHUNK - 1) / GF_CHUNK * GF_CHUNK;
+    const int segments = (n + seg_cols - 1) / seg_cols;
+    dim3 grid((n + GF_ROWS - 1) / GF_ROWS, segments);
+    const size_t smem = sizeof(double2) * ((size_t)2 * dim * GF_ROWS + (size_t)GF_CHUNK * dim);
+    const double2* psi = reinterpret_cast<const double2*>(d_Psi);
+    switch (dim) {
+#define DQGP_GF(DD)                                                                                                            \
+    case DD:                                                                                                                   \
+        DQGP_CUDA(cudaFuncSetAttribute(grad_fid_analytic_rows_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        grad_fid_analytic_rows_kernel<DD><<<grid, GF_ROWS, smem, st>>>(d_Ainv, ld, d_alpha, psi, n, seg_cols, Gpart);          \
+        break;
+        DQGP_GF(2) DQGP_GF(4) DQGP_GF(8) DQGP_GF(16) DQGP_GF(32) DQGP_GF(64)
+#undef DQGP_GF
+    }
+    DQGP_LAUNCH_CHECK("grad_fid_analytic_rows_kernel");
+    const size_t count = (size_t)n * dim * 2;      // complex arrays as interleaved reals: Re<G|D> = sum of the real products
+    grad_analytic_sum_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(reinterpret_cast<const double*>(Gpart), count, segments,
+                                                                            reinterpret_cast<double*>(G));
+    grad_analytic_contract_kernel<<<P, 256, 0, st>>>(d_D, reinterpret_cast<const double*>(G), count, 2.0, d_grad);
+    DQGP_LAUNCH_CHECK("grad_fid_analytic kernels");
     return 0;
 }
 

@@ -826,13 +826,24 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc_kernel(
                         // dtheta/dp = 1 (p, p + c x) or arccos(x) (p arccos x)
                         const dqgp_gate gt = s_gates[par_gate[i]];
                         const double dth = (gt.form == DQGP_A_P_TIMES_ACOS) ? acx[gt.fidx] : 1.0;
+                        if (WANT_STATES) {
+                            // d psi / dp = (dtheta/dp) phi / 2
+                            if (live) {
+                                double2* dst = reinterpret_cast<double2*>(jac) + ((size_t)i * n + j) * T::DIM;
+                                for (int a = lig; a < T::DIM; a += T::SIZE) {
+                                    const double2 v = scr[sv_phys(a)];
+                                    dst[a] = make_double2(0.5 * dth * v.x, 0.5 * dth * v.y);
+                                }
+                            }
+                        } else {
 #pragma unroll 1
-                        for (int b = 0; b < FULL; ++b) features_cross_block<(Q >= 3 ? 3 : 1), Q>(fin, scr, 3 * b, lig, T::SIZE, featC, red);
-                        if (REM == 2) features_cross_block<(Q >= 2 ? 2 : 1), Q>(fin, scr, 3 * FULL, lig, T::SIZE, featC, red);
-                        if (REM == 1) features_cross_block<1, Q>(fin, scr, 3 * FULL, lig, T::SIZE, featC, red);
-                        T::sync();
-                        if (live)
-                            for (int k = lig; k < M3; k += T::SIZE) jac[((size_t)i * n + j) * M3 + k] = dth * featC[k];
+                            for (int b = 0; b < FULL; ++b) features_cross_block<(Q >= 3 ? 3 : 1), Q>(fin, scr, 3 * b, lig, T::SIZE, featC, red);
+                            if (REM == 2) features_cross_block<(Q >= 2 ? 2 : 1), Q>(fin, scr, 3 * FULL, lig, T::SIZE, featC, red);
+                            if (REM == 1) features_cross_block<1, Q>(fin, scr, 3 * FULL, lig, T::SIZE, featC, red);
+                            T::sync();
+                            if (live)
+                                for (int k = lig; k < M3; k += T::SIZE) jac[((size_t)i * n + j) * M3 + k] = dth * featC[k];
+                        }
                     } else {
                         const dqgp_gate gt = s_gates[par_gate[i]];
                         const double th0 = gate_angle(gt, Pm[i], x, acx);
@@ -990,7 +1001,7 @@ static int launch_sv(const dqgp_circuit* c, const double* X, int n, const double
     return 0;
 }
 
-template <int Q>
+template <int Q, bool WANT_STATES>
 static int launch_sv_jac(const dqgp_circuit* c, const double* X, int n, const double* p, double* F, double* J, cudaStream_t st) {
     using T = SvTeam<Q>;
     const int n_gates = (int)c->gates.size(), n_passes = (int)c->passes.size();
@@ -1006,7 +1017,7 @@ static int launch_sv_jac(const dqgp_circuit* c, const double* X, int n, const do
     while (!T::BLOCK && warps > 1 && fixed + team_bytes * teams > 100 * 1024) { warps >>= 1; teams = warps * T::PER_WARP; }
     const size_t smem = fixed + team_bytes * teams;
     DQGP_REQUIRE(smem <= 227 * 1024, "statevector kernel needs %zu bytes of shared memory (q=%d, %d gates)", smem, Q, n_gates);
-    auto kern = statevec_lc_kernel<Q, false, true>;
+    auto kern = statevec_lc_kernel<Q, WANT_STATES, true>;
     DQGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
@@ -1067,6 +1078,26 @@ static int dispatch_sv_shared(const dqgp_circuit* c, const double* X, int n, con
     return -1;
 }
 
+
+template <bool WANT_STATES>
+static int dispatch_sv_jac(const dqgp_circuit* c, const double* X, int n, const double* p, double* out, double* jac, void* stream) {
+    DQGP_REQUIRE(n >= 0, "jacobian: negative size");
+    if (n == 0) return 0;
+    DQGP_REQUIRE(c && X && p && out && jac, "jacobian: NULL argument");
+    DQGP_REQUIRE(c->shareable, "jacobian: a parameter of this circuit feeds several gates");
+    int rc = circuit_on_device(c);
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    switch (c->q) {
+#define DQGP_SV_CASE(QQ) case QQ: return launch_sv_jac<QQ, WANT_STATES>(c, X, n, p, out, jac, st);
+        DQGP_SV_CASE(1) DQGP_SV_CASE(2) DQGP_SV_CASE(3) DQGP_SV_CASE(4) DQGP_SV_CASE(5) DQGP_SV_CASE(6)
+        DQGP_SV_CASE(7) DQGP_SV_CASE(8) DQGP_SV_CASE(9) DQGP_SV_CASE(10) DQGP_SV_CASE(11) DQGP_SV_CASE(12)
+#undef DQGP_SV_CASE
+    }
+    set_error("statevector: unsupported qubit count %d", c->q);
+    return -1;
+}
+
 }  // namespace dqgp
 
 // This file is compiled five times (build.py: -DDQGP_SV_PART=1..5), one group of entry points per object, so the twelve qubit
@@ -1077,22 +1108,10 @@ static int dispatch_sv_shared(const dqgp_circuit* c, const double* X, int n, con
 extern "C" {
 #if DQGP_SV_PART == 0 || DQGP_SV_PART == 5
 int dqgp_features_jacobian(const dqgp_circuit* c, const double* d_X, int n, const double* d_p, double* d_F, double* d_J, void* stream) {
-    using namespace dqgp;
-    DQGP_REQUIRE(n >= 0, "dqgp_features_jacobian: negative size");
-    if (n == 0) return 0;
-    DQGP_REQUIRE(c && d_X && d_p && d_F && d_J, "dqgp_features_jacobian: NULL argument");
-    DQGP_REQUIRE(c->shareable, "dqgp_features_jacobian: a parameter of this circuit feeds several gates");
-    int rc = circuit_on_device(c);
-    if (rc) return rc;
-    cudaStream_t st = as_stream(stream);
-    switch (c->q) {
-#define DQGP_SV_CASE(QQ) case QQ: return launch_sv_jac<QQ>(c, d_X, n, d_p, d_F, d_J, st);
-        DQGP_SV_CASE(1) DQGP_SV_CASE(2) DQGP_SV_CASE(3) DQGP_SV_CASE(4) DQGP_SV_CASE(5) DQGP_SV_CASE(6)
-        DQGP_SV_CASE(7) DQGP_SV_CASE(8) DQGP_SV_CASE(9) DQGP_SV_CASE(10) DQGP_SV_CASE(11) DQGP_SV_CASE(12)
-#undef DQGP_SV_CASE
-    }
-    set_error("statevector: unsupported qubit count %d", c->q);
-    return -1;
+    return dqgp::dispatch_sv_jac<false>(c, d_X, n, d_p, d_F, d_J, stream);
+}
+int dqgp_states_jacobian(const dqgp_circuit* c, const double* d_X, int n, const double* d_p, double* d_Psi, double* d_D, void* stream) {
+    return dqgp::dispatch_sv_jac<true>(c, d_X, n, d_p, d_Psi, d_D, stream);
 }
 #endif
 #if DQGP_SV_PART == 0 || DQGP_SV_PART == 3

@@ -76,7 +76,7 @@ class AgentEngine:
         agent_riemannian.py:275) - the parity path; "analytic" (opt-in) = the exact derivative of the NLL:
         feature Jacobian from one extra suffix simulation per parameter and ONE pass over the n^2 Gram entries.  The analytic
         mode does NOT reproduce the reference's trajectories (its h = pi/8 difference is far from the derivative); it needs the
-        projected kernel with the Gaussian outer kernel."""
+        Gaussian outer kernel (projected) or at most 6 qubits (fidelity)."""
         _require_cuda()
         self._lib = _lib.load()
         X = np.asarray(X, dtype=np.float64)
@@ -102,13 +102,17 @@ class AgentEngine:
         if gradient not in ("central_difference", "analytic"):
             raise ValueError(f"Unknown gradient mode: {gradient}")
         self.gradient_mode = gradient
-        if gradient == "analytic" and (kernel_type != "projected" or self.outer_kernel != "gaussian"):
-            raise ValueError("gradient='analytic' needs the projected kernel with the Gaussian outer kernel")
+        if gradient == "analytic" and kernel_type == "projected" and self.outer_kernel != "gaussian":
+            raise ValueError("gradient='analytic' needs the Gaussian outer kernel for the projected kernel")
+        if gradient == "analytic" and kernel_type == "fidelity" and self.q > 6:
+            raise ValueError("gradient='analytic' supports the fidelity kernel up to 6 qubits")
         self.d_Pm = torch.empty((self.S, self.P), **f64)
         if gradient == "analytic":
             self.d_feat = torch.empty((1, self.n, self.m), **f64)
             self.d_jac = torch.empty((self.P, self.n, self.m), **f64)
-            self.d_work_a = torch.empty(max(1, self._lib.dqgp_grad_analytic_workspace_bytes(self.n, self.m) // 8), **f64)
+            wbytes = (self._lib.dqgp_grad_analytic_workspace_bytes(self.n, self.m) if kernel_type == "projected"
+                      else self._lib.dqgp_grad_fidelity_analytic_workspace_bytes(self.n, 1 << self.q))
+            self.d_work_a = torch.empty(max(1, wbytes // 8), **f64)
         else:
             self.d_feat = torch.empty((self.S, self.n, self.m), **f64)
         self.cholesky_outer_blocks = int(cholesky_outer_blocks)
@@ -137,8 +141,9 @@ class AgentEngine:
             check(lib.dqgp_shift_parameter_sets(d_z.data_ptr(), self.P, self.h, PERIOD, self.d_Pm.data_ptr(), st), "shift sets")
         count = self.S - first if count is None else count
         if self.gradient_mode == "analytic":
-            check(lib.dqgp_features_jacobian(self.circuit.handle, self.d_X.data_ptr(), self.n, self.d_Pm.data_ptr(), self.d_feat.data_ptr(),
-                                             self.d_jac.data_ptr(), st), "feature jacobian")
+            fn = lib.dqgp_features_jacobian if self.kernel_type == "projected" else lib.dqgp_states_jacobian
+            check(fn(self.circuit.handle, self.d_X.data_ptr(), self.n, self.d_Pm.data_ptr(), self.d_feat.data_ptr(), self.d_jac.data_ptr(), st),
+                  "jacobian")
             return
         if first == 0 and count == self.S and self.share_prefix:
             # all 2P+1 central-difference sets of a sample share the circuit prefix before the shifted gate
@@ -168,7 +173,11 @@ class AgentEngine:
 
     def gradient(self):
         lib, st, s = self._lib, stream_ptr(), self.solver
-        if self.gradient_mode == "analytic":
+        if self.gradient_mode == "analytic" and self.kernel_type == "fidelity":
+            check(lib.dqgp_grad_fidelity_analytic(s.inverse_ptr, s.ld, self.d_alpha.data_ptr(), self.d_feat.data_ptr(), self.d_jac.data_ptr(),
+                                                  self.n, 1 << self.q, self.P, self.d_grad.data_ptr(), self.d_work_a.data_ptr(), st),
+                  "grad fidelity analytic")
+        elif self.gradient_mode == "analytic":
             check(lib.dqgp_grad_projected_analytic(self._outer_id, self._hyp, s.inverse_ptr, s.ld, self.d_alpha.data_ptr(), self.d_feat.data_ptr(),
                                                    self.d_jac.data_ptr(), self.n, self.m, self.P, self.d_grad.data_ptr(),
                                                    self.d_work_a.data_ptr(), st), "grad analytic")

@@ -368,8 +368,10 @@ def test_full_size_properties_config4_shard(d):
         assert abs(g1[i].item() - ref) < 1e-6 * max(1.0, abs(ref))
 
 
-@pytest.mark.parametrize("enc,q,dd,layers,n", [("yz_cx", 4, 2, 2, 150), ("kyriienko", 3, 2, 1, 200), ("chebyshev", 3, 2, 1, 180)])
-def test_analytic_gradient_is_the_derivative_of_the_oracle_nll(d, enc, q, dd, layers, n):
+@pytest.mark.parametrize("enc,ktype,q,dd,layers,n", [("yz_cx", "projected", 4, 2, 2, 150), ("kyriienko", "projected", 3, 2, 1, 200),
+                                                     ("chebyshev", "projected", 3, 2, 1, 180), ("hubregtsen", "fidelity", 5, 2, 2, 160),
+                                                     ("yz_cx", "fidelity", 2, 2, 1, 120), ("chebyshev", "fidelity", 3, 2, 1, 100)])
+def test_analytic_gradient_is_the_derivative_of_the_oracle_nll(d, enc, ktype, q, dd, layers, n):
     """AgentEngine(gradient="analytic") (opt-in): the gradient equals the derivative of the NLL computed by
     the ORACLE (NumPy kernel + LAPACK), by central differences of the NLL itself; and the reference's h = pi/8 rule, which the
     default mode reproduces, is visibly a different number."""
@@ -378,7 +380,7 @@ def test_analytic_gradient_is_the_derivative_of_the_oracle_nll(d, enc, q, dd, la
     z = np.round(np.random.RandomState(5).uniform(0.2, 2.9, d.EncodingCircuit(enc, q, dd, layers).num_parameters), 4)
     grads = {}
     for mode in ("analytic", "central_difference"):
-        eng = d.AgentEngine(x, y, encoding_type=enc, kernel_type="projected", num_qubits=q, num_layers=layers, noise_std=0.1, rho=100.0,
+        eng = d.AgentEngine(x, y, encoding_type=enc, kernel_type=ktype, num_qubits=q, num_layers=layers, noise_std=0.1, rho=100.0,
                             L=100.0, gradient=mode)
         dz = d.kernels.dev_f64(z)
         eng.simulate(dz); eng.gram(); eng.factor(); eng.gradient()
@@ -387,7 +389,7 @@ def test_analytic_gradient_is_the_derivative_of_the_oracle_nll(d, enc, q, dd, la
         nll_gpu = float(eng.d_nll[3].item())
 
     def nll(p):
-        qk = qkernels.create_quantum_kernel(q, dd, layers, enc, "projected", "XYZ", "gaussian")
+        qk = qkernels.create_quantum_kernel(q, dd, layers, enc, ktype, "XYZ", "gaussian")
         qk.assign_parameters(p)
         a = qk.evaluate(x, x) + 0.01 * np.eye(n)
         L = np.linalg.cholesky(a)
