@@ -39,7 +39,10 @@ class RiemannianAgent:
                  num_workers=None, shift_value=np.pi / 8, num_layers=2, combined_computation=True, encoding_type="yz_cx",
                  kernel_type="fidelity", measurement="XYZ", outer_kernel="gaussian", outer_kernel_params=None,
                  regularization=None, riemannian_lr=0.01, riemannian_method="gradient_descent", riemannian_beta=0.9,
-                 training_ignores_outer_kernel=True, compute_condition_number=False):
+                 training_ignores_outer_kernel=True, compute_condition_number=False, gradient="central_difference"):
+        # gradient="analytic": opt-in exact NLL derivative (the role of the reference's evaluate_derivatives branch,
+        # agent_riemannian.py:397-404); the default reproduces the reference's live path (central difference, h = shift_value)
+        self.gradient = gradient
         self.agent_id = agent_id
         self.X_sub = np.asarray(X_sub, dtype=np.float64)
         if self.X_sub.ndim == 1:
@@ -69,11 +72,12 @@ class RiemannianAgent:
     def _engine(self):
         n, d = self.X_sub.shape
         key = (self.agent_id, n, d, self.encoding_type, self.kernel_type, self.num_qubits, self.num_layers, self.outer_kernel,
-               float(self.noise_std), float(self.rho), float(self.L), float(self.shift_value), self.training_ignores_outer_kernel)
+               float(self.noise_std), float(self.rho), float(self.L), float(self.shift_value), self.training_ignores_outer_kernel,
+               self.gradient)
         return _engine_for(key, lambda: AgentEngine(
             self.X_sub, self.Y_sub, encoding_type=self.encoding_type, kernel_type=self.kernel_type, num_qubits=self.num_qubits,
             num_layers=self.num_layers, noise_std=self.noise_std, rho=self.rho, L=self.L, outer_kernel=self.outer_kernel,
-            shift_value=self.shift_value, training_ignores_outer_kernel=self.training_ignores_outer_kernel))
+            shift_value=self.shift_value, training_ignores_outer_kernel=self.training_ignores_outer_kernel, gradient=self.gradient))
 
     def train_and_update(self, z, psi_i):
         """-> (theta_i, psi_i, nll_loss, condition_number, nll_components), as agent_riemannian.py:491."""

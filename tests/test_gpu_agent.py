@@ -403,3 +403,24 @@ def test_analytic_gradient_is_the_derivative_of_the_oracle_nll(d, enc, ktype, q,
         ref = (nll(z + e) - nll(z - e)) / (2 * h)
         assert abs(grads["analytic"][i] - ref) < 2e-5 * max(1.0, abs(ref)), (i, grads["analytic"][i], ref)
     assert np.max(np.abs(grads["analytic"] - grads["central_difference"])) > 1e-3 * np.max(np.abs(grads["analytic"]))
+
+
+def test_riemannian_agent_analytic_mode_through_the_reference_api(d):
+    """RiemannianAgent(..., gradient="analytic").train_and_update: same NLL as the default mode, gradient equal to the engine's
+    analytic gradient, and a local update that follows from it by the reference's formulas."""
+    from oracle import agent_step, torus
+    x, y = d.synthetic_dataset(140, 2, "yz_cx")
+    rs = np.random.RandomState(11)
+    P = d.EncodingCircuit("yz_cx", 4, 2, 2).num_parameters
+    z, psi = np.round(rs.uniform(0.2, 2.9, P), 4), np.round(rs.rand(P), 4)
+    out = {}
+    for mode in ("central_difference", "analytic"):
+        ag = d.RiemannianAgent(f"m_{mode}", x, y, 4, 0.1, 100.0, 100.0, use_parameter_shift=True, num_layers=2, encoding_type="yz_cx",
+                               kernel_type="projected", gradient=mode)
+        theta, psi_new, nll, _, _ = ag.train_and_update(z, psi)
+        out[mode] = (theta, psi_new, nll, ag.last_gradient.copy())
+    assert abs(out["analytic"][2] - out["central_difference"][2]) < 1e-9 * abs(out["analytic"][2])
+    g4 = np.round(out["analytic"][3], 4)
+    th_ref, ps_ref = agent_step.local_update(torus.wrap(z), g4, psi, 100.0, 100.0)
+    assert np.max(np.abs(out["analytic"][0] - th_ref)) < 1e-12 and np.max(np.abs(out["analytic"][1] - ps_ref)) < 1e-9
+    assert np.max(np.abs(out["analytic"][3] - out["central_difference"][3])) > 1e-3
