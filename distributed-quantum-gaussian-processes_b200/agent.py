@@ -39,9 +39,19 @@ class RiemannianAgent:
                  num_workers=None, shift_value=np.pi / 8, num_layers=2, combined_computation=True, encoding_type="yz_cx",
                  kernel_type="fidelity", measurement="XYZ", outer_kernel="gaussian", outer_kernel_params=None,
                  regularization=None, riemannian_lr=0.01, riemannian_method="gradient_descent", riemannian_beta=0.9,
-                 training_ignores_outer_kernel=True, compute_condition_number=False, gradient="central_difference"):
-        # gradient="analytic": opt-in exact NLL derivative (the role of the reference's evaluate_derivatives branch,
-        # agent_riemannian.py:397-404); the default reproduces the reference's live path (central difference, h = shift_value)
+                 training_ignores_outer_kernel=None, compute_condition_number=False, gradient=None):
+        # use_parameter_shift selects the reference's branch (agent_riemannian.py:383-404):
+        #   True  (what main.py hard-codes, :2301): the (2P+1)-job workers, whose config dict carries no outer kernel -> Gaussian
+        #         training Grams (Q1), central difference with h = shift_value;
+        #   False, projected: `_manual_projected_kernel_derivatives_riemannian` (:279-312) - the same central difference, but
+        #         through self.q_kernel, which was built with the REAL outer kernel -> training_ignores_outer_kernel=False;
+        #   False, fidelity: `q_kernel.evaluate_derivatives(["K", "dKdp"])` (:402-404), the analytic derivative -> gradient="analytic"
+        #         (up to 6 qubits here; AgentEngine raises beyond that instead of silently substituting the finite difference).
+        # Explicit `training_ignores_outer_kernel` / `gradient` arguments override the mapping.
+        if training_ignores_outer_kernel is None:
+            training_ignores_outer_kernel = bool(use_parameter_shift) or kernel_type != "projected"
+        if gradient is None:
+            gradient = "analytic" if (not use_parameter_shift and kernel_type == "fidelity") else "central_difference"
         self.gradient = gradient
         self.agent_id = agent_id
         self.X_sub = np.asarray(X_sub, dtype=np.float64)

@@ -95,7 +95,8 @@ __global__ void predict_finish_kernel(const double* __restrict__ Kst, int nt, in
     }
     if (lane == 0) {
         if (kss == nullptr) { mean[row] = acc; return; }     // mean-only launch
-        const double v = fmax(kss[row] - quad[row], 1e-10);
+        const double t = kss[row] - quad[row];
+        const double v = (t != t) ? t : fmax(t, 1e-10);     // np.maximum (main.py:1466) propagates NaN; CUDA's fmax would drop it
         mean[row] = acc;
         var[row] = v;
         if (nlpd_terms) {

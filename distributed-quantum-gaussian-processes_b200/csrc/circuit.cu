@@ -60,8 +60,9 @@ static void build(dqgp_circuit& c) {
         case DQGP_CHEBYSHEV: {
             // basis change, L x [RX(p*arccos x) ; CRZ ring: even pairs then odd pairs incl. closing pair], basis change
             for (int i = 0; i < q; ++i) G.push_back(mk(DQGP_G_RY, i, -1, DQGP_A_P, take()));
+            // feature index: a running offset over all layers (squlearn 0.9.x, recalled); equals i % d when q % d == 0 or L == 1
             for (int l = 0; l < L; ++l) {
-                for (int i = 0; i < q; ++i) G.push_back(mk(DQGP_G_RX, i, -1, DQGP_A_P_TIMES_ACOS, take(), i % d));
+                for (int i = 0; i < q; ++i) G.push_back(mk(DQGP_G_RX, i, -1, DQGP_A_P_TIMES_ACOS, take(), (l * q + i) % d));
                 if (q >= 2)   // range(0, q + closed - 1, 2) with closed = 1
                     for (int i = 0; i < q; i += 2) G.push_back(mk(DQGP_G_CRZ, i, (i + 1) % q, DQGP_A_P, take()));
                 if (q > 2)
@@ -86,8 +87,8 @@ static void build(dqgp_circuit& c) {
         case DQGP_YZ_CX: {
             for (int l = 0; l < L; ++l) {
                 for (int i = 0; i < q; ++i) {
-                    G.push_back(mk(DQGP_G_RY, i, -1, DQGP_A_P_PLUS_CX, take(), i % d, 1.0));
-                    G.push_back(mk(DQGP_G_RZ, i, -1, DQGP_A_P_PLUS_CX, take(), i % d, 1.0));
+                    G.push_back(mk(DQGP_G_RY, i, -1, DQGP_A_P_PLUS_CX, take(), (l * q + i) % d, 1.0));   // running feature offset
+                    G.push_back(mk(DQGP_G_RZ, i, -1, DQGP_A_P_PLUS_CX, take(), (l * q + i) % d, 1.0));
                 }
                 for (int i = (l % 2 == 0 ? 0 : 1); i < q - 1; i += 2) G.push_back(mk(DQGP_G_CX, i, i + 1));
             }

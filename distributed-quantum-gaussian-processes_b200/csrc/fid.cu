@@ -164,7 +164,10 @@ __global__ void __launch_bounds__(PW_THREADS, 1) fidelity_dmma_kernel(const doub
 }
 
 static int fd_attr() {
-    static bool done = false;
+    static bool done_dev[64] = {false};      // the attribute is per DEVICE
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& done = done_dev[(dev >= 0 && dev < 64) ? dev : 0];
     if (!done) {
         DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
         DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));

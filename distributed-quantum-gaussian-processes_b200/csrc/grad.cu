@@ -504,7 +504,10 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
         const bool no_clamp = outer == DQGP_OUTER_GAUSSIAN && hyp.a > 0.0 && 4.0 * m * hyp.a < 650.0;
 #define DQGP_G2(OUT)                                                                                                         \
     do {                                                                                                                     \
-        static bool attr_done = false;                                                                                       \
+        static bool attr_done_dev[64] = {false};        /* the attribute is per DEVICE (as gemm_init's flags) */            \
+        int dev_ = 0;                                                                                                        \
+        cudaGetDevice(&dev_);                                                                                                \
+        bool& attr_done = attr_done_dev[(dev_ >= 0 && dev_ < 64) ? dev_ : 0];                                                \
         if (!attr_done) {                                                                                                    \
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \

@@ -317,8 +317,14 @@ class AdmmEngine:
     def capture(self):
         """Capture the device part of one iteration (consensus, all local agents, their streams and the solver's internal
         look-ahead streams) into a CUDA graph; `replay()` then costs one launch plus the row exchange, which stays
-        outside the graph (an in-place copy on one rank, the NCCL all-gather on several)."""
-        self.iteration()                         # warm-up: lazy uploads and function attributes must be set before capture
+        outside the graph (an in-place copy on one rank, the NCCL all-gather on several).  The warm-up iteration that capture
+        needs (lazy uploads, function attributes) does NOT advance the run: theta / psi / z are restored afterwards, so
+        capture() + k replays walks exactly k iterations, like k eager iteration() calls."""
+        keep = [t.clone() for t in (self.theta, self.psi, self.z, self.local_theta, self.local_psi)]
+        self.iteration()                         # warm-up
+        torch.cuda.synchronize()
+        for t, k in zip((self.theta, self.psi, self.z, self.local_theta, self.local_psi), keep):
+            t.copy_(k)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):

@@ -5,7 +5,10 @@ The reference only *constructs* these (``main.py:68-83``, ``agent_riemannian.py:
 in squlearn, which is not available here.  Each builder below restates the published circuit as a flat
 list of ``Gate`` records.  Conventions (Qiskit): little-endian (qubit 0 = least-significant index bit),
 ``RX(t)=exp(-i t X/2)``, ``RY``, ``RZ`` likewise, ``CRZ(t; c, t)=|0><0|(x)I + |1><1|(x)RZ(t)``, start |0..0>.
-Parameter and feature indices wrap (``parameters[ioff % P]``, ``features[i % d]``).
+Parameter and feature indices wrap (``parameters[ioff % P]``, ``features[k % d]``).  ChebyshevPQC and YZ_CX carry a RUNNING
+feature offset across layers (``features[feature_offset % d]``, one step per encoded qubit, never reset) as recalled from
+squlearn 0.9.x; Hubregtsen restarts at feature 0 in every layer.  The two rules coincide whenever ``q % d == 0`` or there
+is one layer — every BASELINE.json config and every golden fixture — so this choice is invisible to them.
 
 Angle forms (``Gate.form``):
   "p"      angle = p[pidx]
@@ -81,9 +84,11 @@ def build_circuit(encoding: str, q: int, d: int, layers: int) -> List[Gate]:
         # the initial parameters, which the reference overwrites (agent_riemannian.py:114).
         for i in range(q):
             gates.append(Gate("ry", i, form="p", pidx=take()))
+        foff = 0
         for _ in range(layers):
             for i in range(q):
-                gates.append(Gate("rx", i, form="p*acos", pidx=take(), fidx=i % d))
+                gates.append(Gate("rx", i, form="p*acos", pidx=take(), fidx=foff % d))
+                foff += 1
             closed = 1
             for i in range(0, q + closed - 1, 2):
                 if q >= 2:
@@ -109,10 +114,12 @@ def build_circuit(encoding: str, q: int, d: int, layers: int) -> List[Gate]:
                     gates.append(Gate("crz", i, (i + 1) % q, form="p", pidx=take()))
     elif encoding == "yz_cx":
         # YZ_CX_EncodingCircuit(c=1.0)
+        foff = 0
         for layer in range(layers):
             for i in range(q):
-                gates.append(Gate("ry", i, form="p+cx", pidx=take(), fidx=i % d, coef=1.0))
-                gates.append(Gate("rz", i, form="p+cx", pidx=take(), fidx=i % d, coef=1.0))
+                gates.append(Gate("ry", i, form="p+cx", pidx=take(), fidx=foff % d, coef=1.0))
+                gates.append(Gate("rz", i, form="p+cx", pidx=take(), fidx=foff % d, coef=1.0))
+                foff += 1
             start = 0 if layer % 2 == 0 else 1
             for i in range(start, q - 1, 2):
                 gates.append(Gate("cx", i, i + 1))

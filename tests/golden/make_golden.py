@@ -119,8 +119,17 @@ def outer_kernel_golden():
                         expsinesquared=ExpSineSquared(length_scale=1.0, periodicity=1.0)(f, g))
 
 
-def trajectory_golden(max_iter=4):
-    """BASELINE.json configs[0] through the real main.main(), recording what crosses its process pool."""
+CFG1_ARGS = ("--input-dim 2 --n-dataset 1000 --encoding chebyshev --kernel-type projected --num-layers 1 "
+             "--num-qubits 3 --outer-kernel matern --rho 100 --L 100 --n-agents 4")
+# configs[1] with the SRTM tile absent (.MISSING_LARGE_BLOBS): the same circuit / kernel / agent count on main.py's
+# synthetic quantum-GP branch
+CFG2_ARGS = ("--input-dim 2 --n-dataset 1000 --encoding chebyshev --kernel-type projected --num-layers 3 "
+             "--num-qubits 4 --outer-kernel matern --rho 100 --L 100 --n-agents 4")
+
+
+def trajectory_golden(max_iter=30, name="trajectory_cfg1", args=CFG1_ARGS):
+    """BASELINE.json configs[0] (or a configs[1]-shaped run) through the real main.main(), recording what crosses its
+    process pool."""
     record = {"iterations": []}
     real_pool = M.ProcessPoolExecutor
 
@@ -158,9 +167,7 @@ def trajectory_golden(max_iter=4):
     # matplotlib is a stub here: make the three plotting helpers no-ops (they do not touch the numerics)
     for fn in ("plot_quantum_gp_data", "plot_agent_data_distribution", "plot_predictions"):
         setattr(M, fn, lambda *a, **k: None)
-    argv = ("main.py --input-dim 2 --n-dataset 1000 --encoding chebyshev --kernel-type projected --num-layers 1 "
-            "--num-qubits 3 --outer-kernel matern --rho 100 --L 100 --n-agents 4 --no-plot --seed 42 --data-seed 7 "
-            f"--max-iter {max_iter}").split()
+    argv = f"main.py {args} --no-plot --seed 42 --data-seed 7 --max-iter {max_iter}".split()
     old = sys.argv
     sys.argv = argv
     log = io.StringIO()
@@ -179,19 +186,26 @@ def trajectory_golden(max_iter=4):
     for a, (xa, ya) in enumerate(shards):
         arrays[f"X_{a}"] = xa
         arrays[f"Y_{a}"] = ya
-    np.savez_compressed(os.path.join(HERE, "trajectory_cfg1_data.npz"), **arrays)
+    np.savez_compressed(os.path.join(HERE, f"{name}_data.npz"), **arrays)
     record["argv"] = " ".join(argv)
     record["n_agents"] = len(shards)
-    with open(os.path.join(HERE, "trajectory_cfg1.json"), "w") as f:
+    with open(os.path.join(HERE, f"{name}.json"), "w") as f:
         json.dump(record, f, indent=1)
     print("trajectory golden:", len(record["iterations"]), "iterations; shard sizes", [s[0].shape[0] for s in shards])
     return log.getvalue()
 
 
 if __name__ == "__main__":
-    torus_golden()
-    outer_kernel_golden()
-    agent_golden()
-    log = trajectory_golden()
-    with open("/tmp/main_cfg1.log", "w") as f:
-        f.write(log)
+    only = sys.argv[1:]
+    if not only or "torus" in only:
+        torus_golden()
+    if not only or "outer" in only:
+        outer_kernel_golden()
+    if not only or "agent" in only:
+        agent_golden()
+    if not only or "cfg1" in only:
+        with open("/tmp/main_cfg1.log", "w") as f:
+            f.write(trajectory_golden(30, "trajectory_cfg1", CFG1_ARGS))
+    if not only or "cfg2" in only:
+        with open("/tmp/main_cfg2.log", "w") as f:
+            f.write(trajectory_golden(10, "trajectory_cfg2", CFG2_ARGS))

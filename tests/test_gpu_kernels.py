@@ -378,3 +378,38 @@ def test_lookahead_cholesky_is_deterministic_at_full_size(d, ob):
     for o in outs[1:]:
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2]) and o[3] == outs[0][3]
     assert ((A @ outs[0][2] - y).abs().max() / y.abs().max()).item() < 1e-9
+
+
+@pytest.mark.parametrize("outer", ["matern", "expsinesquared"])
+@pytest.mark.parametrize("enc,q,dd,layers,n", [("kyriienko", 4, 6, 2, 150), ("chebyshev", 3, 2, 1, 97), ("yz_cx", 5, 4, 2, 200),
+                                                ("hubregtsen", 3, 4, 2, 64)])
+def test_fused_gradient_honoured_outer_kernels_match_oracle(d, outer, enc, q, dd, layers, n):
+    """The Matern (OUTER = 1) and ExpSineSquared (OUTER = 2) instantiations of the fused gradient, i.e. training Grams that
+    HONOUR --outer-kernel (training_ignores_outer_kernel=False; the reference's Q1 default is tested above): dqgp_grad_projected
+    on the ORACLE's C^-1 and alpha equals 1/2 sum(B o dK_i^T) with the oracle's materialised dK (agent_riemannian.py:431-436) to
+    1e-8.  ExpSineSquared Grams are indefinite, so the oracle's C^-1 comes from the reference's LU branch (:419-425) — the kernel
+    under test is the contraction, fed the same operands."""
+    from oracle import agent_step
+    x, y = d.synthetic_dataset(n, dd, enc, seed=n)
+    cfg = agent_step.KernelConfig(enc, "projected", q, layers, outer, training_ignores_outer_kernel=False)
+    eng = d.AgentEngine(x, y, encoding_type=enc, kernel_type="projected", num_qubits=q, num_layers=layers, noise_std=0.1, rho=100.0,
+                        L=100.0, outer_kernel=outer, training_ignores_outer_kernel=False)
+    z = np.round(np.random.RandomState(n).rand(eng.P) * np.pi, 4)
+    K, dK = agent_step.kernel_and_derivatives(cfg, x, np.mod(z, np.pi), np.pi / 8)
+    grad_ref, comp, _, alpha, cinv = agent_step.gp_terms(K, dK, y, 0.1, want_cond=False)
+    eng.simulate(d.kernels.dev_f64(z))
+    eng.gram()
+    Kd = torch.tril(eng.solver.matrix()).cpu().numpy()
+    ref_l = np.tril(K + 0.01 * np.eye(n))
+    assert np.max(np.abs(Kd - ref_l) / np.maximum(np.abs(ref_l), 1e-300)) < 1e-10
+    eng.solver.inverse().copy_(torch.from_numpy(cinv).cuda())
+    eng.d_alpha.copy_(torch.from_numpy(alpha).cuda())
+    eng.gradient()
+    torch.cuda.synchronize()
+    got = eng.d_grad.cpu().numpy()
+    assert np.max(np.abs(got - grad_ref)) < 1e-8 * max(1.0, np.abs(grad_ref).max())
+    if outer == "matern":          # positive definite: the whole device path (Cholesky, alpha, inverse, NLL) as well
+        eng.factor(); eng.gradient()
+        torch.cuda.synchronize(); eng.check_info()
+        assert np.max(np.abs(eng.d_grad.cpu().numpy() - grad_ref)) < 1e-8 * max(1.0, np.abs(grad_ref).max())
+        assert abs(float(eng.d_nll[3].item()) - comp["total"]) < 1e-8 * max(1.0, abs(comp["total"]))

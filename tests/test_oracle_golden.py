@@ -75,6 +75,28 @@ def test_first_iteration_of_reference_main_trajectory():
     assert np.array_equal(z2, np.array(rec["iterations"][1]["z"]))
 
 
+@pytest.mark.parametrize("name,q,layers,late", [("trajectory_cfg1", 3, 1, 29), ("trajectory_cfg2", 4, 3, 9)])
+def test_whole_reference_main_trajectory_consensus_chain(name, q, layers, late):
+    """Every z of the recorded main.main() runs (30 iterations of configs[0]; 10 of the configs[1]-shaped run) follows bit for
+    bit from the previous iteration's recorded theta / psi (main.py:2523), and the oracle's agent step reproduces a LATE
+    iteration's outputs of the smallest shard exactly (the state has left the initial random grid points by then)."""
+    with open(os.path.join(GOLDEN, f"{name}.json")) as f:
+        rec = json.load(f)
+    its = rec["iterations"]
+    assert len(its) == late + 1
+    for k in range(1, len(its)):
+        z = np.round(torus.update_z(np.array(its[k - 1]["theta_out"]), np.array(its[k - 1]["psi_out"]), 100.0), 4)
+        assert np.array_equal(z, np.array(its[k]["z"])), k
+        assert its[k]["psi_in"] == its[k - 1]["psi_out"]
+    data = load_golden(f"{name}_data.npz")
+    it, a = its[late], 3
+    cfg = agent_step.KernelConfig("chebyshev", "projected", q, layers, "matern")
+    r = agent_step.train_and_update(cfg, data[f"X_{a}"], data[f"Y_{a}"], np.array(it["z"]), np.array(it["psi_in"][a]), 0.1,
+                                    100.0, 100.0, workers=None, want_cond=False)
+    assert np.array_equal(r.theta, np.array(it["theta_out"][a])) and np.array_equal(r.psi, np.array(it["psi_out"][a]))
+    assert r.nll == it["nll"][a]
+
+
 def test_q1_training_ignores_outer_kernel_switch():
     g = load_golden("agent_step_cheb_proj_matern_q3.npz")
     kw = dict(encoding_type="chebyshev", kernel_type="projected", num_qubits=3, num_layers=1, outer_kernel="matern")
