@@ -47,9 +47,10 @@ def test_full_size_shard_matches_oracle(d, cfg, outer):
     K = A[hi, lo].cpu().numpy()                     # the training Gram fills the lower tiles (all the factorisation reads)
     K[g["rows"][:, None] == g["cols"][None, :]] -= float(g["noise_std"]) ** 2
     ref = g[f"K_{outer}"]
-    # the stored diagonal is 1 + sigma^2, so the subtraction above leaves rounding of 1.01 - 0.01 there: compare those to 1e-15
+    # the stored diagonal is K_jj + sigma^2, so the subtraction above leaves the rounding of 1.01 - 0.01 there (and a fidelity
+    # diagonal is |<psi|psi>|^2 = 1 to a few ulp on both sides): compare those absolutely
     diag = g["rows"][:, None] == g["cols"][None, :]
-    assert np.max(np.abs(K - ref)[diag], initial=0.0) < 1e-15
+    assert np.max(np.abs(K - ref)[diag], initial=0.0) < 1e-13
     rel = np.abs(K - ref) / np.maximum(np.abs(ref), 1e-300)
     assert np.max(rel[~diag]) < 1e-10, f"K differs from the oracle by {np.max(rel[~diag]):.2e} relative"
     th, ps = torch.empty(eng.P, dtype=torch.float64, device="cuda"), torch.empty(eng.P, dtype=torch.float64, device="cuda")

@@ -20,10 +20,12 @@ ap.add_argument("--layers", type=int, default=3)
 ap.add_argument("--d", type=int, default=4)
 ap.add_argument("--outer", type=int, default=0)
 ap.add_argument("--gradient", default="central_difference", choices=["central_difference", "analytic"])
+ap.add_argument("--outer-kernel", default="gaussian", help="training outer kernel (honoured: cfg5 = matern)")
 a = ap.parse_args()
 x, y = d.synthetic_dataset(a.n, a.d, a.encoding)
 eng = d.AgentEngine(x, y, encoding_type=a.encoding, kernel_type=a.kernel, num_qubits=a.q, num_layers=a.layers, noise_std=0.1,
-                    rho=100.0, L=100.0, cholesky_outer_blocks=a.outer, gradient=a.gradient)
+                    rho=100.0, L=100.0, cholesky_outer_blocks=a.outer, gradient=a.gradient, outer_kernel=a.outer_kernel,
+                    training_ignores_outer_kernel=False)
 rs = np.random.RandomState(42)
 z = d.kernels.dev_f64(np.round(rs.rand(eng.P), 4))
 psi = d.kernels.dev_f64(np.round(rs.rand(eng.P), 4))
