@@ -37,6 +37,7 @@ SIGNATURES = {
     "dqgp_circuit_num_gates": (_i, [_vp]),
     "dqgp_circuit_num_passes": (_i, [_vp]),
     "dqgp_circuit_num_fused_ops": (_i, [_vp]),
+    "dqgp_circuit_shifted_u2_applications": (C.c_longlong, [_vp]),
     "dqgp_circuit_describe": (_i, [_vp, C.POINTER(Gate), _i]),
     "dqgp_features": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
     "dqgp_states": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "dqgp_nll_terms": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "dqgp_admm_local": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp]),
     "dqgp_admm_consensus": (_i, [_vp, _vp, _i, _i, _d, _d, _vp, _vp]),
+    "dqgp_admm_consensus_strided": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _vp, _vp]),
     "dqgp_predict_mean": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "dqgp_predict_finish": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }

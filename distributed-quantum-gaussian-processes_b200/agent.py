@@ -39,7 +39,7 @@ class RiemannianAgent:
                  num_workers=None, shift_value=np.pi / 8, num_layers=2, combined_computation=True, encoding_type="yz_cx",
                  kernel_type="fidelity", measurement="XYZ", outer_kernel="gaussian", outer_kernel_params=None,
                  regularization=None, riemannian_lr=0.01, riemannian_method="gradient_descent", riemannian_beta=0.9,
-                 training_ignores_outer_kernel=None, compute_condition_number=False, gradient=None):
+                 training_ignores_outer_kernel=None, compute_condition_number=False, gradient=None, reupload_shard="if_changed"):
         # use_parameter_shift selects the reference's branch (agent_riemannian.py:383-404):
         #   True  (what main.py hard-codes, :2301): the (2P+1)-job workers, whose config dict carries no outer kernel -> Gaussian
         #         training Grams (Q1), central difference with h = shift_value;
@@ -53,6 +53,9 @@ class RiemannianAgent:
         if gradient is None:
             gradient = "analytic" if (not use_parameter_shift and kernel_type == "fidelity") else "central_difference"
         self.gradient = gradient
+        # "if_changed": X_sub / Y_sub stay resident on the GPU and are re-uploaded only when they differ from the staged copy;
+        # "always": copy them every call, as the reference re-pickles them to its workers every iteration (main.py:2530-2542)
+        self.reupload_shard = reupload_shard
         self.agent_id = agent_id
         self.X_sub = np.asarray(X_sub, dtype=np.float64)
         if self.X_sub.ndim == 1:
@@ -104,24 +107,33 @@ class RiemannianAgent:
             raise ValueError(f"expected {eng.P} parameters, got z {z.size}, psi {psi_i.size}")
         self._setup_riemannian_framework(eng.P)
         ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
+        h_in, h_out = eng.staging()                 # persistent pinned buffers (no cudaHostAlloc per call)
+        h_in[0].copy_(torch.from_numpy(z))
+        h_in[1].copy_(torch.from_numpy(psi_i))
         with ctx:
-            eng.load_data(self.X_sub, self.Y_sub)
-            d_in = dev_f64(np.stack([z, psi_i]))
-            d_out = torch.empty((2, eng.P), dtype=torch.float64, device=d_in.device)
-            eng.step(d_in[0], d_in[1], d_out[0], d_out[1])
-            packed = torch.cat([d_out.reshape(-1), eng.d_nll, eng.d_grad, eng.d_info.to(torch.float64)])
-            host = torch.empty(packed.shape, dtype=torch.float64, pin_memory=True)
-            host.copy_(packed, non_blocking=True)          # one D2H
+            shard_bytes = eng.load_data(self.X_sub, self.Y_sub, always=self.reupload_shard == "always")
+            if getattr(eng, "_d_in", None) is None:
+                eng._d_in = torch.empty((2, eng.P), dtype=torch.float64, device=eng.d_X.device)
+                eng._d_out = torch.empty((3 * eng.P + 5,), dtype=torch.float64, device=eng.d_X.device)
+            d_in, d_out = eng._d_in, eng._d_out
+            d_in.copy_(h_in, non_blocking=True)
+            p = eng.P
+            eng.step(d_in[0], d_in[1], d_out[:p], d_out[p:2 * p])
+            d_out[2 * p:2 * p + 4].copy_(eng.d_nll)
+            d_out[2 * p + 4:3 * p + 4].copy_(eng.d_grad)
+            d_out[3 * p + 4:].copy_(eng.d_info)                 # int32 -> float64
+            h_out.copy_(d_out, non_blocking=True)               # one D2H
             done = torch.cuda.Event()
             done.record()
-        self.h2d_bytes = self.X_sub.nbytes + self.Y_sub.nbytes + z.nbytes + psi_i.nbytes
-        self.d2h_bytes = host.numel() * 8
-        return (eng, d_in, packed, host, done)
+        self.h2d_bytes = shard_bytes + z.nbytes + psi_i.nbytes
+        self.d2h_bytes = h_out.numel() * 8
+        return (eng, d_in, (h_in, h_out), h_out, done)
 
     def collect(self, pending):
-        eng, d_in, _packed, host, done = pending
+        eng, d_in, pair, host, done = pending
         done.synchronize()
-        packed = host.numpy()
+        packed = host.numpy().copy()
+        eng.release(pair)
         p = eng.P
         theta_i, psi_new = packed[:p].copy(), packed[p:2 * p].copy()
         terms = packed[2 * p:2 * p + 4]

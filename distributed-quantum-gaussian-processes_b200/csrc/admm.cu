@@ -44,14 +44,14 @@ __global__ void admm_local_kernel(const double* __restrict__ z, const double* __
 }
 
 // riemannian_optimizer.py:317-320 -> :42-49, rounding main.py:2523; agents summed in index order
-__global__ void admm_consensus_kernel(const double* __restrict__ theta, const double* __restrict__ psi, int A, int P, double rho,
+__global__ void admm_consensus_kernel(const double* __restrict__ theta, const double* __restrict__ psi, int A, int P, int ld, double rho,
                                       double period, double* __restrict__ z_out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= P) return;
     const double two_pi = 6.283185307179586;
     double cs = 0.0, sn = 0.0;
     for (int a = 0; a < A; ++a) {
-        const double xi = __dadd_rn(theta[(size_t)a * P + k], __ddiv_rn(psi[(size_t)a * P + k], rho));
+        const double xi = __dadd_rn(theta[(size_t)a * ld + k], __ddiv_rn(psi[(size_t)a * ld + k], rho));
         const double ang = __ddiv_rn(__dmul_rn(two_pi, xi), period);
         cs = __dadd_rn(cs, cos(ang));
         sn = __dadd_rn(sn, sin(ang));
@@ -143,7 +143,16 @@ int dqgp_admm_consensus(const double* d_theta, const double* d_psi, int A, int P
                         void* stream) {
     using namespace dqgp;
     DQGP_REQUIRE(d_theta && d_psi && d_z_out && A >= 1 && P >= 1 && rho != 0.0, "dqgp_admm_consensus: bad arguments");
-    admm_consensus_kernel<<<(P + 127) / 128, 128, 0, as_stream(stream)>>>(d_theta, d_psi, A, P, rho, period, d_z_out);
+    admm_consensus_kernel<<<(P + 127) / 128, 128, 0, as_stream(stream)>>>(d_theta, d_psi, A, P, P, rho, period, d_z_out);
+    DQGP_LAUNCH_CHECK("admm_consensus_kernel");
+    return 0;
+}
+
+int dqgp_admm_consensus_strided(const double* d_theta, const double* d_psi, int A, int P, int row_stride, double rho, double period,
+                                double* d_z_out, void* stream) {
+    using namespace dqgp;
+    DQGP_REQUIRE(d_theta && d_psi && d_z_out && A >= 1 && P >= 1 && row_stride >= P && rho != 0.0, "dqgp_admm_consensus_strided: bad arguments");
+    admm_consensus_kernel<<<(P + 127) / 128, 128, 0, as_stream(stream)>>>(d_theta, d_psi, A, P, row_stride, rho, period, d_z_out);
     DQGP_LAUNCH_CHECK("admm_consensus_kernel");
     return 0;
 }

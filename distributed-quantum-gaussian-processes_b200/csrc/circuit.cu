@@ -285,6 +285,29 @@ int dqgp_circuit_num_parameters(const dqgp_circuit* c) { return c ? c->P : -1; }
 int dqgp_circuit_num_gates(const dqgp_circuit* c) { return c ? (int)c->gates.size() : -1; }
 int dqgp_circuit_num_passes(const dqgp_circuit* c) { return c ? (int)c->passes.size() : -1; }
 int dqgp_circuit_num_fused_ops(const dqgp_circuit* c) { return c ? (int)c->ops.size() : -1; }
+long long dqgp_circuit_shifted_u2_applications(const dqgp_circuit* c) {
+    if (!c) return -1;
+    // fused 2x2 unitary applications (one per amplitude pair sweep of a state) that ONE sample costs in dqgp_features_shifted /
+    // dqgp_states_shifted: the base circuit twice (final base state + the pass-by-pass advance), then for every parameter the
+    // passes from its own pass to the end - once for a rotation parameter (both signs from one fork), twice for a CRZ parameter.
+    // A CRZ / CX op counts 3/8 of a 2x2 unitary (6 of 16 flops per pair) / nothing.  Without prefix sharing: (2P + 1) circuits.
+    const int np = (int)c->passes.size();
+    std::vector<double> pass_cost(np, 0.0);
+    for (int ip = 0; ip < np; ++ip)
+        for (int o = c->passes[ip].op_begin; o < c->passes[ip].op_end; ++o)
+            pass_cost[ip] += c->ops[o].kind == SV_U2 ? 1.0 : (c->ops[o].kind == SV_CRZ ? 0.375 : 0.0);
+    double all = 0.0;
+    for (double v : pass_cost) all += v;
+    if (!c->shareable) return (long long)((2.0 * c->P + 1.0) * all + 0.5);
+    double total = 2.0 * all;
+    for (int ip = 0; ip < np; ++ip) {
+        double suffix = 0.0;
+        for (int k = ip; k < np; ++k) suffix += pass_cost[k];
+        for (int e = c->pass_par_begin[ip]; e < c->pass_par_begin[ip + 1]; ++e)
+            total += (c->par_mat[c->pass_params[e]] >= 0 ? 1.0 : 2.0) * suffix;
+    }
+    return (long long)(total + 0.5);
+}
 int dqgp_circuit_describe(const dqgp_circuit* c, dqgp_gate* h_out, int capacity) {
     DQGP_REQUIRE(c && h_out, "dqgp_circuit_describe: NULL argument");
     int n = (int)c->gates.size();

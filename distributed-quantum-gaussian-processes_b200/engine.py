@@ -126,12 +126,46 @@ class AgentEngine:
         self.entries_per_step = self.S * self.n * self.n    # full squares, all 2P+1 sets
         self.share_prefix = True
 
-    def load_data(self, X, Y):
-        """Refresh the resident shard from host arrays (the e2e path does this every call, like the
-        reference re-pickles X_i, Y_i to its workers every iteration, main.py:2530-2542)."""
-        self.d_X.copy_(torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64).reshape(self.n, self.d)).pin_memory(),
-                       non_blocking=True)
-        self.d_Y.copy_(torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)).pin_memory(), non_blocking=True)
+    def load_data(self, X, Y, always=False):
+        """Refresh the resident shard from host arrays through PERSISTENT pinned staging buffers (allocated once per engine:
+        a `pin_memory()` per call is a cudaHostAlloc, which cost 3% of an N=8 iteration in round 1).  The reference re-pickles
+        X_i, Y_i to its workers every iteration (main.py:2530-2542); here the shard stays resident on its GPU and is
+        re-uploaded only when the host arrays differ from the staged copy (an exact comparison, ~10 us for 8192 x 4) or
+        when `always` is set (the bench's e2e leg, whose contract counts the shard's H2D in every step).
+        Returns the bytes copied host -> device."""
+        if getattr(self, "_h_X", None) is None:
+            self._h_X = torch.empty((self.n, self.d), dtype=torch.float64).pin_memory()
+            self._h_Y = torch.empty((self.n,), dtype=torch.float64).pin_memory()
+            self._h_X_np, self._h_Y_np = self._h_X.numpy(), self._h_Y.numpy()
+            self._staged, self._upload_done = False, None
+        X = np.asarray(X, dtype=np.float64).reshape(self.n, self.d)
+        Y = np.asarray(Y, dtype=np.float64).reshape(-1)
+        if self._staged and not always and np.array_equal(X, self._h_X_np) and np.array_equal(Y, self._h_Y_np):
+            return 0
+        if self._upload_done is not None:
+            self._upload_done.synchronize()          # the previous async H2D must have read the staging buffers
+        np.copyto(self._h_X_np, X)
+        np.copyto(self._h_Y_np, Y)
+        self.d_X.copy_(self._h_X, non_blocking=True)
+        self.d_Y.copy_(self._h_Y, non_blocking=True)
+        self._upload_done = torch.cuda.Event()
+        self._upload_done.record()
+        self._staged = True
+        return X.nbytes + Y.nbytes
+
+    def staging(self):
+        """A free (in, out) pair of pinned host buffers for one train_and_update call: (2, P) for z / psi and the packed result
+        [theta, psi, nll terms(4), gradient, info].  Pairs are recycled through `release()`; a new pair is allocated only while
+        every existing one is in flight."""
+        if getattr(self, "_staging_pool", None) is None:
+            self._staging_pool = []
+        if self._staging_pool:
+            return self._staging_pool.pop()
+        return (torch.empty((2, self.P), dtype=torch.float64).pin_memory(),
+                torch.empty((3 * self.P + 5,), dtype=torch.float64).pin_memory())
+
+    def release(self, pair):
+        self._staging_pool.append(pair)
 
     # -- phases (each enqueues on the current stream) ----------------------------------------------------------
     def simulate(self, d_z, first=0, count=None):
@@ -243,8 +277,8 @@ def agent_block(rank, world_size, n_agents):
 
 
 def exchange_rows(full, local, group=None, world_size=1):
-    """The ONLY cross-agent exchange of the path (main.py:2523 / :2550-2555): gather every rank's (A_local, P) rows of
-    theta or psi into the replicated (A, P) array.  NCCL over NVLink for CUDA tensors, gloo in the CPU tests."""
+    """The ONLY cross-agent exchange of the path (main.py:2523 / :2550-2555): gather every rank's (A_local, ...) rows
+    (theta and psi side by side) into the replicated (A, ...) array.  NCCL over NVLink for CUDA tensors, gloo in the CPU tests."""
     if world_size == 1:
         full.copy_(local)
         return full
@@ -275,17 +309,18 @@ class AdmmEngine:
         self.agents = [AgentEngine(x, y, rho=rho, L=lips[self.first + i], **agent_kw) for i, (x, y) in enumerate(shards)]
         if any(a.P != self.P for a in self.agents):
             raise ValueError("theta0 does not match the circuit's parameter count")
-        self.theta = dev_f64(theta0)
-        self.psi = dev_f64(psi0)
-        self.z = torch.empty(self.P, dtype=torch.float64, device=self.theta.device)
-        self.local_theta = torch.empty((self.A_local, self.P), dtype=torch.float64, device=self.theta.device)
-        self.local_psi = torch.empty_like(self.local_theta)
+        # theta_a and psi_a side by side in ONE (A, 2, P) buffer: a single all-gather per iteration moves both
+        self.rows = dev_f64(np.stack([np.asarray(theta0, dtype=np.float64), np.asarray(psi0, dtype=np.float64)], axis=1))
+        self.theta, self.psi = self.rows[:, 0], self.rows[:, 1]              # (A, P) views, row stride 2P
+        self.z = torch.empty(self.P, dtype=torch.float64, device=self.rows.device)
+        self.local_rows = torch.empty((self.A_local, 2, self.P), dtype=torch.float64, device=self.rows.device)
+        self.local_theta, self.local_psi = self.local_rows[:, 0], self.local_rows[:, 1]
         self.streams = [torch.cuda.Stream() for _ in self.agents] if (streams and self.A_local > 1) else None
         self.entries_per_iteration = sum(a.entries_per_step for a in self.agents)
 
     def consensus(self):
-        check(self._lib.dqgp_admm_consensus(self.theta.data_ptr(), self.psi.data_ptr(), self.A_total, self.P, self.rho, PERIOD,
-                                            self.z.data_ptr(), stream_ptr()), "consensus")
+        check(self._lib.dqgp_admm_consensus_strided(self.theta.data_ptr(), self.psi.data_ptr(), self.A_total, self.P, 2 * self.P, self.rho,
+                                                    PERIOD, self.z.data_ptr(), stream_ptr()), "consensus")
 
     def _local_part(self):
         """Consensus z (replicated, from the gathered theta/psi) and every local agent's step: device work only."""
@@ -307,8 +342,7 @@ class AdmmEngine:
                 main.wait_event(done)
 
     def _exchange(self):
-        exchange_rows(self.theta, self.local_theta, self.pg, self.world)
-        exchange_rows(self.psi, self.local_psi, self.pg, self.world)
+        exchange_rows(self.rows, self.local_rows, self.pg, self.world)      # ONE collective: (A_local, 2, P) -> (A, 2, P)
 
     def iteration(self):
         self._local_part()
@@ -320,10 +354,10 @@ class AdmmEngine:
         outside the graph (an in-place copy on one rank, the NCCL all-gather on several).  The warm-up iteration that capture
         needs (lazy uploads, function attributes) does NOT advance the run: theta / psi / z are restored afterwards, so
         capture() + k replays walks exactly k iterations, like k eager iteration() calls."""
-        keep = [t.clone() for t in (self.theta, self.psi, self.z, self.local_theta, self.local_psi)]
+        keep = [t.clone() for t in (self.rows, self.z, self.local_rows)]
         self.iteration()                         # warm-up
         torch.cuda.synchronize()
-        for t, k in zip((self.theta, self.psi, self.z, self.local_theta, self.local_psi), keep):
+        for t, k in zip((self.rows, self.z, self.local_rows), keep):
             t.copy_(k)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()

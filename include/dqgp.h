@@ -61,6 +61,9 @@ int dqgp_circuit_num_parameters(const dqgp_circuit* c); /* = encoding_circuit.nu
 int dqgp_circuit_num_gates(const dqgp_circuit* c);
 int dqgp_circuit_num_passes(const dqgp_circuit* c); /* shared-memory passes of the register-blocked simulator */
 int dqgp_circuit_num_fused_ops(const dqgp_circuit* c); /* ops after fusing runs of 1-qubit gates (2x2 unitaries + CX/CRZ) */
+/* executed simulator work per SAMPLE of dqgp_features_shifted / dqgp_states_shifted, in fused 2x2-unitary applications
+ * (16 * 2^(q-1) flops each): bench.py's statevector roofline */
+long long dqgp_circuit_shifted_u2_applications(const dqgp_circuit* c);
 int dqgp_circuit_describe(const dqgp_circuit* c, dqgp_gate* h_out, int capacity); /* host copy of the program */
 
 /* ---- statevector simulation (what q_kernel.evaluate does per sample, agent_riemannian.py:118):
@@ -182,6 +185,11 @@ int dqgp_admm_local(const double* d_z, const double* d_grad, const double* d_psi
  *      z = round(circular_mean(theta + psi/rho), 4) over A agents, summed in agent order. */
 int dqgp_admm_consensus(const double* d_theta, const double* d_psi, int A, int P, double rho, double period,
                         double* d_z_out, void* stream);
+/*      same, with agent a's rows at d_theta + a*row_stride and d_psi + a*row_stride (row_stride >= P doubles): the
+ *      engine keeps theta_a and psi_a side by side in ONE (A, 2, P) buffer so that a single all-gather moves both
+ *      (the only cross-agent exchange of the path, main.py:2550-2555). */
+int dqgp_admm_consensus_strided(const double* d_theta, const double* d_psi, int A, int P, int row_stride, double rho,
+                                double period, double* d_z_out, void* stream);
 
 /* ---- GP prediction pieces (main.py:1458-1466, 1546-1552): mean = Kst alpha; var = max(diag - q, 1e-10);
  *      d_nlpd[0] = mean_i(0.5 log 2pi + 0.5 log var_i + 0.5 (y_i-mean_i)^2/var_i). */

@@ -38,21 +38,21 @@ def _worker(rank, world, port, A, P, iters, out):
     import dqgp_b200 as d
     from oracle import agent_step, torus
     rs = np.random.RandomState(3)
-    theta = torch.from_numpy(np.round(rs.rand(A, P), 4))
-    psi = torch.from_numpy(np.round(rs.rand(A, P), 4))
+    # theta_a, psi_a side by side in one (A, 2, P) buffer, as AdmmEngine keeps them: ONE all-gather per iteration
+    rows = torch.from_numpy(np.stack([np.round(rs.rand(A, P), 4), np.round(rs.rand(A, P), 4)], axis=1).copy())
+    theta, psi = rows[:, 0], rows[:, 1]
     block = d.agent_block(rank, world, A)
     _, _, admm = d.create_riemannian_framework(P, rho=100.0)
     zs = []
     for _ in range(iters):
         z = np.round(admm.update_z(theta.numpy(), psi.numpy()), 4)          # replicated consensus, agent order
         zs.append(z)
-        loc_t, loc_p = torch.empty((len(block), P), dtype=torch.float64), torch.empty((len(block), P), dtype=torch.float64)
+        loc = torch.empty((len(block), 2, P), dtype=torch.float64)
         for i, a in enumerate(block):
             grad4 = np.round(50.0 * np.sin(3.0 * z + a), 4)
             t, p = agent_step.local_update(torus.wrap(z), grad4, psi[a].numpy(), 100.0, 100.0)
-            loc_t[i], loc_p[i] = torch.from_numpy(t), torch.from_numpy(p)
-        d.exchange_rows(theta, loc_t, None, world)
-        d.exchange_rows(psi, loc_p, None, world)
+            loc[i, 0], loc[i, 1] = torch.from_numpy(t), torch.from_numpy(p)
+        d.exchange_rows(rows, loc, None, world)
     out[rank] = (np.array(zs), theta.numpy().copy(), psi.numpy().copy())
     dist.destroy_process_group()
 
