@@ -221,9 +221,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
             for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const double kv = (OUTER == DQGP_OUTER_GAUSSIAN)
-                                          ? fast_exp_tab5(CLAMP ? fmax(c[rb][cb][e], -700.0) : c[rb][cb][e], tab)
-                                          : outer_from_neg_gd2<OUTER>(c[rb][cb][e], hyp, tab);
+                    const double kv = outer_grad_from_neg_gd2<OUTER, CLAMP>(c[rb][cb][e], hyp, tab);
                     part = fma(br[rb][cb][e], kv, part);
                 }
         if (tt & 1) {
@@ -501,7 +499,10 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
         const long long rows = (long long)(2 * P + 1) * n;
         feature_norms_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d_F, rows, m, norms);
         // Pauli features lie in [-1, 1]: gamma d^2 <= 4 m gamma, so the exponent guard is only needed for large gamma
-        const bool no_clamp = outer == DQGP_OUTER_GAUSSIAN && hyp.a > 0.0 && 4.0 * m * hyp.a < 650.0;
+        // the exponent's argument is bounded below by -gamma 4m (Gaussian), -sqrt(3) 2 sqrt(m) / l (Matern), -2 / l^2 (ExpSineSquared)
+        const double worst = outer == DQGP_OUTER_GAUSSIAN ? 4.0 * m * hyp.a
+                             : outer == DQGP_OUTER_MATERN15 ? 1.7320508075688772 * 2.0 * sqrt((double)m) * hyp.a : 2.0 * hyp.a * hyp.a;
+        const bool no_clamp = hyp.a > 0.0 && worst < 650.0;
 #define DQGP_G2(OUT)                                                                                                         \
     do {                                                                                                                     \
         static bool attr_done_dev[64] = {false};        /* the attribute is per DEVICE (as gemm_init's flags) */            \

@@ -113,6 +113,41 @@ __device__ __forceinline__ double outer_from_neg_gd2(double v, const OuterHyp& h
     }
 }
 
+// sqrt for the fused gradient's Matern / ExpSineSquared path: MUFU.RSQ64H seed (20 bits), one Newton step on y ~ 1/sqrt(x),
+// one residual correction on s = x y: 8 FP64-pipe instructions, <= 1 ulp on normal x > 0, no range branch (libm's sqrt
+// carries a slow-path call and measured 16 DFMA-equivalents in this loop, profiles/r01_fp64_peak.json).  The guard that keeps
+// x away from zero / tiny negative rounding residue of the Gram identity is an INTEGER compare on the high word (ALU pipe,
+// not the FP64 pipe that bounds the kernel); NaN passes through (np.sqrt(nan) = nan, as in the reference).
+__device__ __forceinline__ double fast_sqrt_guarded(double x) {
+    if (__double2hiint(x) < 0x01a56e1f) x = 1e-300;            // x < ~1e-300, zero, or negative -> sqrt ~ 1e-150 (= 0 for every use here)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double r = x * y;
+    const double e = fma(-r, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    double s = x * y;
+    const double e2 = fma(-s, s, x);
+    return fma(e2, 0.5 * y, s);
+}
+
+// The fused gradient's outer kernel from v = -gamma_eff d^2: same formulas as outer_from_neg_gd2, built for the FP64 pipe that
+// bounds grad_projected_dmma_kernel: branch-free sqrt (above), degree-5 table exp (10 instructions), (1 + k) e^-k as one FMA,
+// and no exponent clamp when the host has shown the argument cannot go below -700 (CLAMP = false; features lie in [-1, 1]).
+template <int OUTER, bool CLAMP>
+__device__ __forceinline__ double outer_grad_from_neg_gd2(double v, const OuterHyp& h, double tab) {
+    if (OUTER == DQGP_OUTER_GAUSSIAN) {
+        return fast_exp_tab5(CLAMP ? fmax(v, -700.0) : v, tab);
+    } else if (OUTER == DQGP_OUTER_MATERN15) {
+        const double nk = fast_sqrt_guarded(-v) * (-1.7320508075688772 * h.a);      // -sqrt(3) d / l
+        const double e = fast_exp_tab5(CLAMP ? fmax(nk, -700.0) : nk, tab);
+        return fma(-nk, e, e);
+    } else {
+        const double sn = sin(fast_sqrt_guarded(-v) * h.b) * h.a;
+        const double x = -2.0 * (sn * sn);
+        return fast_exp_tab5(CLAMP ? fmax(x, -700.0) : x, tab);
+    }
+}
+
 // DMMA fidelity kernels (fid.cu)
 int fidelity_gram_dmma(const double* Psi1, int n1, const double* Psi2, int n2, int dim, double* K, int ldk, cudaStream_t st);
 int fidelity_grad_dmma(const double* Ainv, int ld, const double* alpha, const double* Psi, int n, int dim, int P, double* partial,
