@@ -62,6 +62,10 @@ SIGNATURES = {
     "dqgp_solver_quadform_rows": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "dqgp_solver_quadform_rows_inplace": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "dqgp_solver_apply_factor": (_i, [_vp, _vp, _vp, _vp]),
+    "dqgp_lu_workspace_bytes": (_sz, [_i]),
+    "dqgp_lu_solve_inv": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "dqgp_dgemm_general": (_i, [_i, _i, _i, _d, _vp, _i, _vp, _i, _d, _vp, _i, _vp]),
+    "dqgp_rowdot": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "dqgp_dgemm": (_i, [_i, _i, _i, _i, _i, _d, _vp, _i, _vp, _i, _d, _vp, _i, _vp]),
     "dqgp_shift_parameter_sets": (_i, [_vp, _i, _d, _d, _vp, _vp]),
     "dqgp_grad_workspace_bytes": (_sz, [_i, _i]),

@@ -9,7 +9,8 @@ reference pickles the same data to its worker processes every iteration) and rea
 Reference behaviours kept: only the (2P+1)-evaluation central-difference path exists (Q3/Q4); training
 Grams use the Gaussian outer kernel whatever ``outer_kernel`` says (Q1) unless
 ``training_ignores_outer_kernel=False``; gradient, theta_i and psi_i are rounded to 4 decimals (Q5);
-``riemannian_*`` arguments are accepted and inert (Q8).  Deviation, documented: ``condition_number`` is NaN
+``riemannian_*`` arguments are accepted and inert (Q8); a failed Cholesky walks the reference's LU rung on the device
+(``agent_riemannian.py:419-425``).  Deviation, documented: ``condition_number`` is NaN
 unless ``compute_condition_number=True`` (the reference's ``np.linalg.cond`` is an O(n^3) SVD used only in
 prints, main.py:2629-2642).
 """
@@ -140,9 +141,17 @@ class RiemannianAgent:
         self.last_gradient = packed[2 * p + 4:3 * p + 4].copy()
         info = int(packed[-1])
         if info != 0:
-            # the reference falls back to LU and then pinv here (agent_riemannian.py:419-428); this engine has
-            # no CPU path by design, so the failure is surfaced instead.
-            raise np.linalg.LinAlgError(f"Agent {self.agent_id}: Cholesky failed at pivot {info} (K + sigma^2 I not SPD)")
+            # np.linalg.cholesky raised in the reference: its except-branch refactors with LU (agent_riemannian.py:419-425).
+            # Same here, on the device: full symmetric Gram, partial-pivoting LU, alpha / explicit inverse / slogdet.
+            d_out = eng._d_out
+            eng.step_fallback(d_in[0], d_in[1], d_out[:p], d_out[p:2 * p])
+            d_out[2 * p:2 * p + 4].copy_(eng.d_nll)
+            d_out[2 * p + 4:3 * p + 4].copy_(eng.d_grad)
+            packed = d_out.cpu().numpy()
+            theta_i, psi_new = packed[:p].copy(), packed[p:2 * p].copy()
+            terms = packed[2 * p:2 * p + 4]
+            self.last_gradient = packed[2 * p + 4:3 * p + 4].copy()
+            self.used_lu_fallback = True
         cond = float("nan")
         if self.compute_condition_number:
             eng.simulate(d_in[0]); eng.gram()      # the solver matrix holds L after the step: rebuild K for the diagnostic

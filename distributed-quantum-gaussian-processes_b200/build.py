@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libdqgp.so")
 # statevec.cu is compiled once per group of entry points (-DDQGP_SV_PART=k): its twelve qubit counts x kernel variants take
 # 2.6 minutes in one translation unit
 SOURCES = ["circuit.cu", ("statevec.cu", 1), ("statevec.cu", 2), ("statevec.cu", 3), ("statevec.cu", 4), ("statevec.cu", 5),
-           "gram.cu", "gemm64.cu", "chol.cu", "grad.cu", "fid.cu", "admm.cu", "api.cu"]
+           "gram.cu", "gemm64.cu", "chol.cu", "lu.cu", "grad.cu", "fid.cu", "admm.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 
@@ -40,6 +40,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
+    headers_mtime = max([os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if f.endswith(".cuh")] +
+                        [os.path.getmtime(os.path.join(HERE, "..", "include", "dqgp.h"))])
+    if os.environ.get("DQGP_NVCC_EXTRA"):
+        force = True
 
     def compile_one(src):
         part = []
@@ -49,6 +53,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             part = [f"-DDQGP_SV_PART={k}"]
         else:
             obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        # incremental: an object is rebuilt when its source or any header (csrc/*.cuh, include/dqgp.h) is newer
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(os.path.join(CSRC, src)), headers_mtime):
+            return obj
         cmd = [nvcc, *NVCC_FLAGS, *part, *os.environ.get("DQGP_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

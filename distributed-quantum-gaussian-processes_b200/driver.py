@@ -43,9 +43,8 @@ def run_admm(shards, *, encoding_type, kernel_type, num_qubits, num_layers, nois
     while True:
         it += 1
         eng.iteration()
+        eng.repair_failed_agents()          # Cholesky failures walk the reference's LU ladder (agent_riemannian.py:419-425)
         z, theta, psi, nll = eng.state()
-        for a in eng.agents:
-            a.check_info()
         rec = {"iteration": it, "z": z.copy(), "theta": theta.copy(), "psi": psi.copy(), "nll": nll.copy(), "cv": None}
         if cv_data is not None:
             cv = k_fold_cross_validation_consensus(cv_data[0], cv_data[1], z, num_qubits, num_layers, noise_std, k_folds=cv_folds,

@@ -189,11 +189,13 @@ class AgentEngine:
         check(fn(self.circuit.handle, self.d_X.data_ptr(), self.n, self.d_Pm[first].data_ptr(), count,
                  self.d_feat[first].data_ptr(), st), "statevector")
 
-    def gram(self):
+    def gram(self, full=False):
+        """Unshifted Gram + sigma^2 I into the solver matrix: the lower 64x64 tiles only (all the Cholesky reads), or, for the
+        LU fallback, the whole symmetric matrix (`full`)."""
         lib, st, s = self._lib, stream_ptr(), self.solver
         base = self.d_feat.data_ptr()          # set 0 = unshifted parameters
         if self.kernel_type == "projected":
-            check(lib.dqgp_gram_projected(self._outer_id, self._hyp, base, self.n, base, self.n, self.m, s.matrix_ptr, s.ld, 2, st),   # lower tiles only
+            check(lib.dqgp_gram_projected(self._outer_id, self._hyp, base, self.n, base, self.n, self.m, s.matrix_ptr, s.ld, 1 if full else 2, st),
                   "gram projected")
         else:
             check(lib.dqgp_gram_fidelity(base, self.n, base, self.n, 1 << self.q, s.matrix_ptr, s.ld, 1, st), "gram fidelity")
@@ -204,6 +206,32 @@ class AgentEngine:
         check(self._lib.dqgp_potrf_solve_inv(self.solver.handle, self.d_Y.data_ptr(), self.d_alpha.data_ptr(),
                                              self.d_logdet.data_ptr(), self.d_info.data_ptr(), 2 if self.gradient_mode == "analytic" else 1,
                                              stream_ptr()), "potrf")
+
+    def factor_lu(self):
+        """The reference's fallback when np.linalg.cholesky raises (agent_riemannian.py:419-425): partial-pivoting LU of
+        C + sigma^2 I (needs `gram(full=True)`), alpha and the explicit inverse by the two triangular solves, and
+        slogdet for the NLL (:442-444).  A non-positive determinant gives NaN: the reference then takes
+        log(det(C + 1e-8 I)) of a non-positive number (:444).  The third rung, np.linalg.pinv (:427-428), is reached in the
+        reference only when LAPACK raises on non-finite input; here non-finite input propagates NaN."""
+        lib, st, s = self._lib, stream_ptr(), self.solver
+        if getattr(self, "d_lu_work", None) is None:
+            self.d_lu_work = torch.empty(int(lib.dqgp_lu_workspace_bytes(self.n)) // 8 + 2, dtype=torch.float64, device=self.d_X.device)
+            self.d_slogdet = torch.empty(2, dtype=torch.float64, device=self.d_X.device)
+        check(lib.dqgp_lu_solve_inv(s.matrix_ptr, s.ld, self.n, self.d_Y.data_ptr(), self.d_alpha.data_ptr(), s.inverse_ptr, s.ld,
+                                    self.d_slogdet.data_ptr(), self.d_lu_work.data_ptr(), st), "lu fallback")
+        nan = torch.full((), float("nan"), dtype=torch.float64, device=self.d_X.device)
+        self.d_logdet.copy_(torch.where(self.d_slogdet[1] > 0, self.d_slogdet[0], nan).reshape(1))
+        self.d_info.zero_()
+        self.used_lu_fallback = True
+
+    def step_fallback(self, d_z, d_psi, d_theta_out, d_psi_out):
+        """Redo a step whose Cholesky failed (`check_info` / d_info > 0) down the reference's ladder: same parameter sets and
+        features, full symmetric Gram, LU instead of Cholesky, then the same fused gradient / NLL / local update."""
+        self.simulate(d_z)
+        self.gram(full=True)
+        self.factor_lu()
+        self.gradient()
+        self.update(d_psi, d_theta_out, d_psi_out)
 
     def gradient(self):
         lib, st, s = self._lib, stream_ptr(), self.solver
@@ -315,6 +343,7 @@ class AdmmEngine:
         self.z = torch.empty(self.P, dtype=torch.float64, device=self.rows.device)
         self.local_rows = torch.empty((self.A_local, 2, self.P), dtype=torch.float64, device=self.rows.device)
         self.local_theta, self.local_psi = self.local_rows[:, 0], self.local_rows[:, 1]
+        self._psi_before = torch.empty((self.A_local, self.P), dtype=torch.float64, device=self.rows.device)
         self.streams = [torch.cuda.Stream() for _ in self.agents] if (streams and self.A_local > 1) else None
         self.entries_per_iteration = sum(a.entries_per_step for a in self.agents)
 
@@ -325,6 +354,7 @@ class AdmmEngine:
     def _local_part(self):
         """Consensus z (replicated, from the gathered theta/psi) and every local agent's step: device work only."""
         self.consensus()
+        self._psi_before.copy_(self.psi[self.first:self.first + self.A_local])     # what repair_failed_agents restarts from
         if self.streams is None:
             for i, ag in enumerate(self.agents):
                 ag.step(self.z, self.psi[self.first + i], self.local_theta[i], self.local_psi[i])
@@ -347,6 +377,24 @@ class AdmmEngine:
     def iteration(self):
         self._local_part()
         self._exchange()
+
+    def repair_failed_agents(self):
+        """Host check after an iteration (synchronises): every local agent whose Cholesky reported a non-positive pivot redoes
+        its step down the reference's LU ladder (agent_riemannian.py:419-425) from the same z and psi, and the rows are
+        exchanged again.  Returns the number of agents repaired on this rank (collective when world_size > 1: every rank
+        must call it)."""
+        infos = torch.stack([a.d_info[0] for a in self.agents]).cpu().numpy()
+        bad = [i for i, v in enumerate(infos) if v != 0]
+        for i in bad:
+            # psi row of the agent as it was BEFORE this iteration's exchange overwrote it: kept in psi_before
+            self.agents[i].step_fallback(self.z, self._psi_before[i], self.local_theta[i], self.local_psi[i])
+        n_bad = torch.tensor([len(bad)], device=self.rows.device)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(n_bad, group=self.pg)
+        if int(n_bad.item()) > 0:
+            self._exchange()
+        return len(bad)
 
     def capture(self):
         """Capture the device part of one iteration (consensus, all local agents, their streams and the solver's internal

@@ -88,14 +88,35 @@ def predict_quantum_gp(X_train, Y_train, X_test, quantum_kernel_params, num_qubi
                                   d_yt.data_ptr() if d_yt is not None else None, mean.data_ptr(), var.data_ptr(),
                                   nlpd_buf.data_ptr() if nlpd_buf is not None else None, st), "predict finish")
     if int(info.item()) != 0:
-        raise RuntimeError("Cholesky failed: training kernel matrix is not positive definite "
-                           "(the reference's np.linalg.inv fallback, main.py:1479-1486, is not on the GPU path)")
+        # np.linalg.cholesky raised in the reference: its except-branch inverts directly (main.py:1479-1486):
+        #   a_inv = np.linalg.inv(K);  alpha = a_inv @ y;  mean = K_st @ alpha;  var = max(diag(K_ss - K_st a_inv K_st^T), 1e-10)
+        # np.linalg.inv is a partial-pivoting LU (getrf + getri): the same factorisation runs here on the device.
+        if lean:
+            raise RuntimeError("Cholesky failed: training kernel matrix is not positive definite, and the LU fallback "
+                               "(main.py:1479-1486) needs the three-square workspace: call with lean=False")
+        qk.evaluate_device(d_xtr, d_xtr, d_p, same=True, out=k_tt, ld=solver.ld)           # both triangles
+        check(lib.dqgp_add_diagonal(solver.matrix_ptr, n, solver.ld, float(noise_std) ** 2, st), "add diagonal")
+        check(lib.dqgp_add_diagonal(solver.matrix_ptr, n, solver.ld, 1e-6, st), "add diagonal")
+        work = torch.empty(int(lib.dqgp_lu_workspace_bytes(n)) // 8 + 2, **f64)
+        check(lib.dqgp_lu_solve_inv(solver.matrix_ptr, solver.ld, n, None, None, solver.inverse_ptr, solver.ld, None, work.data_ptr(), st),
+              "lu fallback")
+        check(lib.dqgp_dgemm_general(n, 1, n, 1.0, solver.inverse_ptr, solver.ld, d_y.data_ptr(), 1, 0.0, alpha.data_ptr(), 1, st),
+              "alpha = A^-1 y")
+        t_rows = torch.empty((nt, n), **f64)
+        check(lib.dqgp_dgemm_general(nt, n, n, 1.0, k_st.data_ptr(), n, solver.inverse_ptr, solver.ld, 0.0, t_rows.data_ptr(), n, st),
+              "K_st A^-1")
+        check(lib.dqgp_rowdot(t_rows.data_ptr(), n, k_st.data_ptr(), n, nt, n, quad.data_ptr(), st), "diag(K_st A^-1 K_st^T)")
+        check(lib.dqgp_predict_finish(kst_ptr, nt, n, ldk_arg, alpha.data_ptr(), kss_diag.data_ptr(), quad.data_ptr(),
+                                      d_yt.data_ptr() if d_yt is not None else None, mean.data_ptr(), var.data_ptr(),
+                                      nlpd_buf.data_ptr() if nlpd_buf is not None else None, st), "predict finish")
+        predict_quantum_gp.used_lu_fallback = True
     predict_quantum_gp.last_nlpd = float(nlpd_buf[0].item()) if nlpd_buf is not None else None
     k_ss = qk.evaluate_device(d_xte, d_xte, d_p, same=True).cpu().numpy() if return_kernels else None
     return (mean.cpu().numpy(), var.cpu().numpy(), k_tt_host, k_st.cpu().numpy() if return_kernels else None, k_ss)
 
 
 predict_quantum_gp.last_nlpd = None
+predict_quantum_gp.used_lu_fallback = False
 
 
 def _self_kernel_diag(qk, d_x, d_p):

@@ -134,6 +134,25 @@ int dqgp_solver_quadform_rows(dqgp_solver* s, const double* d_B, int nb, int ldb
  * (synchronises `stream` then; not graph-capturable at that moment). */
 int dqgp_solver_quadform_rows_inplace(dqgp_solver* s, double* d_B, int nb_pad, int ldb, double* d_out, void* stream);
 
+/* ---- the reference's fallback ladder when np.linalg.cholesky raises (`info` > 0 above):
+ *      agent step: scipy.linalg.lu_factor + lu_solve for alpha and for the explicit inverse against eye(n), then slogdet
+ *      (agent_riemannian.py:419-425, :442); prediction: np.linalg.inv = getrf + getri (main.py:1479-1486).
+ *      dqgp_lu_solve_inv factors d_A (n x n, row-major, leading dimension lda; BOTH triangles must be filled) in place as
+ *      P A = L U with partial pivoting (LAPACK's pivot rule), and writes - each optional, pass NULL to skip -
+ *      d_alpha = A^-1 y (by the two triangular solves, as lu_solve), d_Ainv = A^-1 (n x n, leading dimension ldi),
+ *      d_slogdet[2] = {log|det A|, sign(det A)} (numpy.linalg.slogdet).  d_work: dqgp_lu_workspace_bytes(n) bytes.
+ *      Stream-ordered, no host synchronisation, deterministic.  The third rung (np.linalg.pinv, :427-428) is only reached
+ *      when LAPACK raises on non-finite input; non-finite input propagates NaN here instead.
+ *      This is the exception path (e.g. ExpSineSquared Grams are indefinite): correct and O(n^3), not tuned to a roofline. */
+size_t dqgp_lu_workspace_bytes(int n);
+int dqgp_lu_solve_inv(double* d_A, int lda, int n, const double* d_y, double* d_alpha, double* d_Ainv, int ldi,
+                      double* d_slogdet, void* d_work, void* stream);
+/*      helpers of the prediction fallback (main.py:1482-1486: mean = K_st (A^-1 y), var = diag(K_ss - K_st A^-1 K_st^T)):
+ *      C = beta C + alpha A B for row-major operands of any size; out[i] = <T[i,:], K[i,:]>. */
+int dqgp_dgemm_general(int M, int N, int K, double alpha, const double* d_A, int lda, const double* d_B, int ldb,
+                       double beta, double* d_C, int ldc, void* stream);
+int dqgp_rowdot(const double* d_T, int ldt, const double* d_K, int ldk, int rows, int n, double* d_out, void* stream);
+
 /* fp64 GEMM building block on the DMMA tensor path (used by the factorisation; exposed for tests):
  * C(MxN) = alpha*A*B + beta*C; A is [m][k] if a_k_contig else [k][m]; B is [n][k] if b_k_contig else [k][n].
  * M, N multiples of 128; K multiple of 16; even leading dimensions; 16-byte aligned pointers.

@@ -413,3 +413,64 @@ def test_fused_gradient_honoured_outer_kernels_match_oracle(d, outer, enc, q, dd
         torch.cuda.synchronize(); eng.check_info()
         assert np.max(np.abs(eng.d_grad.cpu().numpy() - grad_ref)) < 1e-8 * max(1.0, np.abs(grad_ref).max())
         assert abs(float(eng.d_nll[3].item()) - comp["total"]) < 1e-8 * max(1.0, abs(comp["total"]))
+    else:                          # indefinite: the Cholesky must report it, and the LU rung (as the oracle's gp_terms) must agree
+        eng.gram(); eng.factor()
+        torch.cuda.synchronize()
+        assert int(eng.d_info.item()) > 0
+        eng.gram(full=True); eng.factor_lu(); eng.gradient()
+        torch.cuda.synchronize()
+        assert np.max(np.abs(eng.d_alpha.cpu().numpy() - alpha)) < 1e-8 * np.abs(alpha).max()
+        assert np.max(np.abs(eng.d_grad.cpu().numpy() - grad_ref)) < 1e-8 * max(1.0, np.abs(grad_ref).max())
+        if np.isfinite(comp["total"]):
+            assert abs(float(eng.d_nll[3].item()) - comp["total"]) < 1e-8 * max(1.0, abs(comp["total"]))
+
+
+@pytest.mark.parametrize("n", [1, 5, 33, 64, 100, 257, 700])
+@pytest.mark.parametrize("kind", ["indefinite", "general"])
+def test_lu_solve_inv_matches_lapack(d, n, kind):
+    """dqgp_lu_solve_inv (the reference's LU rung, agent_riemannian.py:419-425 / main.py:1479-1486) against LAPACK through
+    SciPy / NumPy: alpha = lu_solve(lu_factor(A), y), A^-1 = lu_solve(lu, eye), slogdet."""
+    from scipy.linalg import lu_factor, lu_solve
+    rng = np.random.default_rng(n)
+    if kind == "indefinite":
+        q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        lam = rng.uniform(0.5, 20.0, n) * np.where(rng.random(n) < 0.3, -1.0, 1.0)
+        A = (q * lam) @ q.T
+        A = 0.5 * (A + A.T)
+    else:
+        A = rng.standard_normal((n, n)) + 0.1 * np.eye(n)
+    y = rng.standard_normal(n)
+    lu = lu_factor(A)
+    alpha_ref, inv_ref = lu_solve(lu, y), lu_solve(lu, np.eye(n))
+    sign_ref, logabs_ref = np.linalg.slogdet(A)
+    ld = n + 3                                   # a leading dimension that is not n
+    f64 = dict(dtype=torch.float64, device="cuda")
+    dA = torch.zeros((n, ld), **f64); dA[:, :n] = torch.from_numpy(A).cuda()
+    dinv, dalpha, dsl = torch.full((n, ld), 7.0, **f64), torch.empty(n, **f64), torch.empty(2, **f64)
+    lib = d.load()
+    work = torch.empty(int(lib.dqgp_lu_workspace_bytes(n)) // 8 + 2, **f64)
+    dy = torch.from_numpy(y).cuda()
+    assert lib.dqgp_lu_solve_inv(dA.data_ptr(), ld, n, dy.data_ptr(), dalpha.data_ptr(), dinv.data_ptr(), ld, dsl.data_ptr(),
+                                 work.data_ptr(), _sp()) == 0
+    torch.cuda.synchronize()
+    scale = np.abs(inv_ref).max()
+    assert np.max(np.abs(dinv[:, :n].cpu().numpy() - inv_ref)) < 1e-9 * scale
+    assert torch.all(dinv[:, n:] == 7.0)                                      # nothing written past the n columns
+    assert np.max(np.abs(dalpha.cpu().numpy() - alpha_ref)) < 1e-9 * max(1.0, np.abs(alpha_ref).max())
+    sl = dsl.cpu().numpy()
+    assert sl[1] == sign_ref and abs(sl[0] - logabs_ref) < 1e-10 * max(1.0, abs(logabs_ref))
+    # the L and U factors themselves equal LAPACK's (same pivot rule): compare the packed factor
+    assert np.max(np.abs(dA[:, :n].cpu().numpy() - lu[0])) < 1e-9 * max(1.0, np.abs(lu[0]).max())
+
+
+def test_dgemm_general_and_rowdot(d):
+    rng = np.random.default_rng(1)
+    M, N, K = 37, 91, 53
+    A, B, C = rng.standard_normal((M, K)), rng.standard_normal((K, N)), rng.standard_normal((M, N))
+    dA, dB, dC = (torch.from_numpy(v).cuda() for v in (A, B, C))
+    lib = d.load()
+    assert lib.dqgp_dgemm_general(M, N, K, -0.5, dA.data_ptr(), K, dB.data_ptr(), N, 2.0, dC.data_ptr(), N, _sp()) == 0
+    assert np.max(np.abs(dC.cpu().numpy() - (2.0 * C - 0.5 * A @ B))) < 1e-12
+    out = torch.empty(M, dtype=torch.float64, device="cuda")
+    assert lib.dqgp_rowdot(dA.data_ptr(), K, dA.data_ptr(), K, M, K, out.data_ptr(), _sp()) == 0
+    assert np.max(np.abs(out.cpu().numpy() - (A * A).sum(axis=1))) < 1e-12
