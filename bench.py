@@ -205,17 +205,18 @@ def run_ours(args, w):
     gram_entries = 64 * 64 * t64 * (t64 + 1) // 2 if w["kernel"] == "projected" else n_i * n_i
     # statevector: SURVEY 8(d) counts 14 * 2^q flops per gate per state over all S * n states (what a per-set simulation does);
     # the engine executes far fewer (shared circuit prefixes, both signs of a parameter from one fork, fused 1-qubit runs):
-    # `executed` = 16 * 2^(q-1) flops per fused 2x2 unitary application, counted by the library's own plan
+    # `executed` = 32 * 2^(q-1) flops (16 FMA per amplitude pair, FMA = 2) per fused 2x2 unitary application, counted by the
+    # library's own plan
     lib = d.load()
     circ = ag.circuit
     sv_alg = float(S) * n_i * circ.num_gates * 14.0 * (1 << w["q"])
-    sv_exec = float(n_i) * lib.dqgp_circuit_shifted_u2_applications(circ.handle) * 16.0 * (1 << (w["q"] - 1))
+    sv_exec = float(n_i) * lib.dqgp_circuit_shifted_u2_applications(circ.handle) * 32.0 * (1 << (w["q"] - 1))
     roof = {
         "statevector": {"bound": "fp64", "achieved": sv_alg / (phases["statevector"] * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                         "executed": sv_exec / (phases["statevector"] * 1e-3) / 1e12,
                         "note": "achieved = SURVEY 8(d) algorithmic flops (14 * 2^q per gate per state, S * n states: a per-set simulation) / time, "
                                 "can exceed the peak because prefix sharing and the linear-combination forks skip work; executed = fused 2x2 "
-                                "unitary applications of the plan x 16 * 2^(q-1) flops (Pauli-feature epilogues not counted) / time"},
+                                "unitary applications of the plan x 32 * 2^(q-1) flops (16 FMA per pair; Pauli-feature epilogues not counted) / time"},
         "gradient": {"bound": "fp64", "achieved": grad_flops / (phases["gradient"] * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                      "executed": 0.5 * (1.0 + 1.0 / t64) * grad_flops / (phases["gradient"] * 1e-3) / 1e12,
                      "note": "achieved = algorithmic flops (SURVEY 8d: full squares, transcendental = 1 flop) / time; executed = the lower "
@@ -238,7 +239,7 @@ def run_ours(args, w):
     traffic = load_json(os.path.join(ROOT, "profiles", "r01_traffic.json"), {})
     primary.update({"kernel": {"gradient": "grad_projected_dmma_kernel" if w["kernel"] == "projected" else "fidelity_dmma_kernel<1>",
                                "factor": "gemm_group_kernel", "gram": "gram_projected_dmma_kernel",
-                               "statevector": "statevec_lc_kernel<%d>" % w["q"]}[dominant], "phase": dominant,
+                               "statevector": ("statevec_lc2_kernel<%d>" if w["q"] >= 9 else "statevec_lc_kernel<%d>") % w["q"]}[dominant], "phase": dominant,
                     "traffic": None, "peak_source": "profiles/r01_fp64_peak.json (measured on this pool: pure DMMA/DFMA issue loops)"
                     if primary["bound"] != "hbm" else "MEASURED_PEAKS.json"})
 

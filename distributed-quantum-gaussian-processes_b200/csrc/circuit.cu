@@ -177,6 +177,10 @@ static void build_plan(dqgp_circuit& c) {
             }
         }
         pass.op_end = (int)c.ops.size();
+        pass.lead_end = pass.op_begin;
+        while (pass.lead_end < pass.op_end && c.ops[pass.lead_end].kind == SV_CX && c.ops[pass.lead_end].cq >= 0) ++pass.lead_end;
+        pass.trail_begin = pass.op_end;
+        while (pass.trail_begin > pass.lead_end && c.ops[pass.trail_begin - 1].kind == SV_CX && c.ops[pass.trail_begin - 1].cq >= 0) --pass.trail_begin;
         c.passes.push_back(pass);
     }
     for (auto& f : fused) {

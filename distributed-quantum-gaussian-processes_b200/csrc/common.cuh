@@ -80,6 +80,10 @@ struct SvPass {
     int nq;         // block size 1..3
     int q[3];       // block qubits, ascending
     int op_begin, op_end;
+    // ops [op_begin, lead_end) and [trail_begin, op_end) are CX gates whose control lies OUTSIDE the block: a thread's groups
+    // see a fixed control bit, so these are XORs of the target bit into the LOAD / STORE address of the pass (statevec_lc2_kernel);
+    // kernels that ignore the two fields execute them as ordinary ops
+    int lead_end, trail_begin;
 };
 
 struct dqgp_circuit {

@@ -897,6 +897,432 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc_kernel(
     }
 }
 
+// ---- lc2: the linear-combination form, rebuilt around what ncu showed in round 2 (profiles/r02_sv_q10_before.txt: FP64 pipe
+// 33%, issue slots 52%, 68% of all instructions are not FP64) -------------------------------------------------------------------
+// For circuits whose parameters ALL enter through one RX / RY / RZ (yz_cx, kyriienko: BASELINE configs 4 and 5), features only.
+//  * TWO forks advance together through every pass (run_pass2<B, 2>): the op decode, control predicates, address arithmetic and
+//    fused-matrix loads of a pass are paid once for two states, and every thread carries two independent FP64 chains;
+//  * the first pass of a fork reads the base state and writes the fork's scratch (no copy);
+//  * ONE epilogue sweep per fork gives <phi|O|phi> and Re<psi|O|phi> together (each scratch amplitude is loaded once per qubit
+//    group instead of twice), the Z observables come from elementwise products in a single layout (they need no pairing);
+//  * team reductions halve the data with every shuffle step (team_reduce) instead of all-reducing every value: 85 shuffle steps
+//    per fork instead of 300 - SHFL issues once per cycle per SM, it was 14% of the kernel's time;
+//  * the gate program is read from global memory (uniform, L1-resident) instead of being copied into every CTA's shared memory.
+// __noinline__: one copy of each instantiation for all call sites (the inlined version stalled 14% of the time on instruction
+// fetch, profiles/r02_sv_q10_lc2_v1.txt).
+template <int B, int NS, bool ALT>
+__device__ __noinline__ void run_pass2(const double2* __restrict__ src0, const double2* __restrict__ src1, double2* __restrict__ dst0,
+                                       double2* __restrict__ dst1, const SvPass* __restrict__ pass, const SvOp* __restrict__ ops,
+                                       const double2* __restrict__ mats, const double2* __restrict__ trig, int lig, int lps, int groups,
+                                       int alt_mat0, const double2* __restrict__ alt_u0, int alt_mat1, const double2* __restrict__ alt_u1) {
+    constexpr int N = 1 << B;
+    const SvPass ps = *pass;
+    const int q0 = ps.q[0], q1 = ps.q[1], q2 = ps.q[2];
+    int off[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) off[j] = ((j & 1) ? (1 << q0) : 0) + ((B > 1 && (j & 2)) ? (1 << q1) : 0) + ((B > 2 && (j & 4)) ? (1 << q2) : 0);
+    for (int gi = lig; gi < groups; gi += lps) {
+        int base = insert_zero_bit(gi, q0);
+        if (B > 1) base = insert_zero_bit(base, q1);
+        if (B > 2) base = insert_zero_bit(base, q2);
+        // CX gates with an outside control at the head / tail of the pass: flip the target bit of the load / store address
+        int xl = 0, xs = 0;
+        for (int o = ps.op_begin; o < ps.lead_end; ++o) {
+            const SvOp op = ops[o];
+            if ((base >> op.cq) & 1) xl ^= 1 << (op.lbit == 0 ? q0 : (op.lbit == 1 ? q1 : q2));
+        }
+        for (int o = ps.trail_begin; o < ps.op_end; ++o) {
+            const SvOp op = ops[o];
+            if ((base >> op.cq) & 1) xs ^= 1 << (op.lbit == 0 ? q0 : (op.lbit == 1 ? q1 : q2));
+        }
+        int addr[N];
+        double2 r0[N], r1[N];      // r1 is dead code for NS == 1
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            addr[j] = base + off[j];
+            const int a = sv_phys(addr[j] ^ xl);
+            r0[j] = src0[a];
+            if (NS == 2) r1[j] = src1[a];
+        }
+        SvOp nxt = ops[ps.lead_end < ps.trail_begin ? ps.lead_end : ps.op_begin];
+#pragma unroll 1
+        for (int o = ps.lead_end; o < ps.trail_begin; ++o) {
+            const SvOp op = nxt;
+            if (o + 1 < ps.trail_begin) nxt = ops[o + 1];          // the next op's fetch overlaps this op's arithmetic
+            if (op.kind == SV_U2) {
+                const double2* u0 = mats + 4 * op.idx;
+                const double2* u1 = u0;
+                if (ALT) {
+                    if (op.idx == alt_mat0) u0 = alt_u0;
+                    if (NS == 2 && op.idx == alt_mat1) u1 = alt_u1;
+                }
+                double2 a = u0[0], b = u0[1], c = u0[2], d = u0[3];
+                if (op.lbit == 0) apply_u2<N, 0>(r0, a, b, c, d);
+                else if (B > 1 && op.lbit == 1) apply_u2<N, (B > 1 ? 1 : 0)>(r0, a, b, c, d);
+                else if (B > 2) apply_u2<N, (B > 2 ? 2 : 0)>(r0, a, b, c, d);
+                if (NS == 2) {
+                    if (ALT && u1 != u0) { a = u1[0]; b = u1[1]; c = u1[2]; d = u1[3]; }
+                    if (op.lbit == 0) apply_u2<N, 0>(r1, a, b, c, d);
+                    else if (B > 1 && op.lbit == 1) apply_u2<N, (B > 1 ? 1 : 0)>(r1, a, b, c, d);
+                    else if (B > 2) apply_u2<N, (B > 2 ? 2 : 0)>(r1, a, b, c, d);
+                }
+            } else {
+                const bool ext = (op.cq >= 0) ? (((base >> op.cq) & 1) != 0) : false;
+                const double2 cs = (op.kind == SV_CRZ) ? trig[op.idx] : make_double2(1.0, 0.0);
+                if (op.lbit == 0) {
+                    apply_controlled<N, 0>(r0, op.kind, op.cloc, ext, cs.x, cs.y);
+                    if (NS == 2) apply_controlled<N, 0>(r1, op.kind, op.cloc, ext, cs.x, cs.y);
+                } else if (B > 1 && op.lbit == 1) {
+                    apply_controlled<N, (B > 1 ? 1 : 0)>(r0, op.kind, op.cloc, ext, cs.x, cs.y);
+                    if (NS == 2) apply_controlled<N, (B > 1 ? 1 : 0)>(r1, op.kind, op.cloc, ext, cs.x, cs.y);
+                } else if (B > 2) {
+                    apply_controlled<N, (B > 2 ? 2 : 0)>(r0, op.kind, op.cloc, ext, cs.x, cs.y);
+                    if (NS == 2) apply_controlled<N, (B > 2 ? 2 : 0)>(r1, op.kind, op.cloc, ext, cs.x, cs.y);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const int a = sv_phys(addr[j] ^ xs);
+            dst0[a] = r0[j];
+            if (NS == 2) dst1[a] = r1[j];
+        }
+    }
+}
+
+template <int Q, int NS, bool ALT>
+__device__ __forceinline__ void sv_pass2(const double2* src0, const double2* src1, double2* dst0, double2* dst1, const SvPass* ps_ptr,
+                                         const SvOp* __restrict__ ops, const double2* __restrict__ u2, const double2* __restrict__ trig, int lig,
+                                         int am0, const double2* au0, int am1, const double2* au1) {
+    using T = SvTeam<Q>;
+    const int nq = ps_ptr->nq;
+    if (nq == 3) run_pass2<(Q >= 3 ? 3 : 1), NS, ALT>(src0, src1, dst0, dst1, ps_ptr, ops, u2, trig, lig, T::SIZE, T::DIM >> 3, am0, au0, am1, au1);
+    else if (nq == 2) run_pass2<(Q >= 2 ? 2 : 1), NS, ALT>(src0, src1, dst0, dst1, ps_ptr, ops, u2, trig, lig, T::SIZE, T::DIM >> 2, am0, au0, am1, au1);
+    else run_pass2<1, NS, ALT>(src0, src1, dst0, dst1, ps_ptr, ops, u2, trig, lig, T::SIZE, T::DIM >> 1, am0, au0, am1, au1);
+    T::sync();
+}
+
+// Sum v[0..N) over the W (power of two, <= 32, aligned) lanes of a team, halving the data with every shuffle step: a lane
+// whose bit m is set keeps the upper half and sends the lower one.  Afterwards slots [0, max(1, N/W)) of every lane hold the team
+// totals of the original indices idx_base + slot; when N < W the remaining steps all-reduce and `writer` marks one lane per index.
+template <int N, int W>
+__device__ __forceinline__ void team_reduce(double (&v)[N], int lane_in_team, int& idx_base, bool& writer) {
+    idx_base = 0;
+    writer = true;
+    int n = N;
+#pragma unroll
+    for (int m = W >> 1; m >= 1; m >>= 1) {
+        const bool hi = (lane_in_team & m) != 0;
+        if (n > 1) {
+            const int half = n >> 1;
+#pragma unroll
+            for (int j = 0; j < N / 2; ++j) {
+                if (j < half) {
+                    const double send = hi ? v[j] : v[j + half];
+                    const double keep = hi ? v[j + half] : v[j];
+                    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                }
+            }
+            idx_base += hi ? half : 0;
+            n = half;
+        } else {
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+            writer = writer && !hi;
+        }
+    }
+}
+template <int N, int W>
+struct TeamReduceLeft { static constexpr int value = (N / W) > 1 ? (N / W) : 1; };
+
+// value ids of one fork in the reduction buffer: [Bx | By | Bz | Cx | Cy | Cz] x Q, B = <phi|O|phi> (X, Y without their factor 2),
+// C = Re<psi|O|phi>; red[id * NW + warp]
+template <int Q, int B>
+__device__ __forceinline__ void lc2_group_xy(const double2* __restrict__ fin, const double2* __restrict__ scr, int k0, int lig, int warp,
+                                             double* __restrict__ red) {
+    using T = SvTeam<Q>;
+    constexpr int N = 1 << B, NV = 16, W = T::SIZE < 32 ? T::SIZE : 32, NW = T::BLOCK ? T::SIZE / 32 : 1;
+    const int groups = T::DIM >> B;
+    double v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = 0.0;
+    for (int gi = lig; gi < groups; gi += T::SIZE) {
+        int base = gi;
+#pragma unroll
+        for (int l = 0; l < B; ++l) base = insert_zero_bit(base, k0 + l);
+        double2 p[N], s[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            int o = 0;
+#pragma unroll
+            for (int l = 0; l < B; ++l) o += ((j >> l) & 1) << (k0 + l);
+            const int a = sv_phys(base + o);
+            p[j] = fin[a];
+            s[j] = scr[a];
+        }
+#pragma unroll
+        for (int l = 0; l < B; ++l)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                if (j & (1 << l)) continue;
+                const double2 a = s[j], b = s[j | (1 << l)], pa = p[j], pb = p[j | (1 << l)];
+                v[0 * B + l] = fma(a.x, b.x, fma(a.y, b.y, v[0 * B + l]));                                   // Re conj(phi_a) phi_b
+                v[1 * B + l] = fma(a.x, b.y, fma(-a.y, b.x, v[1 * B + l]));                                  // Im conj(phi_a) phi_b
+                v[2 * B + l] = fma(pa.x, b.x, fma(pa.y, b.y, fma(pb.x, a.x, fma(pb.y, a.y, v[2 * B + l]))));    // Re<psi|X|phi>
+                v[3 * B + l] = fma(pa.x, b.y, fma(-pa.y, b.x, fma(-pb.x, a.y, fma(pb.y, a.x, v[3 * B + l]))));  // Re<psi|Y|phi>
+            }
+    }
+    int idx;
+    bool writer;
+    team_reduce<NV, W>(v, lig & (W - 1), idx, writer);
+    constexpr int LEFT = TeamReduceLeft<NV, W>::value;
+    if (writer) {
+#pragma unroll
+        for (int j = 0; j < LEFT; ++j) {
+            const int e = idx + j;                 // slot = kind4 * B + l
+            if (e < 4 * B) {
+                const int kind4 = e / B, l = e - kind4 * B;
+                const int id = (kind4 < 2 ? kind4 : kind4 + 1) * Q + k0 + l;      // Bx, By, Cx, Cy -> rows 0, 1, 3, 4
+                red[id * NW + warp] = v[j];
+            }
+        }
+    }
+}
+
+// Z observables of a fork from ONE layout (block qubits 0, 1, 2): <phi|Z_k|phi> = sum_a (+-)|phi_a|^2, Re<psi|Z_k|phi> likewise
+template <int Q>
+__device__ __forceinline__ void lc2_group_z(const double2* __restrict__ fin, const double2* __restrict__ scr, int lig, int warp,
+                                            double* __restrict__ red) {
+    using T = SvTeam<Q>;
+    constexpr int NZ = (2 * Q <= 16) ? 16 : 32, W = T::SIZE < 32 ? T::SIZE : 32, NW = T::BLOCK ? T::SIZE / 32 : 1;
+    double v[NZ];
+#pragma unroll
+    for (int i = 0; i < NZ; ++i) v[i] = 0.0;
+    for (int gi = lig; gi < (T::DIM >> 3); gi += T::SIZE) {
+        const int base = gi << 3;
+        double pp[8], ww[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int a = sv_phys(base + j);
+            const double2 ps = fin[a], ph = scr[a];
+            pp[j] = fma(ph.x, ph.x, ph.y * ph.y);
+            ww[j] = fma(ps.x, ph.x, ps.y * ph.y);
+        }
+        // block qubits: signed sums over the 8 slots; outside qubits: the slot total with the sign of the group's index bit
+        const double p01 = pp[0] + pp[1], p23 = pp[2] + pp[3], p45 = pp[4] + pp[5], p67 = pp[6] + pp[7];
+        const double w01 = ww[0] + ww[1], w23 = ww[2] + ww[3], w45 = ww[4] + ww[5], w67 = ww[6] + ww[7];
+        v[0] += ((pp[0] - pp[1]) + (pp[2] - pp[3])) + ((pp[4] - pp[5]) + (pp[6] - pp[7]));
+        v[Q + 0] += ((ww[0] - ww[1]) + (ww[2] - ww[3])) + ((ww[4] - ww[5]) + (ww[6] - ww[7]));
+        v[1] += (p01 - p23) + (p45 - p67);
+        v[Q + 1] += (w01 - w23) + (w45 - w67);
+        const double plo = p01 + p23, phi_ = p45 + p67, wlo = w01 + w23, whi = w45 + w67;
+        v[2] += plo - phi_;
+        v[Q + 2] += wlo - whi;
+        const double pt = plo + phi_, wt = wlo + whi;
+#pragma unroll
+        for (int k = 3; k < Q; ++k) {
+            const bool neg = ((gi >> (k - 3)) & 1) != 0;
+            v[k] += neg ? -pt : pt;
+            v[Q + k] += neg ? -wt : wt;
+        }
+    }
+    int idx;
+    bool writer;
+    team_reduce<NZ, W>(v, lig & (W - 1), idx, writer);
+    constexpr int LEFT = TeamReduceLeft<NZ, W>::value;
+    if (writer) {
+#pragma unroll
+        for (int j = 0; j < LEFT; ++j) {
+            const int e = idx + j;                 // slot = z2 * Q + k
+            if (e < 2 * Q) {
+                const int z2 = e / Q, k = e - z2 * Q;
+                red[((z2 ? 5 : 2) * Q + k) * NW + warp] = v[j];
+            }
+        }
+    }
+}
+
+// one fork's epilogue: both central-difference sets of parameter i from A = <psi|O|psi> (featA), B, C
+template <int Q>
+__device__ __forceinline__ void lc2_emit(const double2* __restrict__ fin, const double2* __restrict__ scr, const double* __restrict__ featA,
+                                         double* __restrict__ red, int lig, bool live, double c0, double s0, double c1, double s1,
+                                         double* __restrict__ out_plus, double* __restrict__ out_minus) {
+    using T = SvTeam<Q>;
+    constexpr int FULL = Q / 3, REM = Q % 3, NW = T::BLOCK ? T::SIZE / 32 : 1, M3 = 3 * Q;
+    const int warp = T::BLOCK ? (lig >> 5) : 0;
+    lc2_group_z<Q>(fin, scr, lig, warp, red);
+#pragma unroll 1
+    for (int b = 0; b < FULL; ++b) lc2_group_xy<Q, 3>(fin, scr, 3 * b, lig, warp, red);
+    if (REM == 2) lc2_group_xy<Q, 2>(fin, scr, 3 * FULL, lig, warp, red);
+    if (REM == 1) lc2_group_xy<Q, 1>(fin, scr, 3 * FULL, lig, warp, red);
+    T::sync();
+    if (live) {
+        for (int k = lig; k < M3; k += T::SIZE) {
+            double Bv = 0.0, Cv = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { Bv += red[k * NW + w]; Cv += red[(M3 + k) * NW + w]; }
+            if (k < 2 * Q) Bv *= 2.0;            // X, Y: every pair was counted once
+            const double A = featA[k];
+            out_plus[k] = fma(c0 * c0, A, fma(s0 * s0, Bv, 2.0 * s0 * c0 * Cv));
+            out_minus[k] = fma(c1 * c1, A, fma(s1 * s1, Bv, 2.0 * s1 * c1 * Cv));
+        }
+    }
+    T::sync();
+}
+
+template <int Q>
+__global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
+    const dqgp_gate* __restrict__ g_gates, int n_gates, const SvPass* __restrict__ g_passes, int n_passes, const SvOp* __restrict__ g_ops,
+    const SvMat* __restrict__ g_mats, int n_mats, const int* __restrict__ g_mat_gates, const int* __restrict__ g_share, int d, int P,
+    int uses_acos, int pair_forks, const double* __restrict__ X, int n, const double* __restrict__ Pm, double* __restrict__ out) {
+    using T = SvTeam<Q>;
+    constexpr int M3 = 3 * Q, M3P = (M3 + 1) & ~1, NW = T::BLOCK ? T::SIZE / 32 : 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int* par_gate = g_share;
+    const int* par_mat = g_share + P;
+    const int* pass_par_begin = g_share + 2 * P;
+    const int* pass_params = g_share + 2 * P + n_passes + 1;
+    // per CTA: the op list and the pass table (read in every pass; the rest of the gate program stays in global memory)
+    const size_t op_bytes = (sizeof(SvOp) * n_gates + 15) & ~size_t(15), pass_bytes = (sizeof(SvPass) * n_passes + 15) & ~size_t(15);
+    SvOp* s_ops = reinterpret_cast<SvOp*>(smem_raw);
+    SvPass* s_passes = reinterpret_cast<SvPass*>(smem_raw + op_bytes);
+    for (int i = threadIdx.x; i < n_gates; i += blockDim.x) s_ops[i] = g_ops[i];        // #ops <= #gates
+    for (int i = threadIdx.x; i < n_passes; i += blockDim.x) s_passes[i] = g_passes[i];
+    __syncthreads();
+    // per-team storage: base | scratch 0 | scratch 1 | final base state | cos/sin table | fused matrices | 2 fork matrices | acos | red | A
+    const size_t team_bytes = sizeof(double2) * (4 * T::DIM + n_gates + 4 * n_mats + 8) + sizeof(double) * (((d + 1) & ~1) + 2 * M3 * NW + M3P + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int team_in_block = T::BLOCK ? 0 : warp * T::PER_WARP + lane / T::SIZE;
+    const int lig = T::BLOCK ? threadIdx.x : lane % T::SIZE;
+    const int teams_per_block = T::BLOCK ? 1 : (blockDim.x >> 5) * T::PER_WARP;
+    unsigned char* my = smem_raw + op_bytes + pass_bytes + team_bytes * team_in_block;
+    double2* base = reinterpret_cast<double2*>(my);
+    double2* scr0 = base + T::DIM;
+    double2* scr1 = scr0 + T::DIM;
+    double2* fin = scr1 + T::DIM;
+    double2* trig = fin + T::DIM;
+    double2* u2 = trig + n_gates;
+    double2* altm = u2 + 4 * n_mats;
+    double* acx = reinterpret_cast<double*>(altm + 8);
+    double* red = acx + ((d + 1) & ~1);
+    double* featA = red + 2 * M3 * NW;
+    double* coef = featA + M3P;
+
+    const long long n_rounds = (n + (long long)gridDim.x * teams_per_block - 1) / ((long long)gridDim.x * teams_per_block);
+    for (long long round = 0; round < n_rounds; ++round) {
+        long long j = (round * gridDim.x + blockIdx.x) * teams_per_block + team_in_block;
+        const bool live = j < n;
+        if (!live) j = n - 1;
+        const double* x = X + (size_t)j * d;
+        if (uses_acos) {
+            for (int f = lig; f < d; f += T::SIZE) acx[f] = acos(x[f]);
+            T::sync();
+        }
+        for (int g = lig; g < n_gates; g += T::SIZE) {
+            const dqgp_gate gt = g_gates[g];
+            if (gt.form == DQGP_A_NONE) continue;
+            double sn, cs;
+            sincos(0.5 * gate_angle(gt, gt.pidx >= 0 ? Pm[gt.pidx] : 0.0, x, acx), &sn, &cs);
+            trig[g] = make_double2(cs, sn);
+        }
+        for (int i = lig; i < T::DIM; i += T::SIZE) { base[i] = make_double2(i == 0 ? 1.0 : 0.0, 0.0); fin[i] = base[i]; }
+        T::sync();
+        for (int f = lig; f < n_mats; f += T::SIZE) compose_matrix(g_mats[f], g_mat_gates, g_gates, trig, -1, make_double2(0, 0), u2 + 4 * f);
+        T::sync();
+
+        // sweep 1: the final base state (kept for the cross terms) and the base set's features A
+        for (int ip = 0; ip < n_passes; ++ip) sv_pass2<Q, 1, false>(fin, fin, fin, fin, s_passes + ip, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
+        {
+            constexpr int FULL = Q / 3, REM = Q % 3;
+#pragma unroll 1
+            for (int b = 0; b < FULL; ++b) features_block<(Q >= 3 ? 3 : 1), Q>(fin, 3 * b, lig, T::SIZE, true, featA, red);
+            if (REM == 2) features_block<(Q >= 2 ? 2 : 1), Q>(fin, 3 * FULL, lig, T::SIZE, true, featA, red);
+            if (REM == 1) features_block<1, Q>(fin, 3 * FULL, lig, T::SIZE, true, featA, red);
+            T::sync();
+            if (live)
+                for (int k = lig; k < M3; k += T::SIZE) out[(size_t)j * M3 + k] = featA[k];
+        }
+        T::sync();
+
+        // sweep 2: advance the base pass by pass; before pass ip runs, fork every parameter whose rotation lives in it
+        for (int ip = 0; ip < n_passes; ++ip) {
+            const int pb = pass_par_begin[ip], pe = pass_par_begin[ip + 1];
+            const SvPass* ps0 = s_passes + ip;
+            for (int f0 = pb; f0 < pe; f0 += (pair_forks ? 2 : 1)) {
+                const int i0 = pass_params[f0];
+                const int i1 = (pair_forks && f0 + 1 < pe) ? pass_params[f0 + 1] : -1;
+                // fork matrices: the parameter's rotation with its angle advanced by pi: (cos, sin)(theta/2 + pi/2) = (-sin, cos)(theta/2)
+                // and the linear-combination coefficients cos / sin of half the two angle differences (once per fork, not per thread)
+                for (int e = lig; e < 2; e += T::SIZE) {
+                    const int i = e == 0 ? i0 : i1;
+                    if (i >= 0) {
+                        const int g = par_gate[i];
+                        compose_matrix(g_mats[par_mat[i]], g_mat_gates, g_gates, trig, g, make_double2(-trig[g].y, trig[g].x), altm + 4 * e);
+                        const dqgp_gate gt = g_gates[g];
+                        const double th0 = gate_angle(gt, Pm[i], x, acx);
+                        sincos(0.5 * (gate_angle(gt, Pm[(size_t)(1 + 2 * i) * P + i], x, acx) - th0), &coef[4 * e + 1], &coef[4 * e + 0]);
+                        sincos(0.5 * (gate_angle(gt, Pm[(size_t)(2 + 2 * i) * P + i], x, acx) - th0), &coef[4 * e + 3], &coef[4 * e + 2]);
+                    }
+                }
+                T::sync();
+                if (i1 >= 0) {
+                    sv_pass2<Q, 2, true>(base, base, scr0, scr1, ps0, s_ops, u2, trig, lig, par_mat[i0], altm, par_mat[i1], altm + 4);
+                    for (int kp = ip + 1; kp < n_passes; ++kp)
+                        sv_pass2<Q, 2, false>(scr0, scr1, scr0, scr1, s_passes + kp, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
+                } else {
+                    sv_pass2<Q, 1, true>(base, base, scr0, scr0, ps0, s_ops, u2, trig, lig, par_mat[i0], altm, -1, nullptr);
+                    for (int kp = ip + 1; kp < n_passes; ++kp)
+                        sv_pass2<Q, 1, false>(scr0, scr0, scr0, scr0, s_passes + kp, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
+                }
+#pragma unroll 1
+                for (int e = 0; e < 2; ++e) {
+                    const int i = e == 0 ? i0 : i1;
+                    if (i < 0) break;
+                    lc2_emit<Q>(fin, e == 0 ? scr0 : scr1, featA, red, lig, live, coef[4 * e], coef[4 * e + 1], coef[4 * e + 2], coef[4 * e + 3],
+                                out + ((size_t)(1 + 2 * i) * n + j) * M3, out + ((size_t)(2 + 2 * i) * n + j) * M3);
+                }
+            }
+            sv_pass2<Q, 1, false>(base, base, base, base, ps0, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
+        }
+        T::sync();
+    }
+}
+
+template <int Q>
+static int launch_sv_lc2(const dqgp_circuit* c, const double* X, int n, const double* Pm, double* out, cudaStream_t st) {
+    using T = SvTeam<Q>;
+    const int n_gates = (int)c->gates.size(), n_passes = (int)c->passes.size(), n_mats = (int)c->mats.size();
+    constexpr int M3 = 3 * Q, M3P = (M3 + 1) & ~1, NW = T::BLOCK ? T::SIZE / 32 : 1;
+    const size_t team_bytes = sizeof(double2) * (4 * T::DIM + n_gates + 4 * n_mats + 8) + sizeof(double) * (((c->d + 1) & ~1) + 2 * M3 * NW + M3P + 8);
+    const size_t fixed = ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvPass) * n_passes + 15) & ~size_t(15));
+    int warps = T::BLOCK ? T::SIZE / 32 : 4;
+    if (!T::BLOCK) {
+        // CTA size that keeps the most warps resident under the shared-memory limit (four state copies per team)
+        int best = 0;
+        for (int w = 4; w >= 1; --w) {
+            const size_t bytes = fixed + team_bytes * w * T::PER_WARP + 1024;
+            const int resident = bytes <= 228 * 1024 ? (int)((228 * 1024) / bytes) * w : 0;
+            if (resident > best) { best = resident; warps = w; }
+        }
+    }
+    const int teams = T::BLOCK ? 1 : warps * T::PER_WARP;
+    const size_t smem = fixed + team_bytes * teams;
+    if (smem > 227 * 1024) return 1;          // caller falls back to the one-fork kernel
+    auto kern = statevec_lc2_kernel<Q>;
+    DQGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = ((long long)n + teams - 1) / teams;
+    const long long cap = (long long)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) return 0;
+    const int pair_forks = getenv("DQGP_SV_NO_PAIR") == nullptr;
+    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d_passes, n_passes, c->d_ops, c->d_mats, n_mats, c->d_mat_gates,
+                                                    c->d_share, c->d, c->P, c->uses_acos ? 1 : 0, pair_forks, X, n, Pm, out);
+    DQGP_LAUNCH_CHECK("statevec_lc2_kernel");
+    return 0;
+}
+
 template <int Q, bool WANT_STATES>
 static int launch_sv_shared(const dqgp_circuit* c, const double* X, int n, const double* Pm, double* out, cudaStream_t st) {
     using T = SvTeam<Q>;
@@ -909,6 +1335,17 @@ static int launch_sv_shared(const dqgp_circuit* c, const double* X, int n, const
     // linear-combination form (statevec_lc_kernel) unless DQGP_SV_NO_LC is set (A/B checks against the two-fork kernel) or its
     // third copy of the state does not fit in shared memory (q = 12 with a long gate list)
     bool use_lc = getenv("DQGP_SV_NO_LC") == nullptr;
+    // lc2 (two forks per pass, fused epilogue) wins where a CTA owns the state (q >= 9: config 5, 60 -> 44 ms); with one state per
+    // warp (q <= 8) its fourth state copy and larger code cost more than they save (config 4: 4.4 ms against 3.9), so the
+    // one-fork kernel below stays the default there (DQGP_SV_FORCE_LC2 overrides, for tests and A/B runs)
+    if (!WANT_STATES && Q >= 3 && use_lc && getenv("DQGP_SV_NO_LC2") == nullptr && (T::BLOCK || getenv("DQGP_SV_FORCE_LC2") != nullptr)) {
+        bool all_rot = true;
+        for (int i = 0; i < c->P; ++i) all_rot = all_rot && c->par_mat[i] >= 0;
+        if (all_rot) {
+            const int rc = launch_sv_lc2<(Q >= 3 ? Q : 3)>(c, X, n, Pm, out, st);
+            if (rc <= 0) return rc;          // 1 = does not fit in shared memory: the one-fork kernel below
+        }
+    }
     auto team_size = [&](bool lc) {
         return sizeof(double2) * ((lc ? 3 : 2) * T::DIM + n_gates + 4 * n_mats + 4 * T::SLOTS) +
                sizeof(double) * (((c->d + 1) & ~1) + (T::BLOCK ? 9 * (T::SIZE / 32) + 1 : 0) + (lc ? 3 * ((3 * Q + 1) & ~1) : 0));

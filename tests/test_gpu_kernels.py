@@ -88,6 +88,17 @@ def test_shared_prefix_simulation_matches_per_set_kernels(d, enc, q, dd, layers,
             assert (F - F_ref).abs().max().item() < 2e-14
             assert (S - S_ref).abs().max().item() < 2e-14
             assert torch.equal(F[0], F_ref[0]) and torch.equal(S[0], S_ref[0])      # the base set is simulated directly
+    # statevec_lc2_kernel (two forks per pass, fused epilogue, CX gates folded into the load / store addresses): the default
+    # for q >= 9 when every parameter sits on a rotation; forced here for every q, with and without fork pairing
+    for env in ({"DQGP_SV_FORCE_LC2": "1"}, {"DQGP_SV_FORCE_LC2": "1", "DQGP_SV_NO_PAIR": "1"}, {"DQGP_SV_NO_LC2": "1"}):
+        for k in ("DQGP_SV_FORCE_LC2", "DQGP_SV_NO_PAIR", "DQGP_SV_NO_LC2"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        F = torch.full_like(F_ref, float("nan"))
+        assert lib.dqgp_features_shifted(ec.handle, dx.data_ptr(), n, dpm.data_ptr(), P, F.data_ptr(), _sp()) == 0, lib.dqgp_last_error()
+        torch.cuda.synchronize()
+        assert (F - F_ref).abs().max().item() < 2e-14, env
 
 
 def test_features_empty_and_single(d):
