@@ -1169,7 +1169,8 @@ __device__ __forceinline__ void lc2_emit(const double2* __restrict__ fin, const 
     T::sync();
 }
 
-template <int Q>
+// PAIR = false: one fork at a time and three state copies (no second scratch): the variant for one-state-per-warp teams (q <= 8)
+template <int Q, bool PAIR>
 __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
     const dqgp_gate* __restrict__ g_gates, int n_gates, const SvPass* __restrict__ g_passes, int n_passes, const SvOp* __restrict__ g_ops,
     const SvMat* __restrict__ g_mats, int n_mats, const int* __restrict__ g_mat_gates, const int* __restrict__ g_share, int d, int P,
@@ -1189,7 +1190,7 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
     for (int i = threadIdx.x; i < n_passes; i += blockDim.x) s_passes[i] = g_passes[i];
     __syncthreads();
     // per-team storage: base | scratch 0 | scratch 1 | final base state | cos/sin table | fused matrices | 2 fork matrices | acos | red | A
-    const size_t team_bytes = sizeof(double2) * (4 * T::DIM + n_gates + 4 * n_mats + 8) + sizeof(double) * (((d + 1) & ~1) + 2 * M3 * NW + M3P + 8);
+    const size_t team_bytes = sizeof(double2) * ((PAIR ? 4 : 3) * T::DIM + n_gates + 4 * n_mats + 8) + sizeof(double) * (((d + 1) & ~1) + 2 * M3 * NW + M3P + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int team_in_block = T::BLOCK ? 0 : warp * T::PER_WARP + lane / T::SIZE;
     const int lig = T::BLOCK ? threadIdx.x : lane % T::SIZE;
@@ -1197,8 +1198,8 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
     unsigned char* my = smem_raw + op_bytes + pass_bytes + team_bytes * team_in_block;
     double2* base = reinterpret_cast<double2*>(my);
     double2* scr0 = base + T::DIM;
-    double2* scr1 = scr0 + T::DIM;
-    double2* fin = scr1 + T::DIM;
+    double2* scr1 = PAIR ? scr0 + T::DIM : scr0;
+    double2* fin = scr0 + (PAIR ? 2 : 1) * T::DIM;
     double2* trig = fin + T::DIM;
     double2* u2 = trig + n_gates;
     double2* altm = u2 + 4 * n_mats;
@@ -1247,9 +1248,9 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
         for (int ip = 0; ip < n_passes; ++ip) {
             const int pb = pass_par_begin[ip], pe = pass_par_begin[ip + 1];
             const SvPass* ps0 = s_passes + ip;
-            for (int f0 = pb; f0 < pe; f0 += (pair_forks ? 2 : 1)) {
+            for (int f0 = pb; f0 < pe; f0 += ((PAIR && pair_forks) ? 2 : 1)) {
                 const int i0 = pass_params[f0];
-                const int i1 = (pair_forks && f0 + 1 < pe) ? pass_params[f0 + 1] : -1;
+                const int i1 = (PAIR && pair_forks && f0 + 1 < pe) ? pass_params[f0 + 1] : -1;
                 // fork matrices: the parameter's rotation with its angle advanced by pi: (cos, sin)(theta/2 + pi/2) = (-sin, cos)(theta/2)
                 // and the linear-combination coefficients cos / sin of half the two angle differences (once per fork, not per thread)
                 for (int e = lig; e < 2; e += T::SIZE) {
@@ -1264,10 +1265,10 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
                     }
                 }
                 T::sync();
-                if (i1 >= 0) {
-                    sv_pass2<Q, 2, true>(base, base, scr0, scr1, ps0, s_ops, u2, trig, lig, par_mat[i0], altm, par_mat[i1], altm + 4);
+                if (PAIR && i1 >= 0) {
+                    sv_pass2<Q, (PAIR ? 2 : 1), true>(base, base, scr0, scr1, ps0, s_ops, u2, trig, lig, par_mat[i0], altm, par_mat[i1], altm + 4);
                     for (int kp = ip + 1; kp < n_passes; ++kp)
-                        sv_pass2<Q, 2, false>(scr0, scr1, scr0, scr1, s_passes + kp, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
+                        sv_pass2<Q, (PAIR ? 2 : 1), false>(scr0, scr1, scr0, scr1, s_passes + kp, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
                 } else {
                     sv_pass2<Q, 1, true>(base, base, scr0, scr0, ps0, s_ops, u2, trig, lig, par_mat[i0], altm, -1, nullptr);
                     for (int kp = ip + 1; kp < n_passes; ++kp)
@@ -1292,7 +1293,8 @@ static int launch_sv_lc2(const dqgp_circuit* c, const double* X, int n, const do
     using T = SvTeam<Q>;
     const int n_gates = (int)c->gates.size(), n_passes = (int)c->passes.size(), n_mats = (int)c->mats.size();
     constexpr int M3 = 3 * Q, M3P = (M3 + 1) & ~1, NW = T::BLOCK ? T::SIZE / 32 : 1;
-    const size_t team_bytes = sizeof(double2) * (4 * T::DIM + n_gates + 4 * n_mats + 8) + sizeof(double) * (((c->d + 1) & ~1) + 2 * M3 * NW + M3P + 8);
+    constexpr bool PAIR = T::BLOCK;
+    const size_t team_bytes = sizeof(double2) * ((PAIR ? 4 : 3) * T::DIM + n_gates + 4 * n_mats + 8) + sizeof(double) * (((c->d + 1) & ~1) + 2 * M3 * NW + M3P + 8);
     const size_t fixed = ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvPass) * n_passes + 15) & ~size_t(15));
     int warps = T::BLOCK ? T::SIZE / 32 : 4;
     if (!T::BLOCK) {
@@ -1307,7 +1309,7 @@ static int launch_sv_lc2(const dqgp_circuit* c, const double* X, int n, const do
     const int teams = T::BLOCK ? 1 : warps * T::PER_WARP;
     const size_t smem = fixed + team_bytes * teams;
     if (smem > 227 * 1024) return 1;          // caller falls back to the one-fork kernel
-    auto kern = statevec_lc2_kernel<Q>;
+    auto kern = statevec_lc2_kernel<Q, PAIR>;
     DQGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));

@@ -484,3 +484,27 @@ def test_admm_engine_repairs_failed_agents_with_the_lu_rung(d):
         z_ref, th, ps, _ = driver.admm_iteration(cfg, shards, th, ps, 0.1, 100.0, 100.0)
         z, theta, psi, _ = eng.state()
         assert np.max(np.abs(z - z_ref)) < 1e-12 and np.max(np.abs(theta - th)) < 1e-12 and np.max(np.abs(psi - ps)) < 1e-9
+
+
+def test_agent_step_on_a_second_device_after_the_first(d):
+    """Kernel attributes (dynamic shared memory above 48 KB) are per DEVICE: one process that touches two GPUs must be able to
+    run the fused gradient / fidelity kernels on both (round-1 advisor finding: a process-wide `static bool` guard)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import agent_step
+    x, y = d.synthetic_dataset(130, 3, "yz_cx")
+    rs = np.random.RandomState(1)
+    res = {}
+    for kt in ("projected", "fidelity"):
+        P = d.EncodingCircuit("yz_cx", 4, 3, 2).num_parameters
+        z, psi = np.round(rs.rand(P), 4), np.round(rs.rand(P), 4)
+        ref = agent_step.train_and_update(agent_step.KernelConfig("yz_cx", kt, 4, 2), x, y, z, psi, 0.1, 100.0, 100.0, want_cond=False)
+        for dev in (0, 1):
+            with torch.cuda.device(dev):
+                eng = d.AgentEngine(x, y, encoding_type="yz_cx", kernel_type=kt, num_qubits=4, num_layers=2, noise_std=0.1, rho=100.0, L=100.0)
+                dz = d.kernels.dev_f64(z, device=f"cuda:{dev}")
+                eng.simulate(dz); eng.gram(); eng.factor(); eng.gradient()
+                torch.cuda.synchronize()
+                g = eng.d_grad.cpu().numpy()
+            assert np.max(np.abs(g - ref.grad)) < 1e-8 * max(1.0, np.abs(ref.grad).max()), (kt, dev)
+    torch.cuda.set_device(0)
