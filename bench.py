@@ -309,6 +309,7 @@ def run_e2e(args, w, d, torch, dist, world, rank, shards, theta0, psi0, n_i, P, 
 
     steps = max(1, min(args.steps, args.e2e_steps))
     one_iteration()                      # warm-up (engine cache, pinned buffers)
+    one_iteration()                      # second call: every agent captures its step as a CUDA graph
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

@@ -57,6 +57,8 @@ class RiemannianAgent:
         # "if_changed": X_sub / Y_sub stay resident on the GPU and are re-uploaded only when they differ from the staged copy;
         # "always": copy them every call, as the reference re-pickles them to its workers every iteration (main.py:2530-2542)
         self.reupload_shard = reupload_shard
+        import os
+        self.use_cuda_graph = os.environ.get("DQGP_AGENT_GRAPH", "1") != "0"
         self.agent_id = agent_id
         self.X_sub = np.asarray(X_sub, dtype=np.float64)
         if self.X_sub.ndim == 1:
@@ -108,33 +110,57 @@ class RiemannianAgent:
             raise ValueError(f"expected {eng.P} parameters, got z {z.size}, psi {psi_i.size}")
         self._setup_riemannian_framework(eng.P)
         ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
-        h_in, h_out = eng.staging()                 # persistent pinned buffers (no cudaHostAlloc per call)
-        h_in[0].copy_(torch.from_numpy(z))
-        h_in[1].copy_(torch.from_numpy(psi_i))
-        with ctx:
-            shard_bytes = eng.load_data(self.X_sub, self.Y_sub, always=self.reupload_shard == "always")
-            if getattr(eng, "_d_in", None) is None:
-                eng._d_in = torch.empty((2, eng.P), dtype=torch.float64, device=eng.d_X.device)
-                eng._d_out = torch.empty((3 * eng.P + 5,), dtype=torch.float64, device=eng.d_X.device)
-            d_in, d_out = eng._d_in, eng._d_out
+        if getattr(eng, "_d_in", None) is None:
+            eng._d_in = torch.empty((2, eng.P), dtype=torch.float64, device=eng.d_X.device)
+            eng._d_out = torch.empty((3 * eng.P + 5,), dtype=torch.float64, device=eng.d_X.device)
+            eng._graph, eng._graph_busy, eng._eager_calls = None, False, 0
+        d_in, d_out, p = eng._d_in, eng._d_out, eng.P
+
+        def enqueue(h_in, h_out):
+            """H2D of z / psi, the whole step, packing of the result, one D2H: ~100 launches, or one CUDA-graph launch."""
             d_in.copy_(h_in, non_blocking=True)
-            p = eng.P
             eng.step(d_in[0], d_in[1], d_out[:p], d_out[p:2 * p])
             d_out[2 * p:2 * p + 4].copy_(eng.d_nll)
             d_out[2 * p + 4:3 * p + 4].copy_(eng.d_grad)
             d_out[3 * p + 4:].copy_(eng.d_info)                 # int32 -> float64
-            h_out.copy_(d_out, non_blocking=True)               # one D2H
+            h_out.copy_(d_out, non_blocking=True)
+
+        # From the second call on, the step replays as ONE CUDA graph (the engine's own pinned staging pair is baked into its
+        # copy nodes); a call that arrives while that pair is still in flight, or DQGP_AGENT_GRAPH=0, takes the eager path.
+        use_graph = self.use_cuda_graph and not eng._graph_busy and eng._eager_calls >= 1
+        if use_graph and eng._graph is None:
+            eng._g_pair = eng.staging()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                enqueue(*eng._g_pair)
+            eng._graph = graph
+        pair = eng._g_pair if use_graph else eng.staging()      # persistent pinned buffers (no cudaHostAlloc per call)
+        h_in, h_out = pair
+        h_in[0].copy_(torch.from_numpy(z))
+        h_in[1].copy_(torch.from_numpy(psi_i))
+        with ctx:
+            shard_bytes = eng.load_data(self.X_sub, self.Y_sub, always=self.reupload_shard == "always")
+            if use_graph:
+                eng._graph.replay()
+                eng._graph_busy = True
+            else:
+                enqueue(h_in, h_out)
+                eng._eager_calls += 1
             done = torch.cuda.Event()
             done.record()
         self.h2d_bytes = shard_bytes + z.nbytes + psi_i.nbytes
         self.d2h_bytes = h_out.numel() * 8
-        return (eng, d_in, (h_in, h_out), h_out, done)
+        return (eng, d_in, (pair, use_graph), h_out, done)
 
     def collect(self, pending):
-        eng, d_in, pair, host, done = pending
+        eng, d_in, (pair, used_graph), host, done = pending
         done.synchronize()
         packed = host.numpy().copy()
-        eng.release(pair)
+        if used_graph:
+            eng._graph_busy = False
+        else:
+            eng.release(pair)
         p = eng.P
         theta_i, psi_new = packed[:p].copy(), packed[p:2 * p].copy()
         terms = packed[2 * p:2 * p + 4]
