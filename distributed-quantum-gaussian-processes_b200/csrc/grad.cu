@@ -125,8 +125,25 @@ __device__ __forceinline__ void g2_stage(double* buf, const double* __restrict__
     else if (threadIdx.x < 2 * PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(col0 + threadIdx.x - PW_TILE, n - 1)]);
 }
 
+// Same tile through the bulk-copy engine (cp.async.bulk = TMA without a tensor map, SASS UBLKCP): one copy per sample row (m doubles,
+// a multiple of 16 bytes when m is even) straight into the padded row of the fragment layout, completion counted in bytes on the
+// stage's mbarrier.  The norms (8-byte granularity, not always 16-byte aligned) stay on cp.async.
+__device__ __forceinline__ void g2_stage_bulk(double* buf, const double* __restrict__ Fs, const double* __restrict__ Ns, int row0, int col0, int n,
+                                              int m, unsigned long long* bar) {
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, 2u * PW_TILE * m * sizeof(double));
+    if (threadIdx.x < 2 * PW_TILE) {
+        const int r = threadIdx.x & (PW_TILE - 1), is_col = threadIdx.x >> 6;
+        const double* src = Fs + (size_t)min((is_col ? col0 : row0) + r, n - 1) * m;
+        bulk_copy_g2s(buf + (is_col * PW_TILE + r) * G2_PITCH, src, m * sizeof(double), bar);
+    }
+    double* nr = buf + 2 * PW_TILE * G2_PITCH;
+    if (threadIdx.x < PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(row0 + threadIdx.x, n - 1)]);
+    else if (threadIdx.x < 2 * PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(col0 + threadIdx.x - PW_TILE, n - 1)]);
+}
+
 // CLAMP: guard the exponent against arguments below -700 (only reachable when gamma * 4m > 700; features lie in [-1, 1])
-template <int OUTER, int VEC, bool CLAMP = true>
+// BULK: stage the feature tiles with cp.async.bulk + mbarrier instead of per-thread cp.async (needs VEC == 2)
+template <int OUTER, int VEC, bool CLAMP = true, bool BULK = false>
 __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(const double* __restrict__ Ainv, int ld,
                                                                            const double* __restrict__ alpha,
                                                                            const double* __restrict__ F,
@@ -134,12 +151,17 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
                                                                            OuterHyp hyp, double* __restrict__ partial) {
     extern __shared__ __align__(16) double g2_smem[];
     __shared__ double s_red[2][PW_THREADS / 32];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     int bi, bj;
     tile_from_index(blockIdx.x, bi, bj);
     const int row0 = bi * PW_TILE, col0 = bj * PW_TILE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wr = warp >> 1, wc = warp & 1, g = lane >> 2, t = lane & 3;
     const int ksteps = (m + 3) >> 2;
+    if (BULK) {
+        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+        __syncthreads();
+    }
     const double gam = (OUTER == DQGP_OUTER_GAUSSIAN) ? hyp.a : 1.0;
     const double a_scale = 2.0 * gam;
     const double tab = exp_table_entry();
@@ -170,11 +192,13 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
 
     const size_t set_stride = (size_t)n * m;
     const int T = 2 * P;
-    g2_stage<VEC>(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m);
+    if (BULK) g2_stage_bulk(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m, &s_bar[0]);
+    else g2_stage<VEC>(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m);
     cp_async_commit();
     double pplus = 0.0, pminus = 0.0;
     for (int tt = 0; tt < T; ++tt) {
         cp_async_wait<0>();
+        if (BULK) mbar_wait(&s_bar[tt & 1], (tt >> 1) & 1);
         __syncthreads();
         if (tt >= 2 && (tt & 1) == 0 && threadIdx.x == 0) {
             const int i = (tt >> 1) - 1;
@@ -184,7 +208,8 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
             partial[(size_t)blockIdx.x * P + i] = s;
         }
         if (tt + 1 < T) {
-            g2_stage<VEC>(g2_smem + ((tt + 1) & 1) * G2_STAGE_DOUBLES, F + (size_t)(tt + 2) * set_stride, Nrm + (size_t)(tt + 2) * n, row0, col0, n, m);
+            if (BULK) g2_stage_bulk(g2_smem + ((tt + 1) & 1) * G2_STAGE_DOUBLES, F + (size_t)(tt + 2) * set_stride, Nrm + (size_t)(tt + 2) * n, row0, col0, n, m, &s_bar[(tt + 1) & 1]);
+            else g2_stage<VEC>(g2_smem + ((tt + 1) & 1) * G2_STAGE_DOUBLES, F + (size_t)(tt + 2) * set_stride, Nrm + (size_t)(tt + 2) * n, row0, col0, n, m);
         }
         cp_async_commit();
         const double* buf = g2_smem + (tt & 1) * G2_STAGE_DOUBLES;
@@ -503,6 +528,8 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
         const double worst = outer == DQGP_OUTER_GAUSSIAN ? 4.0 * m * hyp.a
                              : outer == DQGP_OUTER_MATERN15 ? 1.7320508075688772 * 2.0 * sqrt((double)m) * hyp.a : 2.0 * hyp.a * hyp.a;
         const bool no_clamp = hyp.a > 0.0 && worst < 650.0;
+        // feature tiles through the bulk-copy (TMA) engine unless DQGP_GRAD_NO_BULK is set (A/B runs against per-thread cp.async)
+        const bool use_bulk = getenv("DQGP_GRAD_NO_BULK") == nullptr;
 #define DQGP_G2(OUT)                                                                                                         \
     do {                                                                                                                     \
         static bool attr_done_dev[64] = {false};        /* the attribute is per DEVICE (as gemm_init's flags) */            \
@@ -513,10 +540,15 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
+            DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
+            DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             attr_done = true;                                                                                                \
         }                                                                                                                    \
         if ((m & 1) == 0 && (reinterpret_cast<uintptr_t>(d_F) & 15) == 0) {                                                  \
-            if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+            if (use_bulk) {                                                                                                  \
+                if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+                else grad_projected_dmma_kernel<OUT, 2, true, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+            } else if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
             else grad_projected_dmma_kernel<OUT, 2><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
         } else                                                                                                               \
             grad_projected_dmma_kernel<OUT, 1><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
