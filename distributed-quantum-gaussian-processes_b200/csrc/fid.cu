@@ -30,7 +30,18 @@ __device__ __forceinline__ void fd_stage(double* buf, const double* __restrict__
     }
 }
 
-template <int MODE>
+// the same chunk through the bulk-copy (TMA) engine: one cp.async.bulk per state row (kc doubles), bytes counted on `bar`
+__device__ __forceinline__ void fd_stage_bulk(double* buf, const double* __restrict__ S1, const double* __restrict__ S2, int row0,
+                                              int col0, int n1, int n2, int d2, int k0, int kc, unsigned long long* bar) {
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, 2u * PW_TILE * kc * sizeof(double));
+    if (threadIdx.x < 2 * PW_TILE) {
+        const int r = threadIdx.x & (PW_TILE - 1), is_col = threadIdx.x >> 6;
+        const double* src = is_col ? S2 + (size_t)min(col0 + r, n2 - 1) * d2 + k0 : S1 + (size_t)min(row0 + r, n1 - 1) * d2 + k0;
+        bulk_copy_g2s(buf + (is_col * PW_TILE + r) * FD_PITCH, src, kc * sizeof(double), bar);
+    }
+}
+
+template <int MODE, bool BULK = true>
 __global__ void __launch_bounds__(PW_THREADS, 1) fidelity_dmma_kernel(const double* __restrict__ Psi1, int n1,
                                                                       const double* __restrict__ Psi2, int n2, int d2, int n_sets,
                                                                       double* __restrict__ K, int ldk,
@@ -39,6 +50,11 @@ __global__ void __launch_bounds__(PW_THREADS, 1) fidelity_dmma_kernel(const doub
                                                                       double* __restrict__ partial) {
     extern __shared__ __align__(16) double fd_smem[];
     __shared__ double s_red[2][PW_THREADS / 32];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    if (BULK) {
+        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+        __syncthreads();
+    }
     int bi, bj;
     if (MODE == 1) {
         bi = int((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
@@ -75,13 +91,15 @@ __global__ void __launch_bounds__(PW_THREADS, 1) fidelity_dmma_kernel(const doub
     const size_t set_stride1 = (size_t)n1 * d2, set_stride2 = (size_t)n2 * d2;
     const int first_set = (MODE == 1) ? 1 : 0;
     const int total = n_sets * n_chunks;
-    fd_stage(fd_smem, Psi1 + first_set * set_stride1, Psi2 + first_set * set_stride2, row0, col0, n1, n2, d2, 0, kc);
+    if (BULK) fd_stage_bulk(fd_smem, Psi1 + first_set * set_stride1, Psi2 + first_set * set_stride2, row0, col0, n1, n2, d2, 0, kc, &s_bar[0]);
+    else fd_stage(fd_smem, Psi1 + first_set * set_stride1, Psi2 + first_set * set_stride2, row0, col0, n1, n2, d2, 0, kc);
     cp_async_commit();
     double re[2][4][2], im[2][4][2];
     double pplus = 0.0;
     for (int it = 0; it < total; ++it) {
         const int set = it / n_chunks, ch = it - set * n_chunks;
-        cp_async_wait<0>();
+        if (BULK) mbar_wait(&s_bar[it & 1], (it >> 1) & 1);
+        else cp_async_wait<0>();
         __syncthreads();
         if (MODE == 1 && ch == 0 && set >= 2 && (set & 1) == 0 && threadIdx.x == 0) {
             const int i = (set >> 1) - 1;
@@ -92,8 +110,12 @@ __global__ void __launch_bounds__(PW_THREADS, 1) fidelity_dmma_kernel(const doub
         }
         if (it + 1 < total) {
             const int ns = (it + 1) / n_chunks, nch = (it + 1) - ns * n_chunks;
-            fd_stage(fd_smem + ((it + 1) & 1) * FD_STAGE, Psi1 + (size_t)(first_set + ns) * set_stride1,
-                     Psi2 + (size_t)(first_set + ns) * set_stride2, row0, col0, n1, n2, d2, nch * kc, kc);
+            if (BULK)
+                fd_stage_bulk(fd_smem + ((it + 1) & 1) * FD_STAGE, Psi1 + (size_t)(first_set + ns) * set_stride1,
+                              Psi2 + (size_t)(first_set + ns) * set_stride2, row0, col0, n1, n2, d2, nch * kc, kc, &s_bar[(it + 1) & 1]);
+            else
+                fd_stage(fd_smem + ((it + 1) & 1) * FD_STAGE, Psi1 + (size_t)(first_set + ns) * set_stride1,
+                         Psi2 + (size_t)(first_set + ns) * set_stride2, row0, col0, n1, n2, d2, nch * kc, kc);
         }
         cp_async_commit();
         if (ch == 0) {
@@ -171,6 +193,8 @@ static int fd_attr() {
     if (!done) {
         DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
         DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
+        DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
+        DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
         done = true;
     }
     return 0;
@@ -180,7 +204,9 @@ int fidelity_gram_dmma(const double* Psi1, int n1, const double* Psi2, int n2, i
     int rc = fd_attr();
     if (rc) return rc;
     dim3 grid((n2 + PW_TILE - 1) / PW_TILE, (n1 + PW_TILE - 1) / PW_TILE);
-    fidelity_dmma_kernel<0><<<grid, PW_THREADS, FD_SMEM, st>>>(Psi1, n1, Psi2, n2, 2 * dim, 1, K, ldk, nullptr, 0, nullptr, 0, nullptr);
+    static const bool no_bulk = getenv("DQGP_FID_NO_BULK") != nullptr;      // A/B: per-thread cp.async staging
+    if (no_bulk) fidelity_dmma_kernel<0, false><<<grid, PW_THREADS, FD_SMEM, st>>>(Psi1, n1, Psi2, n2, 2 * dim, 1, K, ldk, nullptr, 0, nullptr, 0, nullptr);
+    else fidelity_dmma_kernel<0><<<grid, PW_THREADS, FD_SMEM, st>>>(Psi1, n1, Psi2, n2, 2 * dim, 1, K, ldk, nullptr, 0, nullptr, 0, nullptr);
     DQGP_LAUNCH_CHECK("fidelity_dmma_kernel<0>");
     return 0;
 }
@@ -189,7 +215,9 @@ int fidelity_grad_dmma(const double* Ainv, int ld, const double* alpha, const do
                        int tiles, cudaStream_t st) {
     int rc = fd_attr();
     if (rc) return rc;
-    fidelity_dmma_kernel<1><<<tiles, PW_THREADS, FD_SMEM, st>>>(Psi, n, Psi, n, 2 * dim, 2 * P, nullptr, 0, Ainv, ld, alpha, P, partial);
+    static const bool no_bulk = getenv("DQGP_FID_NO_BULK") != nullptr;
+    if (no_bulk) fidelity_dmma_kernel<1, false><<<tiles, PW_THREADS, FD_SMEM, st>>>(Psi, n, Psi, n, 2 * dim, 2 * P, nullptr, 0, Ainv, ld, alpha, P, partial);
+    else fidelity_dmma_kernel<1><<<tiles, PW_THREADS, FD_SMEM, st>>>(Psi, n, Psi, n, 2 * dim, 2 * P, nullptr, 0, Ainv, ld, alpha, P, partial);
     DQGP_LAUNCH_CHECK("fidelity_dmma_kernel<1>");
     return 0;
 }

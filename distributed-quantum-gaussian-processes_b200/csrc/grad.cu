@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(PW_THREADS) grad_projected_kernel(const double
 // 16x32 = 2x4 DMMA blocks; B stays in registers for all 2P sets; feature tiles double-buffered with cp.async.
 constexpr int G2_STAGE_DOUBLES = 2 * PW_TILE * G2_PITCH + 2 * PW_TILE;
 constexpr size_t G2_SMEM = sizeof(double) * 2 * G2_STAGE_DOUBLES;
+constexpr size_t G2_SMEM_P28 = sizeof(double) * 3 * (2 * PW_TILE * 28 + 2 * PW_TILE);      // PITCH = 28, three stages
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
@@ -101,14 +102,14 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 // Stage one parameter set's row and column feature tiles (64 x m each) + their squared norms.  Four threads per
 // sample row, no integer division: thread (row = tid>>2, lane4 = tid&3) copies chunks lane4, lane4+4, ... of its row.
 // VEC=2: m even -> 16-byte cp.async (row starts are 16-byte aligned); VEC=1: 8-byte copies.
-template <int VEC>
+template <int VEC, int PITCH>
 __device__ __forceinline__ void g2_stage(double* buf, const double* __restrict__ Fs, const double* __restrict__ Ns, int row0,
                                          int col0, int n, int m) {
     const int r = threadIdx.x >> 2, l4 = threadIdx.x & 3;
     const double* src_r = Fs + (size_t)min(row0 + r, n - 1) * m;
     const double* src_c = Fs + (size_t)min(col0 + r, n - 1) * m;
-    double* dst_r = buf + r * G2_PITCH;
-    double* dst_c = buf + PW_TILE * G2_PITCH + r * G2_PITCH;
+    double* dst_r = buf + r * PITCH;
+    double* dst_c = buf + PW_TILE * PITCH + r * PITCH;
     if (VEC == 2) {
         for (int k = 2 * l4; k < m; k += 8) {
             cp_async16(dst_r + k, src_r + k);
@@ -120,7 +121,7 @@ __device__ __forceinline__ void g2_stage(double* buf, const double* __restrict__
             cp_async8(dst_c + k, src_c + k);
         }
     }
-    double* nr = buf + 2 * PW_TILE * G2_PITCH;
+    double* nr = buf + 2 * PW_TILE * PITCH;
     if (threadIdx.x < PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(row0 + threadIdx.x, n - 1)]);
     else if (threadIdx.x < 2 * PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(col0 + threadIdx.x - PW_TILE, n - 1)]);
 }
@@ -128,30 +129,35 @@ __device__ __forceinline__ void g2_stage(double* buf, const double* __restrict__
 // Same tile through the bulk-copy engine (cp.async.bulk = TMA without a tensor map, SASS UBLKCP): one copy per sample row (m doubles,
 // a multiple of 16 bytes when m is even) straight into the padded row of the fragment layout, completion counted in bytes on the
 // stage's mbarrier.  The norms (8-byte granularity, not always 16-byte aligned) stay on cp.async.
+template <int PITCH>
 __device__ __forceinline__ void g2_stage_bulk(double* buf, const double* __restrict__ Fs, const double* __restrict__ Ns, int row0, int col0, int n,
                                               int m, unsigned long long* bar) {
     if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, 2u * PW_TILE * m * sizeof(double));
     if (threadIdx.x < 2 * PW_TILE) {
         const int r = threadIdx.x & (PW_TILE - 1), is_col = threadIdx.x >> 6;
         const double* src = Fs + (size_t)min((is_col ? col0 : row0) + r, n - 1) * m;
-        bulk_copy_g2s(buf + (is_col * PW_TILE + r) * G2_PITCH, src, m * sizeof(double), bar);
+        bulk_copy_g2s(buf + (is_col * PW_TILE + r) * PITCH, src, m * sizeof(double), bar);
     }
-    double* nr = buf + 2 * PW_TILE * G2_PITCH;
+    double* nr = buf + 2 * PW_TILE * PITCH;
     if (threadIdx.x < PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(row0 + threadIdx.x, n - 1)]);
     else if (threadIdx.x < 2 * PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(col0 + threadIdx.x - PW_TILE, n - 1)]);
 }
 
 // CLAMP: guard the exponent against arguments below -700 (only reachable when gamma * 4m > 700; features lie in [-1, 1])
 // BULK: stage the feature tiles with cp.async.bulk + mbarrier instead of per-thread cp.async (needs VEC == 2)
-template <int OUTER, int VEC, bool CLAMP = true, bool BULK = false>
+// PITCH: doubles per staged sample row, = 4 (mod 8) so the DMMA fragment loads are bank-conflict-free, >= m.  With PITCH = 28 (m <= 28:
+// up to 9 qubits) a stage is 29.7 KB and THREE stages fit beside a second CTA, so a tile's copy is issued two sets ahead.
+template <int OUTER, int VEC, bool CLAMP = true, bool BULK = false, int PITCH = G2_PITCH>
 __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(const double* __restrict__ Ainv, int ld,
                                                                            const double* __restrict__ alpha,
                                                                            const double* __restrict__ F,
                                                                            const double* __restrict__ Nrm, int n, int m, int P,
                                                                            OuterHyp hyp, double* __restrict__ partial) {
+    constexpr int STAGES = (BULK && PITCH <= 28) ? 3 : 2;
+    constexpr int G2_STAGE_DOUBLES = 2 * PW_TILE * PITCH + 2 * PW_TILE;
     extern __shared__ __align__(16) double g2_smem[];
     __shared__ double s_red[2][PW_THREADS / 32];
-    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ __align__(8) unsigned long long s_bar[3];
     int bi, bj;
     tile_from_index(blockIdx.x, bi, bj);
     const int row0 = bi * PW_TILE, col0 = bj * PW_TILE;
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
     const int wr = warp >> 1, wc = warp & 1, g = lane >> 2, t = lane & 3;
     const int ksteps = (m + 3) >> 2;
     if (BULK) {
-        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init(&s_bar[2], 1); mbar_fence_init(); }
         __syncthreads();
     }
     const double gam = (OUTER == DQGP_OUTER_GAUSSIAN) ? hyp.a : 1.0;
@@ -167,11 +173,11 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
     const double tab = exp_table_entry();
 
     // zero the k-padding columns of both stages once (cp.async never writes them)
-    for (int e = threadIdx.x; e < 2 * 2 * PW_TILE * (G2_PITCH - m); e += PW_THREADS) {
-        const int per = G2_PITCH - m;
+    for (int e = threadIdx.x; e < STAGES * 2 * PW_TILE * (PITCH - m); e += PW_THREADS) {
+        const int per = PITCH - m;
         const int row = e / per, k = m + (e - row * per);          // row in [0, 4*64): stage x operand x sample
         const int stage = row / (2 * PW_TILE), rr = row - stage * 2 * PW_TILE;
-        g2_smem[stage * G2_STAGE_DOUBLES + rr * G2_PITCH + k] = 0.0;
+        g2_smem[stage * G2_STAGE_DOUBLES + rr * PITCH + k] = 0.0;
     }
 
     // B = weight * (A^-1 - alpha alpha^T) for this lane's 16 entries; zero outside the matrix and on the diagonal
@@ -192,13 +198,18 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
 
     const size_t set_stride = (size_t)n * m;
     const int T = 2 * P;
-    if (BULK) g2_stage_bulk(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m, &s_bar[0]);
-    else g2_stage<VEC>(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m);
+    if (BULK) g2_stage_bulk<PITCH>(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m, &s_bar[0]);
+    else g2_stage<VEC, PITCH>(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m);
     cp_async_commit();
+    if (STAGES == 3) {
+        if (T > 1) g2_stage_bulk<PITCH>(g2_smem + G2_STAGE_DOUBLES, F + 2 * set_stride, Nrm + 2 * (size_t)n, row0, col0, n, m, &s_bar[1]);
+        cp_async_commit();
+    }
     double pplus = 0.0, pminus = 0.0;
     for (int tt = 0; tt < T; ++tt) {
-        cp_async_wait<0>();
-        if (BULK) mbar_wait(&s_bar[tt & 1], (tt >> 1) & 1);
+        const int cur = tt % STAGES;
+        if (STAGES == 3) cp_async_wait<1>(); else cp_async_wait<0>();
+        if (BULK) mbar_wait(&s_bar[cur], (tt / STAGES) & 1);
         __syncthreads();
         if (tt >= 2 && (tt & 1) == 0 && threadIdx.x == 0) {
             const int i = (tt >> 1) - 1;
@@ -207,15 +218,19 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
             for (int w = 0; w < PW_THREADS / 32; ++w) s += s_red[i & 1][w];
             partial[(size_t)blockIdx.x * P + i] = s;
         }
-        if (tt + 1 < T) {
-            if (BULK) g2_stage_bulk(g2_smem + ((tt + 1) & 1) * G2_STAGE_DOUBLES, F + (size_t)(tt + 2) * set_stride, Nrm + (size_t)(tt + 2) * n, row0, col0, n, m, &s_bar[(tt + 1) & 1]);
-            else g2_stage<VEC>(g2_smem + ((tt + 1) & 1) * G2_STAGE_DOUBLES, F + (size_t)(tt + 2) * set_stride, Nrm + (size_t)(tt + 2) * n, row0, col0, n, m);
+        {
+            const int nx = tt + STAGES - 1;          // the set whose copy is issued now; its stage was last read at iteration tt - 1
+            if (nx < T) {
+                const int ns = nx % STAGES;
+                if (BULK) g2_stage_bulk<PITCH>(g2_smem + ns * G2_STAGE_DOUBLES, F + (size_t)(nx + 1) * set_stride, Nrm + (size_t)(nx + 1) * n, row0, col0, n, m, &s_bar[ns]);
+                else g2_stage<VEC, PITCH>(g2_smem + ns * G2_STAGE_DOUBLES, F + (size_t)(nx + 1) * set_stride, Nrm + (size_t)(nx + 1) * n, row0, col0, n, m);
+            }
         }
         cp_async_commit();
-        const double* buf = g2_smem + (tt & 1) * G2_STAGE_DOUBLES;
-        const double* Fr = buf + (wr * 16 + g) * G2_PITCH + t;
-        const double* Fc = buf + PW_TILE * G2_PITCH + (wc * 32 + g) * G2_PITCH + t;
-        const double* nr = buf + 2 * PW_TILE * G2_PITCH;
+        const double* buf = g2_smem + cur * G2_STAGE_DOUBLES;
+        const double* Fr = buf + (wr * 16 + g) * PITCH + t;
+        const double* Fc = buf + PW_TILE * PITCH + (wc * 32 + g) * PITCH + t;
+        const double* nr = buf + 2 * PW_TILE * PITCH;
         double c[2][4][2];
         {
             const double n0 = -gam * nr[wr * 16 + g], n1 = -gam * nr[wr * 16 + 8 + g];
@@ -229,10 +244,10 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
         }
 #pragma unroll 2
         for (int kk = 0; kk < ksteps; ++kk) {
-            const double a0 = a_scale * Fr[kk * 4], a1 = a_scale * Fr[8 * G2_PITCH + kk * 4];
+            const double a0 = a_scale * Fr[kk * 4], a1 = a_scale * Fr[8 * PITCH + kk * 4];
             double b[4];
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) b[cb] = Fc[cb * 8 * G2_PITCH + kk * 4];
+            for (int cb = 0; cb < 4; ++cb) b[cb] = Fc[cb * 8 * PITCH + kk * 4];
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 dmma884(c[0][cb][0], c[0][cb][1], a0, b[cb]);
@@ -530,6 +545,9 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
         const bool no_clamp = hyp.a > 0.0 && worst < 650.0;
         // feature tiles through the bulk-copy (TMA) engine unless DQGP_GRAD_NO_BULK is set (A/B runs against per-thread cp.async)
         const bool use_bulk = getenv("DQGP_GRAD_NO_BULK") == nullptr;
+        // pitch 28 + three stages (copy issued two sets ahead) measured 1% SLOWER than pitch 36 + two stages at config 4 (8.74 against
+        // 8.63 ms): the copy is already hidden one set ahead; kept as an opt-in for A/B runs
+        const bool use_p28 = getenv("DQGP_GRAD_P28") != nullptr;
 #define DQGP_G2(OUT)                                                                                                         \
     do {                                                                                                                     \
         static bool attr_done_dev[64] = {false};        /* the attribute is per DEVICE (as gemm_init's flags) */            \
@@ -542,11 +560,13 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
+            DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, false, true, 28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM_P28)); \
             attr_done = true;                                                                                                \
         }                                                                                                                    \
         if ((m & 1) == 0 && (reinterpret_cast<uintptr_t>(d_F) & 15) == 0) {                                                  \
             if (use_bulk) {                                                                                                  \
-                if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+                if (no_clamp && m <= 28 && use_p28) grad_projected_dmma_kernel<OUT, 2, false, true, 28><<<tiles, PW_THREADS, G2_SMEM_P28, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+                else if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
                 else grad_projected_dmma_kernel<OUT, 2, true, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
             } else if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
             else grad_projected_dmma_kernel<OUT, 2><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
