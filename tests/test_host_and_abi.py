@@ -113,3 +113,73 @@ def test_synthetic_dataset_identical_to_oracle(d):
     for enc in ("yz_cx", "chebyshev"):
         a, b = d.synthetic_dataset(50, 3, enc), driver.synthetic_dataset(50, 3, enc)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def _python_plan(enc, q, dd, layers):
+    """Independent Python port of the planner's greedy pass grouping (csrc/circuit.cu: build_plan): gate indices per pass."""
+    from oracle import circuits
+    gates = circuits.build_circuit(enc, q, dd, layers)
+    done, passes, bmax = [False] * len(gates), [], min(q, 3)
+    while not all(done):
+        blk, blocked, members = [], 0, []
+        for g, gt in enumerate(gates):
+            if done[g]:
+                continue
+            two = gt.name in ("cx", "crz")
+            tgt = gt.q1 if two else gt.q0
+            qs = (1 << tgt) | ((1 << gt.q0) if two else 0)
+            if (qs & blocked) == 0 and (tgt in blk or len(blk) < bmax):
+                if tgt not in blk:
+                    blk.append(tgt)
+                members.append(g)
+                done[g] = True
+            else:
+                blocked |= qs
+        passes.append((sorted(blk), members))
+    return gates, passes
+
+
+@pytest.mark.parametrize("enc,q,dd,layers", [("kyriienko", 10, 6, 4), ("yz_cx", 8, 4, 3), ("chebyshev", 4, 2, 3), ("hubregtsen", 5, 2, 2)])
+def test_plan_statistics_match_an_independent_port(d, enc, q, dd, layers):
+    """Pass count, fused-op count and the executed-work counter of bench.py's statevector roofline
+    (dqgp_circuit_shifted_u2_applications) against a Python port of the planner: host-side, no device needed."""
+    ec = d.EncodingCircuit(enc, q, dd, layers)
+    gates, passes = _python_plan(enc, q, dd, layers)
+    lib = d.load()
+    assert lib.dqgp_circuit_num_passes(ec.handle) == len(passes)
+    # fused ops per pass: runs of 1-qubit gates on one qubit collapse into one 2x2 unitary until a 2-qubit gate touches the qubit
+    cost, par_pass, uses, n_u2 = [], {}, {}, 0
+    for ip, (blk, members) in enumerate(passes):
+        open_q, u2, crz = set(), 0, 0
+        for g in members:
+            gt = gates[g]
+            if gt.name in ("cx", "crz"):
+                open_q.discard(gt.q1); open_q.discard(gt.q0)
+                crz += gt.name == "crz"
+            elif gt.q0 not in open_q:
+                open_q.add(gt.q0); u2 += 1
+            if gt.pidx >= 0:
+                par_pass[gt.pidx] = (ip, gt.name == "crz")
+                uses[gt.pidx] = uses.get(gt.pidx, 0) + 1
+        cost.append(u2 + 0.375 * crz)
+        n_u2 += u2
+    n_ops = sum(sum(1 for g in m if gates[g].name in ("cx", "crz")) for _, m in passes) + n_u2
+    assert lib.dqgp_circuit_num_fused_ops(ec.handle) == n_ops
+    assert all(v == 1 for v in uses.values())
+    total = 2.0 * sum(cost) + sum((2.0 if is_crz else 1.0) * sum(cost[ip:]) for ip, is_crz in par_pass.values())
+    assert lib.dqgp_circuit_shifted_u2_applications(ec.handle) == int(total + 0.5)
+
+
+def test_use_parameter_shift_selects_the_reference_branch(d):
+    """agent_riemannian.py:383-404: True -> the (2P+1)-job workers (Gaussian training Grams, Q1); False + projected -> central
+    differences through the agent's own kernel (REAL outer kernel); False + fidelity -> analytic derivatives.  Host logic only."""
+    x, y = np.zeros((4, 2)), np.zeros(4)
+    mk = lambda **kw: d.RiemannianAgent("a", x, y, 3, 0.1, 100.0, 100.0, num_layers=1, encoding_type="yz_cx", outer_kernel="matern", **kw)
+    a = mk(use_parameter_shift=True, kernel_type="projected")
+    assert a.training_ignores_outer_kernel is True and a.gradient == "central_difference"
+    a = mk(use_parameter_shift=False, kernel_type="projected")
+    assert a.training_ignores_outer_kernel is False and a.gradient == "central_difference"
+    a = mk(use_parameter_shift=False, kernel_type="fidelity")
+    assert a.gradient == "analytic"
+    a = mk(use_parameter_shift=False, kernel_type="fidelity", gradient="central_difference", training_ignores_outer_kernel=True)
+    assert a.gradient == "central_difference" and a.training_ignores_outer_kernel is True
