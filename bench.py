@@ -112,9 +112,12 @@ def flops_per_entry(w):
 
 
 def run_ours(args, w):
+    """The headline workload in full (e2e, CPU baseline, rooflines), then - same process, same box - the other BASELINE configs
+    named in --also as compact entries under "other_workloads", so that config 5 (the scaling stress) and config 3 (the fidelity
+    kernel) are in the ONE JSON line the driver records."""
+    import gc
     import torch
     import torch.distributed as dist
-    import dqgp_b200 as d
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -126,6 +129,42 @@ def run_ours(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         pg = dist.group.WORLD
+    line = measure(args, w, args.workload, pg, world, rank, local_rank, full=True)
+    import dqgp_b200.agent as _agent
+    _agent._ENGINE_CACHE.clear()          # the e2e leg's engines (3 squares per agent) are not needed any more
+    others = {}
+    for name in [v for v in args.also.split(",") if v and v != args.workload]:
+        wo = WORKLOADS[name]
+        if wo["agents"] % world:
+            continue
+        gc.collect(); torch.cuda.empty_cache()
+        sub = copy_args(args, steps=max(2, min(args.steps, 3 if name == "cfg5" else 10)), warmup=3)
+        r = measure(sub, wo, name, pg, world, rank, local_rank, full=False)
+        if rank == 0:
+            others[name] = {k: r[k] for k in ("ms_per_step", "value", "admm_iters_per_s", "steps", "warmup", "phases_ms_one_agent", "roofline",
+                                              "step_level", "clocks", "final_z_head") if k in r}
+            others[name]["workload"] = r["config"]["workload"]
+            others[name]["rooflines_frac"] = {k: {"frac": v["frac"], **({"frac_executed": v["frac_executed"]} if "frac_executed" in v else {})}
+                                              for k, v in r["rooflines"].items()}
+    if rank == 0:
+        if others:
+            line["other_workloads"] = others
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def copy_args(args, **kw):
+    out = argparse.Namespace(**vars(args))
+    for k, v in kw.items():
+        setattr(out, k, v)
+    return out
+
+
+def measure(args, w, workload_name, pg, world, rank, local_rank, full):
+    import torch
+    import torch.distributed as dist
+    import dqgp_b200 as d
 
     shards, theta0, psi0, n_i, P = make_problem(w, world, rank)
     kw = dict(encoding_type=w["encoding"], kernel_type=w["kernel"], num_qubits=w["q"], num_layers=w["layers"], noise_std=NOISE_STD,
@@ -255,10 +294,10 @@ def run_ours(args, w):
         primary["traffic_note"] = ("dram__bytes_read+write of one launch under ncu (profiles/r01_traffic.json): " + tk.get("launch", tk.get("note", "")))
 
     # ---- e2e: host buffers through RiemannianAgent.train_and_update + host consensus ------------------------------
-    e2e = None if args.skip_e2e else run_e2e(args, w, d, torch, dist, world, rank, shards, theta0, psi0, n_i, P, entries_per_iter)
+    e2e = None if (args.skip_e2e or not full) else run_e2e(args, w, d, torch, dist, world, rank, shards, theta0, psi0, n_i, P, entries_per_iter)
 
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if full and rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_sample(w, n_i, P)
 
     launches = (sum(a.launches_per_step() for a in eng.agents) + 2) * world    # + consensus, the row exchange; all ranks
@@ -269,7 +308,7 @@ def run_ours(args, w):
             "admm_iters_per_s": 1e3 / ms_per_step,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "agents": w["agents"], "samples_per_agent": n_i, "parameters": P,
+            "config": {"workload": f"{workload_name}: {w['desc']}", "agents": w["agents"], "samples_per_agent": n_i, "parameters": P,
                        "parameter_sets": S, "entries_per_iteration": entries_per_iter, "agents_per_gpu": w["agents"] // world,
                        "training_outer_kernel": "gaussian" if not w["honour_outer"] else w["outer"],
                        "cache": "per-agent working set (3 x n_pad^2 fp64 = %.1f GB) exceeds the 126 MB L2; no flush needed" % (3 * 8 * np_pad ** 2 / 1e9),
@@ -278,9 +317,8 @@ def run_ours(args, w):
             "phases_ms_one_agent": phases, "roofline": primary, "rooflines": roof, "step_level": step_level, "cpu_baseline": cpu_base,
             "final_nll_rank0": [float(v) for v in nll], "final_z_head": [float(v) for v in z_final[:4]],
         }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def run_e2e(args, w, d, torch, dist, world, rank, shards, theta0, psi0, n_i, P, entries_per_iter):
@@ -413,6 +451,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--also", default="cfg5,cfg3", help="other BASELINE workloads measured after the headline one (compact entries "
+                                                        "under other_workloads); '' to skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--outer-blocks", type=int, default=0, help="Cholesky outer panel width in 128-blocks (0 = engine default)")
