@@ -138,7 +138,7 @@ def run_ours(args, w):
         if wo["agents"] % world:
             continue
         gc.collect(); torch.cuda.empty_cache()
-        sub = copy_args(args, steps=max(2, min(args.steps, 3 if name == "cfg5" else 10)), warmup=3)
+        sub = copy_args(args, steps=max(2, min(args.steps, 3 if name == "cfg5" else 20)), warmup=3 if name == "cfg5" else 5)
         r = measure(sub, wo, name, pg, world, rank, local_rank, full=False)
         if rank == 0:
             others[name] = {k: r[k] for k in ("ms_per_step", "value", "admm_iters_per_s", "steps", "warmup", "phases_ms_one_agent", "roofline",
@@ -284,7 +284,7 @@ def measure(args, w, workload_name, pg, world, rank, local_rank, full):
     traffic = load_json(os.path.join(ROOT, "profiles", "r01_traffic.json"), {})
     primary.update({"kernel": {"gradient": "grad_projected_dmma_kernel" if w["kernel"] == "projected" else "fidelity_dmma_kernel<1>",
                                "factor": "gemm_group_kernel", "gram": "gram_projected_dmma_kernel",
-                               "statevector": ("statevec_lc2_kernel<%d>" if w["q"] >= 9 else "statevec_lc_kernel<%d>") % w["q"]}[dominant], "phase": dominant,
+                               "statevector": ("statevec_lc2_kernel<%d>" if w["encoding"] in ("yz_cx", "kyriienko") else "statevec_lc_kernel<%d>") % w["q"]}[dominant], "phase": dominant,
                     "traffic": None, "peak_source": "profiles/r01_fp64_peak.json (measured on this pool: pure DMMA/DFMA issue loops)"
                     if primary["bound"] != "hbm" else "MEASURED_PEAKS.json"})
 

@@ -36,6 +36,7 @@ SIGNATURES = {
     "dqgp_circuit_num_parameters": (_i, [_vp]),
     "dqgp_circuit_num_gates": (_i, [_vp]),
     "dqgp_circuit_num_passes": (_i, [_vp]),
+    "dqgp_circuit_num_passes_cx_free": (_i, [_vp]),
     "dqgp_circuit_num_fused_ops": (_i, [_vp]),
     "dqgp_circuit_shifted_u2_applications": (C.c_longlong, [_vp]),
     "dqgp_circuit_describe": (_i, [_vp, C.POINTER(Gate), _i]),

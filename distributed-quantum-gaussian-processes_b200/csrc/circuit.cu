@@ -3,6 +3,7 @@
 // (ctor sites: reference main.py:68-83, agent_riemannian.py:51-66) with default options; the Kyriienko
 // program is this project's own definition because the reference's call has no upstream behaviour
 // (SURVEY Q13).  An independent restatement lives in oracle/circuits.py; tests compare the two.
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include "common.cuh"
@@ -220,6 +221,111 @@ static void build_plan(dqgp_circuit& c) {
     }
 }
 
+// CX-free plan (SvPass3): list scheduling over the circuit's events (fused 1-qubit runs, CX).  A CX whose predecessors are done is
+// applied to the map at once; a pass takes the (up to three) earliest ready fused unitaries, on distinct qubits; no CX lies between the
+// unitaries of a pass, so they all see one map.
+static void build_plan3(dqgp_circuit& c) {
+    c.has_plan3 = false;
+    c.n_passes3 = 0;
+    const int n = (int)c.gates.size(), q = c.q, P = c.P;
+    if (!c.shareable || P <= 0) return;
+    for (const auto& g : c.gates)
+        if (g.kind == DQGP_G_CRZ) return;
+    struct Event { bool cx; int a, b; int mat; };
+    std::vector<Event> ev;
+    std::vector<int> open_run(q, -1), gate_mat(n, -1);
+    for (int g = 0; g < n; ++g) {
+        const dqgp_gate& gt = c.gates[g];
+        if (gt.kind == DQGP_G_CX) {
+            open_run[gt.q0] = open_run[gt.q1] = -1;
+            ev.push_back({true, gt.q0, gt.q1, -1});
+        } else {
+            if (open_run[gt.q0] < 0) {
+                open_run[gt.q0] = (int)ev.size();
+                ev.push_back({false, gt.q0, -1, (int)c.mats3.size()});
+                SvMat m; m.g_begin = m.g_end = 0;
+                c.mats3.push_back(m);
+            }
+            gate_mat[g] = ev[open_run[gt.q0]].mat;
+        }
+    }
+    // constituent gates of every fused matrix, in application order
+    for (size_t f = 0; f < c.mats3.size(); ++f) {
+        c.mats3[f].g_begin = (int)c.mat_gates3.size();
+        for (int g = 0; g < n; ++g)
+            if (gate_mat[g] == (int)f) c.mat_gates3.push_back(g);
+        c.mats3[f].g_end = (int)c.mat_gates3.size();
+    }
+    const int ne = (int)ev.size();
+    std::vector<char> done(ne, 0);
+    auto ready = [&](int e) {
+        const unsigned qs = (1u << ev[e].a) | (ev[e].cx ? (1u << ev[e].b) : 0u);
+        for (int f = 0; f < e; ++f)
+            if (!done[f] && (qs & ((1u << ev[f].a) | (ev[f].cx ? (1u << ev[f].b) : 0u)))) return false;
+        return true;
+    };
+    std::vector<int> mask(q);
+    for (int k = 0; k < q; ++k) mask[k] = 1 << k;
+    auto fill_rest = [&](SvPass3& ps, const std::vector<int>& blk) {
+        int r = 0;
+        for (int k = 0; k < q; ++k) {
+            bool in = false;
+            for (int b : blk) in |= (b == k);
+            if (!in) ps.rest[r++] = mask[k];
+        }
+        for (; r < MAX_QUBITS; ++r) ps.rest[r] = 0;
+        ps.nq = (int)blk.size();
+        for (int l = 0; l < 3; ++l) ps.bm[l] = l < (int)blk.size() ? mask[blk[l]] : 0;
+    };
+    std::vector<int> mat_pass(c.mats3.size(), -1);
+    int left = ne;
+    while (left > 0) {
+        for (bool progress = true; progress;) {
+            progress = false;
+            for (int e = 0; e < ne; ++e)
+                if (!done[e] && ev[e].cx && ready(e)) { mask[ev[e].a] ^= mask[ev[e].b]; done[e] = 1; --left; progress = true; }
+        }
+        std::vector<int> blk, members;
+        for (int e = 0; e < ne && (int)blk.size() < 3; ++e)
+            if (!done[e] && !ev[e].cx && ready(e)) { blk.push_back(ev[e].a); members.push_back(e); }
+        if (members.empty()) break;
+        SvPass3 ps;
+        fill_rest(ps, blk);
+        ps.op_begin = (int)c.ops3.size();
+        for (size_t l = 0; l < members.size(); ++l) {
+            SvOp op;
+            op.kind = SV_U2; op.lbit = (int8_t)l; op.cloc = -1; op.cq = -1; op.pad = 0; op.idx = (int16_t)ev[members[l]].mat;
+            c.ops3.push_back(op);
+            mat_pass[ev[members[l]].mat] = (int)c.passes3.size();
+            done[members[l]] = 1; --left;
+        }
+        ps.op_end = (int)c.ops3.size();
+        c.passes3.push_back(ps);
+    }
+    if (left != 0) { c.passes3.clear(); c.ops3.clear(); c.mats3.clear(); c.mat_gates3.clear(); return; }   // cannot happen for a valid circuit
+    c.n_passes3 = (int)c.passes3.size();
+    // epilogue groups under the final map: qubits {0,1,2}, {3,4,5}, ... and the remainder
+    for (int k0 = 0; k0 < q; k0 += 3) {
+        std::vector<int> blk;
+        for (int k = k0; k < std::min(q, k0 + 3); ++k) blk.push_back(k);
+        SvPass3 ps;
+        fill_rest(ps, blk);
+        ps.op_begin = ps.op_end = 0;
+        c.passes3.push_back(ps);
+    }
+    // where each parameter enters: its rotation's fused matrix and that matrix's pass
+    c.par_mat3.assign(P, -1);
+    for (int i = 0; i < P; ++i) c.par_mat3[i] = gate_mat[c.par_gate[i]];
+    c.pass_par_begin3.assign(c.n_passes3 + 1, 0);
+    for (int ip = 0; ip < c.n_passes3; ++ip) {
+        c.pass_par_begin3[ip] = (int)c.pass_params3.size();
+        for (int i = 0; i < P; ++i)
+            if (c.par_mat3[i] >= 0 && mat_pass[c.par_mat3[i]] == ip) c.pass_params3.push_back(i);
+    }
+    c.pass_par_begin3[c.n_passes3] = (int)c.pass_params3.size();
+    c.has_plan3 = (int)c.pass_params3.size() == P;
+}
+
 static std::mutex g_upload_mutex;
 int circuit_on_device(const dqgp_circuit* cc) {
     dqgp_circuit* c = const_cast<dqgp_circuit*>(cc);
@@ -232,7 +338,8 @@ int circuit_on_device(const dqgp_circuit* cc) {
     DQGP_CUDA(cudaMemcpy(c->d_gates, c->gates.data(), sizeof(dqgp_gate) * c->gates.size(), cudaMemcpyHostToDevice));
     DQGP_CUDA(cudaMalloc(&c->d_passes, sizeof(SvPass) * c->passes.size()));
     DQGP_CUDA(cudaMemcpy(c->d_passes, c->passes.data(), sizeof(SvPass) * c->passes.size(), cudaMemcpyHostToDevice));
-    DQGP_CUDA(cudaMalloc(&c->d_ops, sizeof(SvOp) * c->ops.size()));
+    // the kernels stage n_gates op slots (#ops <= #gates): size the buffers accordingly
+    DQGP_CUDA(cudaMalloc(&c->d_ops, sizeof(SvOp) * std::max(c->ops.size(), c->gates.size())));
     DQGP_CUDA(cudaMemcpy(c->d_ops, c->ops.data(), sizeof(SvOp) * c->ops.size(), cudaMemcpyHostToDevice));
     DQGP_CUDA(cudaMalloc(&c->d_mats, sizeof(SvMat) * (c->mats.size() + 1)));
     DQGP_CUDA(cudaMemcpy(c->d_mats, c->mats.data(), sizeof(SvMat) * c->mats.size(), cudaMemcpyHostToDevice));
@@ -246,6 +353,23 @@ int circuit_on_device(const dqgp_circuit* cc) {
         pack.insert(pack.end(), c->pass_params.begin(), c->pass_params.end());
         DQGP_CUDA(cudaMalloc(&c->d_share, sizeof(int) * pack.size()));
         DQGP_CUDA(cudaMemcpy(c->d_share, pack.data(), sizeof(int) * pack.size(), cudaMemcpyHostToDevice));
+    }
+    if (c->has_plan3) {
+        DQGP_CUDA(cudaMalloc(&c->d_passes3, sizeof(SvPass3) * c->passes3.size()));
+        DQGP_CUDA(cudaMemcpy(c->d_passes3, c->passes3.data(), sizeof(SvPass3) * c->passes3.size(), cudaMemcpyHostToDevice));
+        DQGP_CUDA(cudaMalloc(&c->d_ops3, sizeof(SvOp) * std::max(c->ops3.size(), c->gates.size())));
+        DQGP_CUDA(cudaMemcpy(c->d_ops3, c->ops3.data(), sizeof(SvOp) * c->ops3.size(), cudaMemcpyHostToDevice));
+        DQGP_CUDA(cudaMalloc(&c->d_mats3, sizeof(SvMat) * c->mats3.size()));
+        DQGP_CUDA(cudaMemcpy(c->d_mats3, c->mats3.data(), sizeof(SvMat) * c->mats3.size(), cudaMemcpyHostToDevice));
+        DQGP_CUDA(cudaMalloc(&c->d_mat_gates3, sizeof(int) * c->mat_gates3.size()));
+        DQGP_CUDA(cudaMemcpy(c->d_mat_gates3, c->mat_gates3.data(), sizeof(int) * c->mat_gates3.size(), cudaMemcpyHostToDevice));
+        std::vector<int> pack;
+        pack.insert(pack.end(), c->par_gate.begin(), c->par_gate.end());
+        pack.insert(pack.end(), c->par_mat3.begin(), c->par_mat3.end());
+        pack.insert(pack.end(), c->pass_par_begin3.begin(), c->pass_par_begin3.end());
+        pack.insert(pack.end(), c->pass_params3.begin(), c->pass_params3.end());
+        DQGP_CUDA(cudaMalloc(&c->d_share3, sizeof(int) * pack.size()));
+        DQGP_CUDA(cudaMemcpy(c->d_share3, pack.data(), sizeof(int) * pack.size(), cudaMemcpyHostToDevice));
     }
     c->device = dev;
     return 0;
@@ -269,8 +393,10 @@ int dqgp_circuit_create(int encoding, int num_qubits, int num_features, int num_
     c->encoding = encoding; c->q = num_qubits; c->d = num_features; c->layers = num_layers;
     c->P = dqgp::count_parameters(encoding, num_qubits, num_layers);
     c->uses_acos = false; c->d_gates = nullptr; c->d_passes = nullptr; c->d_ops = nullptr; c->d_mats = nullptr; c->d_mat_gates = nullptr; c->d_share = nullptr; c->shareable = false;
+    c->d_passes3 = nullptr; c->d_ops3 = nullptr; c->d_mats3 = nullptr; c->d_mat_gates3 = nullptr; c->d_share3 = nullptr;
     dqgp::build(*c);
     dqgp::build_plan(*c);
+    dqgp::build_plan3(*c);
     c->device = -1;
     *out = c;   // the device copy of the program is made on first use (dqgp::circuit_on_device)
     return 0;
@@ -283,11 +409,17 @@ void dqgp_circuit_destroy(dqgp_circuit* c) {
     if (c->d_mats) cudaFree(c->d_mats);
     if (c->d_mat_gates) cudaFree(c->d_mat_gates);
     if (c->d_share) cudaFree(c->d_share);
+    if (c->d_passes3) cudaFree(c->d_passes3);
+    if (c->d_ops3) cudaFree(c->d_ops3);
+    if (c->d_mats3) cudaFree(c->d_mats3);
+    if (c->d_mat_gates3) cudaFree(c->d_mat_gates3);
+    if (c->d_share3) cudaFree(c->d_share3);
     delete c;
 }
 int dqgp_circuit_num_parameters(const dqgp_circuit* c) { return c ? c->P : -1; }
 int dqgp_circuit_num_gates(const dqgp_circuit* c) { return c ? (int)c->gates.size() : -1; }
 int dqgp_circuit_num_passes(const dqgp_circuit* c) { return c ? (int)c->passes.size() : -1; }
+int dqgp_circuit_num_passes_cx_free(const dqgp_circuit* c) { return c ? (c->has_plan3 ? c->n_passes3 : 0) : -1; }
 int dqgp_circuit_num_fused_ops(const dqgp_circuit* c) { return c ? (int)c->ops.size() : -1; }
 long long dqgp_circuit_shifted_u2_applications(const dqgp_circuit* c) {
     if (!c) return -1;
@@ -295,6 +427,19 @@ long long dqgp_circuit_shifted_u2_applications(const dqgp_circuit* c) {
     // dqgp_states_shifted: the base circuit twice (final base state + the pass-by-pass advance), then for every parameter the
     // passes from its own pass to the end - once for a rotation parameter (both signs from one fork), twice for a CRZ parameter.
     // A CRZ / CX op counts 3/8 of a 2x2 unitary (6 of 16 flops per pair) / nothing.  Without prefix sharing: (2P + 1) circuits.
+    if (c->has_plan3) {      // the CX-free plan (what dqgp_features_shifted runs for circuits without CRZ): fused unitaries only
+        const int np3 = c->n_passes3;
+        double all3 = 0.0, total3 = 0.0;
+        std::vector<double> cost3(np3, 0.0);
+        for (int ip = 0; ip < np3; ++ip) { cost3[ip] = c->passes3[ip].op_end - c->passes3[ip].op_begin; all3 += cost3[ip]; }
+        total3 = 2.0 * all3;
+        for (int ip = 0; ip < np3; ++ip) {
+            double suffix = 0.0;
+            for (int k = ip; k < np3; ++k) suffix += cost3[k];
+            total3 += (c->pass_par_begin3[ip + 1] - c->pass_par_begin3[ip]) * suffix;
+        }
+        return (long long)(total3 + 0.5);
+    }
     const int np = (int)c->passes.size();
     std::vector<double> pass_cost(np, 0.0);
     for (int ip = 0; ip < np; ++ip)

@@ -111,6 +111,19 @@ struct SvPass {
     int lead_end, trail_begin;
 };
 
+// Plan of the CX-free simulator (statevec_lc2_kernel<.., MAPPED = true>): circuits made of 1-qubit gates and CX only.  A CX is never
+// executed: amplitudes stay where they are and the map from LOGICAL basis index x to PHYSICAL position p = M x (M over GF(2), one
+// column mask per logical qubit) absorbs it - CX(c -> t) replaces the control's mask m_c by m_c ^ m_t.  A pass applies the fused 2x2
+// unitaries of <= 3 logical qubits: a thread owns the coset of span{bm} selected by the bits of its index (bit i <-> rest[i]),
+// register j holds the amplitude whose logical block bits are j, at position p0 ^ comb(j).  Entries past the real passes describe
+// the Pauli-feature epilogue's qubit groups under the FINAL map.
+struct SvPass3 {
+    int nq;                              // block size 1..3
+    int bm[3];                           // masks of the block's logical qubits (register bit l <-> bm[l])
+    int rest[dqgp::MAX_QUBITS];          // masks of the other logical qubits, ascending logical index: coset bit i <-> rest[i]
+    int op_begin, op_end;                // ops3 range (SV_U2 only: lbit, idx = fused matrix)
+};
+
 struct dqgp_circuit {
     int encoding, q, d, layers, P;
     bool uses_acos;
@@ -125,6 +138,18 @@ struct dqgp_circuit {
     std::vector<int> par_mat;       // [P] fused matrix containing that gate, or -1 (CRZ)
     std::vector<int> pass_par_begin;// [n_passes+1] ranges into pass_params
     std::vector<int> pass_params;   // [P] parameters ordered by the pass their op belongs to
+    // CX-free plan (has_plan3: no CRZ in the circuit, every parameter on one rotation)
+    bool has_plan3;
+    int n_passes3;                  // real passes; passes3 holds n_passes3 + ceil(q/3) entries (epilogue groups at the end)
+    std::vector<SvPass3> passes3;
+    std::vector<SvOp> ops3;
+    std::vector<SvMat> mats3;
+    std::vector<int> mat_gates3, par_mat3, pass_par_begin3, pass_params3;
+    SvPass3* d_passes3;
+    SvOp* d_ops3;
+    SvMat* d_mats3;
+    int* d_mat_gates3;
+    int* d_share3;                  // par_gate | par_mat3 | pass_par_begin3 | pass_params3
     int* d_share;                   // device copy: par_gate | par_mat | pass_par_begin | pass_params
     dqgp_gate* d_gates;            // device copies
     SvPass* d_passes;

@@ -15,6 +15,7 @@
 // __syncwarp separates passes.  The epilogue reduces <X_k>,<Y_k>,<Z_k> three qubits at a time from registers
 // with group-local shuffles, or streams the state to HBM for the fidelity kernel.
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 
 namespace dqgp {
@@ -1002,6 +1003,79 @@ __device__ __forceinline__ void sv_pass2(const double2* src0, const double2* src
     T::sync();
 }
 
+// ---- CX-free passes (SvPass3): the coset a thread owns is selected by the bits of its index through the pass's rest masks; register j
+// holds the amplitude whose logical block bits are j.  Only fused 2x2 unitaries are executed: CX gates live in the index map.
+template <int NREST>
+__device__ __forceinline__ int coset_base(const int* __restrict__ rest, int gi) {
+    int p0 = 0;
+#pragma unroll
+    for (int i = 0; i < NREST; ++i) p0 ^= (-((gi >> i) & 1)) & rest[i];
+    return p0;
+}
+
+template <int Q, int B, int NS, bool ALT>
+__device__ __noinline__ void run_pass3(const double2* __restrict__ src0, const double2* __restrict__ src1, double2* __restrict__ dst0,
+                                       double2* __restrict__ dst1, const SvPass3* __restrict__ pass, const SvOp* __restrict__ ops,
+                                       const double2* __restrict__ mats, int lig, int lps, int alt_mat0, const double2* __restrict__ alt_u0,
+                                       int alt_mat1, const double2* __restrict__ alt_u1) {
+    constexpr int N = 1 << B, GROUPS = (1 << Q) >> B;
+    const int m0 = pass->bm[0], m1 = pass->bm[1], m2 = pass->bm[2];
+    const int op_begin = pass->op_begin, op_end = pass->op_end;
+    int comb[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) comb[j] = ((j & 1) ? m0 : 0) ^ ((B > 1 && (j & 2)) ? m1 : 0) ^ ((B > 2 && (j & 4)) ? m2 : 0);
+    for (int gi = lig; gi < GROUPS; gi += lps) {
+        const int p0 = coset_base<Q - B>(pass->rest, gi);
+        int addr[N];
+        double2 r0[N], r1[N];      // r1 is dead code for NS == 1
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            addr[j] = sv_phys(p0 ^ comb[j]);
+            r0[j] = src0[addr[j]];
+            if (NS == 2) r1[j] = src1[addr[j]];
+        }
+        SvOp nxt = ops[op_begin];
+#pragma unroll 1
+        for (int o = op_begin; o < op_end; ++o) {
+            const SvOp op = nxt;
+            if (o + 1 < op_end) nxt = ops[o + 1];
+            const double2* u0 = mats + 4 * op.idx;
+            const double2* u1 = u0;
+            if (ALT) {
+                if (op.idx == alt_mat0) u0 = alt_u0;
+                if (NS == 2 && op.idx == alt_mat1) u1 = alt_u1;
+            }
+            double2 a = u0[0], b = u0[1], c = u0[2], d = u0[3];
+            if (op.lbit == 0) apply_u2<N, 0>(r0, a, b, c, d);
+            else if (B > 1 && op.lbit == 1) apply_u2<N, (B > 1 ? 1 : 0)>(r0, a, b, c, d);
+            else if (B > 2) apply_u2<N, (B > 2 ? 2 : 0)>(r0, a, b, c, d);
+            if (NS == 2) {
+                if (ALT && u1 != u0) { a = u1[0]; b = u1[1]; c = u1[2]; d = u1[3]; }
+                if (op.lbit == 0) apply_u2<N, 0>(r1, a, b, c, d);
+                else if (B > 1 && op.lbit == 1) apply_u2<N, (B > 1 ? 1 : 0)>(r1, a, b, c, d);
+                else if (B > 2) apply_u2<N, (B > 2 ? 2 : 0)>(r1, a, b, c, d);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            dst0[addr[j]] = r0[j];
+            if (NS == 2) dst1[addr[j]] = r1[j];
+        }
+    }
+}
+
+template <int Q, int NS, bool ALT>
+__device__ __forceinline__ void sv_pass3(const double2* src0, const double2* src1, double2* dst0, double2* dst1, const SvPass3* ps_ptr,
+                                         const SvOp* __restrict__ ops, const double2* __restrict__ u2, int lig, int am0, const double2* au0,
+                                         int am1, const double2* au1) {
+    using T = SvTeam<Q>;
+    const int nq = ps_ptr->nq;
+    if (nq == 3) run_pass3<Q, (Q >= 3 ? 3 : 1), NS, ALT>(src0, src1, dst0, dst1, ps_ptr, ops, u2, lig, T::SIZE, am0, au0, am1, au1);
+    else if (nq == 2) run_pass3<Q, (Q >= 2 ? 2 : 1), NS, ALT>(src0, src1, dst0, dst1, ps_ptr, ops, u2, lig, T::SIZE, am0, au0, am1, au1);
+    else run_pass3<Q, 1, NS, ALT>(src0, src1, dst0, dst1, ps_ptr, ops, u2, lig, T::SIZE, am0, au0, am1, au1);
+    T::sync();
+}
+
 // Sum v[0..N) over the W (power of two, <= 32, aligned) lanes of a team, halving the data with every shuffle step: a lane
 // whose bit m is set keeps the upper half and sends the lower one.  Afterwards slots [0, max(1, N/W)) of every lane hold the team
 // totals of the original indices idx_base + slot; when N < W the remaining steps all-reduce and `writer` marks one lane per index.
@@ -1036,26 +1110,36 @@ struct TeamReduceLeft { static constexpr int value = (N / W) > 1 ? (N / W) : 1; 
 
 // value ids of one fork in the reduction buffer: [Bx | By | Bz | Cx | Cy | Cz] x Q, B = <phi|O|phi> (X, Y without their factor 2),
 // C = Re<psi|O|phi>; red[id * NW + warp]
-template <int Q, int B>
+// MAPPED: positions through the final index map of the CX-free plan (`grp`: the group's block / rest masks)
+template <int Q, int B, bool MAPPED = false>
 __device__ __forceinline__ void lc2_group_xy(const double2* __restrict__ fin, const double2* __restrict__ scr, int k0, int lig, int warp,
-                                             double* __restrict__ red) {
+                                             double* __restrict__ red, const SvPass3* __restrict__ grp = nullptr) {
     using T = SvTeam<Q>;
     constexpr int N = 1 << B, NV = 16, W = T::SIZE < 32 ? T::SIZE : 32, NW = T::BLOCK ? T::SIZE / 32 : 1;
     const int groups = T::DIM >> B;
     double v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = 0.0;
+    int comb[N];
+    if (MAPPED) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) comb[j] = ((j & 1) ? grp->bm[0] : 0) ^ ((B > 1 && (j & 2)) ? grp->bm[1] : 0) ^ ((B > 2 && (j & 4)) ? grp->bm[2] : 0);
+    }
     for (int gi = lig; gi < groups; gi += T::SIZE) {
         int base = gi;
+        if (MAPPED) {
+            base = coset_base<Q - B>(grp->rest, gi);
+        } else {
 #pragma unroll
-        for (int l = 0; l < B; ++l) base = insert_zero_bit(base, k0 + l);
+            for (int l = 0; l < B; ++l) base = insert_zero_bit(base, k0 + l);
+        }
         double2 p[N], s[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             int o = 0;
 #pragma unroll
             for (int l = 0; l < B; ++l) o += ((j >> l) & 1) << (k0 + l);
-            const int a = sv_phys(base + o);
+            const int a = MAPPED ? sv_phys(base ^ comb[j]) : sv_phys(base + o);
             p[j] = fin[a];
             s[j] = scr[a];
         }
@@ -1089,20 +1173,25 @@ __device__ __forceinline__ void lc2_group_xy(const double2* __restrict__ fin, co
 }
 
 // Z observables of a fork from ONE layout (block qubits 0, 1, 2): <phi|Z_k|phi> = sum_a (+-)|phi_a|^2, Re<psi|Z_k|phi> likewise
-template <int Q>
+template <int Q, bool MAPPED = false>
 __device__ __forceinline__ void lc2_group_z(const double2* __restrict__ fin, const double2* __restrict__ scr, int lig, int warp,
-                                            double* __restrict__ red) {
+                                            double* __restrict__ red, const SvPass3* __restrict__ grp = nullptr) {
     using T = SvTeam<Q>;
     constexpr int NZ = (2 * Q <= 16) ? 16 : 32, W = T::SIZE < 32 ? T::SIZE : 32, NW = T::BLOCK ? T::SIZE / 32 : 1;
     double v[NZ];
 #pragma unroll
     for (int i = 0; i < NZ; ++i) v[i] = 0.0;
+    int comb[8];
+    if (MAPPED) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) comb[j] = ((j & 1) ? grp->bm[0] : 0) ^ ((j & 2) ? grp->bm[1] : 0) ^ ((j & 4) ? grp->bm[2] : 0);
+    }
     for (int gi = lig; gi < (T::DIM >> 3); gi += T::SIZE) {
-        const int base = gi << 3;
+        const int base = MAPPED ? coset_base<(Q >= 3 ? Q - 3 : 0)>(grp->rest, gi) : (gi << 3);
         double pp[8], ww[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int a = sv_phys(base + j);
+            const int a = MAPPED ? sv_phys(base ^ comb[j]) : sv_phys(base + j);
             const double2 ps = fin[a], ph = scr[a];
             pp[j] = fma(ph.x, ph.x, ph.y * ph.y);
             ww[j] = fma(ps.x, ph.x, ps.y * ph.y);
@@ -1142,18 +1231,27 @@ __device__ __forceinline__ void lc2_group_z(const double2* __restrict__ fin, con
 }
 
 // one fork's epilogue: both central-difference sets of parameter i from A = <psi|O|psi> (featA), B, C
-template <int Q>
+// all partial sums of one fork into `red` (no synchronisation); `grps`: the epilogue groups of the CX-free plan (MAPPED)
+template <int Q, bool MAPPED>
+__device__ __forceinline__ void lc2_collect(const double2* __restrict__ fin, const double2* __restrict__ scr, double* __restrict__ red, int lig,
+                                            const SvPass3* __restrict__ grps) {
+    using T = SvTeam<Q>;
+    constexpr int FULL = Q / 3, REM = Q % 3;
+    const int warp = T::BLOCK ? (lig >> 5) : 0;
+    lc2_group_z<Q, MAPPED>(fin, scr, lig, warp, red, grps);
+#pragma unroll 1
+    for (int b = 0; b < FULL; ++b) lc2_group_xy<Q, 3, MAPPED>(fin, scr, 3 * b, lig, warp, red, MAPPED ? grps + b : nullptr);
+    if (REM == 2) lc2_group_xy<Q, 2, MAPPED>(fin, scr, 3 * FULL, lig, warp, red, MAPPED ? grps + FULL : nullptr);
+    if (REM == 1) lc2_group_xy<Q, 1, MAPPED>(fin, scr, 3 * FULL, lig, warp, red, MAPPED ? grps + FULL : nullptr);
+}
+
+template <int Q, bool MAPPED = false>
 __device__ __forceinline__ void lc2_emit(const double2* __restrict__ fin, const double2* __restrict__ scr, const double* __restrict__ featA,
                                          double* __restrict__ red, int lig, bool live, double c0, double s0, double c1, double s1,
-                                         double* __restrict__ out_plus, double* __restrict__ out_minus) {
+                                         double* __restrict__ out_plus, double* __restrict__ out_minus, const SvPass3* __restrict__ grps = nullptr) {
     using T = SvTeam<Q>;
-    constexpr int FULL = Q / 3, REM = Q % 3, NW = T::BLOCK ? T::SIZE / 32 : 1, M3 = 3 * Q;
-    const int warp = T::BLOCK ? (lig >> 5) : 0;
-    lc2_group_z<Q>(fin, scr, lig, warp, red);
-#pragma unroll 1
-    for (int b = 0; b < FULL; ++b) lc2_group_xy<Q, 3>(fin, scr, 3 * b, lig, warp, red);
-    if (REM == 2) lc2_group_xy<Q, 2>(fin, scr, 3 * FULL, lig, warp, red);
-    if (REM == 1) lc2_group_xy<Q, 1>(fin, scr, 3 * FULL, lig, warp, red);
+    constexpr int NW = T::BLOCK ? T::SIZE / 32 : 1, M3 = 3 * Q;
+    lc2_collect<Q, MAPPED>(fin, scr, red, lig, grps);
     T::sync();
     if (live) {
         for (int k = lig; k < M3; k += T::SIZE) {
@@ -1169,25 +1267,39 @@ __device__ __forceinline__ void lc2_emit(const double2* __restrict__ fin, const 
     T::sync();
 }
 
+template <int Q, int NS, bool ALT, bool MAPPED, typename PassT>
+__device__ __forceinline__ void lc2_pass(const double2* src0, const double2* src1, double2* dst0, double2* dst1, const PassT* ps,
+                                         const SvOp* __restrict__ ops, const double2* __restrict__ u2, const double2* __restrict__ trig, int lig,
+                                         int am0, const double2* au0, int am1, const double2* au1) {
+    if constexpr (MAPPED) sv_pass3<Q, NS, ALT>(src0, src1, dst0, dst1, ps, ops, u2, lig, am0, au0, am1, au1);
+    else sv_pass2<Q, NS, ALT>(src0, src1, dst0, dst1, ps, ops, u2, trig, lig, am0, au0, am1, au1);
+}
+
 // PAIR = false: one fork at a time and three state copies (no second scratch): the variant for one-state-per-warp teams (q <= 8)
-template <int Q, bool PAIR>
+// MAPPED = true: the CX-free plan (SvPass3 passes; CX gates absorbed into the logical -> physical index map, Pauli features read
+// through the final map)
+template <int Q, bool PAIR, bool MAPPED>
 __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
-    const dqgp_gate* __restrict__ g_gates, int n_gates, const SvPass* __restrict__ g_passes, int n_passes, const SvOp* __restrict__ g_ops,
+    const dqgp_gate* __restrict__ g_gates, int n_gates, const typename std::conditional<MAPPED, SvPass3, SvPass>::type* __restrict__ g_passes,
+    int n_passes, const SvOp* __restrict__ g_ops,
     const SvMat* __restrict__ g_mats, int n_mats, const int* __restrict__ g_mat_gates, const int* __restrict__ g_share, int d, int P,
     int uses_acos, int pair_forks, const double* __restrict__ X, int n, const double* __restrict__ Pm, double* __restrict__ out) {
     using T = SvTeam<Q>;
+    using PassT = typename std::conditional<MAPPED, SvPass3, SvPass>::type;
     constexpr int M3 = 3 * Q, M3P = (M3 + 1) & ~1, NW = T::BLOCK ? T::SIZE / 32 : 1;
+    constexpr int N_EPI = MAPPED ? (Q + 2) / 3 : 0;        // epilogue group entries stored after the real passes
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int* par_gate = g_share;
     const int* par_mat = g_share + P;
     const int* pass_par_begin = g_share + 2 * P;
     const int* pass_params = g_share + 2 * P + n_passes + 1;
     // per CTA: the op list and the pass table (read in every pass; the rest of the gate program stays in global memory)
-    const size_t op_bytes = (sizeof(SvOp) * n_gates + 15) & ~size_t(15), pass_bytes = (sizeof(SvPass) * n_passes + 15) & ~size_t(15);
+    const size_t op_bytes = (sizeof(SvOp) * n_gates + 15) & ~size_t(15), pass_bytes = (sizeof(PassT) * (n_passes + N_EPI) + 15) & ~size_t(15);
     SvOp* s_ops = reinterpret_cast<SvOp*>(smem_raw);
-    SvPass* s_passes = reinterpret_cast<SvPass*>(smem_raw + op_bytes);
+    PassT* s_passes = reinterpret_cast<PassT*>(smem_raw + op_bytes);
     for (int i = threadIdx.x; i < n_gates; i += blockDim.x) s_ops[i] = g_ops[i];        // #ops <= #gates
-    for (int i = threadIdx.x; i < n_passes; i += blockDim.x) s_passes[i] = g_passes[i];
+    for (int i = threadIdx.x; i < n_passes + N_EPI; i += blockDim.x) s_passes[i] = g_passes[i];
+    const SvPass3* epi = reinterpret_cast<const SvPass3*>(s_passes + n_passes);        // MAPPED only
     __syncthreads();
     // per-team storage: base | scratch 0 | scratch 1 | final base state | cos/sin table | fused matrices | 2 fork matrices | acos | red | A
     const size_t team_bytes = sizeof(double2) * ((PAIR ? 4 : 3) * T::DIM + n_gates + 4 * n_mats + 8) + sizeof(double) * (((d + 1) & ~1) + 2 * M3 * NW + M3P + 8);
@@ -1231,8 +1343,21 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
         T::sync();
 
         // sweep 1: the final base state (kept for the cross terms) and the base set's features A
-        for (int ip = 0; ip < n_passes; ++ip) sv_pass2<Q, 1, false>(fin, fin, fin, fin, s_passes + ip, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
-        {
+        for (int ip = 0; ip < n_passes; ++ip) lc2_pass<Q, 1, false, MAPPED>(fin, fin, fin, fin, s_passes + ip, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
+        if (MAPPED) {
+            // A = <psi|O|psi> through the final index map: the fork epilogue's own sums with phi = psi
+            lc2_collect<Q, MAPPED>(fin, fin, red, lig, epi);
+            T::sync();
+            for (int k = lig; k < M3; k += T::SIZE) {
+                double Bv = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) Bv += red[k * NW + w];
+                featA[k] = (k < 2 * Q) ? 2.0 * Bv : Bv;
+            }
+            T::sync();
+            if (live)
+                for (int k = lig; k < M3; k += T::SIZE) out[(size_t)j * M3 + k] = featA[k];
+        } else {
             constexpr int FULL = Q / 3, REM = Q % 3;
 #pragma unroll 1
             for (int b = 0; b < FULL; ++b) features_block<(Q >= 3 ? 3 : 1), Q>(fin, 3 * b, lig, T::SIZE, true, featA, red);
@@ -1247,7 +1372,7 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
         // sweep 2: advance the base pass by pass; before pass ip runs, fork every parameter whose rotation lives in it
         for (int ip = 0; ip < n_passes; ++ip) {
             const int pb = pass_par_begin[ip], pe = pass_par_begin[ip + 1];
-            const SvPass* ps0 = s_passes + ip;
+            const PassT* ps0 = s_passes + ip;
             for (int f0 = pb; f0 < pe; f0 += ((PAIR && pair_forks) ? 2 : 1)) {
                 const int i0 = pass_params[f0];
                 const int i1 = (PAIR && pair_forks && f0 + 1 < pe) ? pass_params[f0 + 1] : -1;
@@ -1266,36 +1391,39 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
                 }
                 T::sync();
                 if (PAIR && i1 >= 0) {
-                    sv_pass2<Q, (PAIR ? 2 : 1), true>(base, base, scr0, scr1, ps0, s_ops, u2, trig, lig, par_mat[i0], altm, par_mat[i1], altm + 4);
+                    lc2_pass<Q, (PAIR ? 2 : 1), true, MAPPED>(base, base, scr0, scr1, ps0, s_ops, u2, trig, lig, par_mat[i0], altm, par_mat[i1], altm + 4);
                     for (int kp = ip + 1; kp < n_passes; ++kp)
-                        sv_pass2<Q, (PAIR ? 2 : 1), false>(scr0, scr1, scr0, scr1, s_passes + kp, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
+                        lc2_pass<Q, (PAIR ? 2 : 1), false, MAPPED>(scr0, scr1, scr0, scr1, s_passes + kp, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
                 } else {
-                    sv_pass2<Q, 1, true>(base, base, scr0, scr0, ps0, s_ops, u2, trig, lig, par_mat[i0], altm, -1, nullptr);
+                    lc2_pass<Q, 1, true, MAPPED>(base, base, scr0, scr0, ps0, s_ops, u2, trig, lig, par_mat[i0], altm, -1, nullptr);
                     for (int kp = ip + 1; kp < n_passes; ++kp)
-                        sv_pass2<Q, 1, false>(scr0, scr0, scr0, scr0, s_passes + kp, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
+                        lc2_pass<Q, 1, false, MAPPED>(scr0, scr0, scr0, scr0, s_passes + kp, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
                 }
 #pragma unroll 1
                 for (int e = 0; e < 2; ++e) {
                     const int i = e == 0 ? i0 : i1;
                     if (i < 0) break;
-                    lc2_emit<Q>(fin, e == 0 ? scr0 : scr1, featA, red, lig, live, coef[4 * e], coef[4 * e + 1], coef[4 * e + 2], coef[4 * e + 3],
-                                out + ((size_t)(1 + 2 * i) * n + j) * M3, out + ((size_t)(2 + 2 * i) * n + j) * M3);
+                    lc2_emit<Q, MAPPED>(fin, e == 0 ? scr0 : scr1, featA, red, lig, live, coef[4 * e], coef[4 * e + 1], coef[4 * e + 2], coef[4 * e + 3],
+                                        out + ((size_t)(1 + 2 * i) * n + j) * M3, out + ((size_t)(2 + 2 * i) * n + j) * M3, epi);
                 }
             }
-            sv_pass2<Q, 1, false>(base, base, base, base, ps0, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
+            lc2_pass<Q, 1, false, MAPPED>(base, base, base, base, ps0, s_ops, u2, trig, lig, -1, nullptr, -1, nullptr);
         }
         T::sync();
     }
 }
 
-template <int Q>
+template <int Q, bool MAPPED>
 static int launch_sv_lc2(const dqgp_circuit* c, const double* X, int n, const double* Pm, double* out, cudaStream_t st) {
     using T = SvTeam<Q>;
-    const int n_gates = (int)c->gates.size(), n_passes = (int)c->passes.size(), n_mats = (int)c->mats.size();
+    using PassT = typename std::conditional<MAPPED, SvPass3, SvPass>::type;
+    const int n_gates = (int)c->gates.size();
+    const int n_passes = MAPPED ? c->n_passes3 : (int)c->passes.size(), n_mats = (int)(MAPPED ? c->mats3.size() : c->mats.size());
+    const int n_epi = MAPPED ? (Q + 2) / 3 : 0;
     constexpr int M3 = 3 * Q, M3P = (M3 + 1) & ~1, NW = T::BLOCK ? T::SIZE / 32 : 1;
     constexpr bool PAIR = T::BLOCK;
     const size_t team_bytes = sizeof(double2) * ((PAIR ? 4 : 3) * T::DIM + n_gates + 4 * n_mats + 8) + sizeof(double) * (((c->d + 1) & ~1) + 2 * M3 * NW + M3P + 8);
-    const size_t fixed = ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(SvPass) * n_passes + 15) & ~size_t(15));
+    const size_t fixed = ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(PassT) * (n_passes + n_epi) + 15) & ~size_t(15));
     int warps = T::BLOCK ? T::SIZE / 32 : 4;
     if (!T::BLOCK) {
         // CTA size that keeps the most warps resident under the shared-memory limit (four state copies per team)
@@ -1309,7 +1437,7 @@ static int launch_sv_lc2(const dqgp_circuit* c, const double* X, int n, const do
     const int teams = T::BLOCK ? 1 : warps * T::PER_WARP;
     const size_t smem = fixed + team_bytes * teams;
     if (smem > 227 * 1024) return 1;          // caller falls back to the one-fork kernel
-    auto kern = statevec_lc2_kernel<Q, PAIR>;
+    auto kern = statevec_lc2_kernel<Q, PAIR, MAPPED>;
     DQGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     DQGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
@@ -1319,8 +1447,12 @@ static int launch_sv_lc2(const dqgp_circuit* c, const double* X, int n, const do
     if (blocks > cap) blocks = cap;
     if (blocks < 1) return 0;
     const int pair_forks = getenv("DQGP_SV_NO_PAIR") == nullptr;
-    kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d_passes, n_passes, c->d_ops, c->d_mats, n_mats, c->d_mat_gates,
-                                                    c->d_share, c->d, c->P, c->uses_acos ? 1 : 0, pair_forks, X, n, Pm, out);
+    if constexpr (MAPPED)
+        kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d_passes3, n_passes, c->d_ops3, c->d_mats3, n_mats, c->d_mat_gates3,
+                                                        c->d_share3, c->d, c->P, c->uses_acos ? 1 : 0, pair_forks, X, n, Pm, out);
+    else
+        kern<<<(unsigned)blocks, warps * 32, smem, st>>>(c->d_gates, n_gates, c->d_passes, n_passes, c->d_ops, c->d_mats, n_mats, c->d_mat_gates,
+                                                        c->d_share, c->d, c->P, c->uses_acos ? 1 : 0, pair_forks, X, n, Pm, out);
     DQGP_LAUNCH_CHECK("statevec_lc2_kernel");
     return 0;
 }
@@ -1337,14 +1469,18 @@ static int launch_sv_shared(const dqgp_circuit* c, const double* X, int n, const
     // linear-combination form (statevec_lc_kernel) unless DQGP_SV_NO_LC is set (A/B checks against the two-fork kernel) or its
     // third copy of the state does not fit in shared memory (q = 12 with a long gate list)
     bool use_lc = getenv("DQGP_SV_NO_LC") == nullptr;
-    // lc2 (two forks per pass, fused epilogue) wins where a CTA owns the state (q >= 9: config 5, 60 -> 44 ms); with one state per
-    // warp (q <= 8) its fourth state copy and larger code cost more than they save (config 4: 4.4 ms against 3.9), so the
-    // one-fork kernel below stays the default there (DQGP_SV_FORCE_LC2 overrides, for tests and A/B runs)
-    if (!WANT_STATES && Q >= 3 && use_lc && getenv("DQGP_SV_NO_LC2") == nullptr && (T::BLOCK || getenv("DQGP_SV_FORCE_LC2") != nullptr)) {
+    // lc2 (fused epilogue, halving reductions; two forks per pass where a CTA owns the state) for circuits whose parameters all sit on
+    // rotations.  With the CX-free plan (no CRZ in the circuit: yz_cx, kyriienko) it is the default for every q: config 5's shard
+    // 60 -> 36 ms, config 4's 3.9 -> 3.1 ms.  Without that plan its larger code only pays for q >= 9 (one state per warp: instruction-fetch
+    // bound, 4.3 ms against 3.9), so the one-fork kernel below stays the default there (DQGP_SV_FORCE_LC2 overrides, for tests / A-B)
+    if (!WANT_STATES && Q >= 3 && use_lc && getenv("DQGP_SV_NO_LC2") == nullptr &&
+        (T::BLOCK || getenv("DQGP_SV_FORCE_LC2") != nullptr || (c->has_plan3 && getenv("DQGP_SV_NO_MAPPED") == nullptr))) {
         bool all_rot = true;
         for (int i = 0; i < c->P; ++i) all_rot = all_rot && c->par_mat[i] >= 0;
         if (all_rot) {
-            const int rc = launch_sv_lc2<(Q >= 3 ? Q : 3)>(c, X, n, Pm, out, st);
+            // the CX-free plan when the circuit has one (no CRZ): CX gates cost nothing and the pass loop shrinks to fused 2x2 unitaries
+            const bool mapped = c->has_plan3 && getenv("DQGP_SV_NO_MAPPED") == nullptr;
+            const int rc = mapped ? launch_sv_lc2<(Q >= 3 ? Q : 3), true>(c, X, n, Pm, out, st) : launch_sv_lc2<(Q >= 3 ? Q : 3), false>(c, X, n, Pm, out, st);
             if (rc <= 0) return rc;          // 1 = does not fit in shared memory: the one-fork kernel below
         }
     }

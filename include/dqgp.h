@@ -60,6 +60,8 @@ void dqgp_circuit_destroy(dqgp_circuit* c);
 int dqgp_circuit_num_parameters(const dqgp_circuit* c); /* = encoding_circuit.num_parameters (main.py:199) */
 int dqgp_circuit_num_gates(const dqgp_circuit* c);
 int dqgp_circuit_num_passes(const dqgp_circuit* c); /* shared-memory passes of the register-blocked simulator */
+int dqgp_circuit_num_passes_cx_free(const dqgp_circuit* c); /* passes of the CX-free plan (CX gates absorbed into the index map);
+                                                              0 when the circuit has CRZ gates or a parameter feeding several gates */
 int dqgp_circuit_num_fused_ops(const dqgp_circuit* c); /* ops after fusing runs of 1-qubit gates (2x2 unitaries + CX/CRZ) */
 /* executed simulator work per SAMPLE of dqgp_features_shifted / dqgp_states_shifted, in fused 2x2-unitary applications
  * (16 * 2^(q-1) flops each): bench.py's statevector roofline */

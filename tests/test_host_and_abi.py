@@ -167,6 +167,35 @@ def test_plan_statistics_match_an_independent_port(d, enc, q, dd, layers):
     assert lib.dqgp_circuit_num_fused_ops(ec.handle) == n_ops
     assert all(v == 1 for v in uses.values())
     total = 2.0 * sum(cost) + sum((2.0 if is_crz else 1.0) * sum(cost[ip:]) for ip, is_crz in par_pass.values())
+    ref3 = _python_cx_free_plan(enc, q, dd, layers)
+    if ref3 is not None:
+        # circuits without CRZ run the CX-free plan: the counter follows THAT plan (one fused unitary per qubit of a pass)
+        passes3 = ref3[0]
+        gates3 = gates
+        # pass of every parameter: replay the event construction to find which run (and so which pass) owns the parameter's gate
+        run_of_gate, open_run, runs = {}, {}, []
+        for g, gt in enumerate(gates3):
+            if gt.name == "cx":
+                open_run.pop(gt.q0, None); open_run.pop(gt.q1, None)
+            else:
+                if gt.q0 not in open_run:
+                    open_run[gt.q0] = len(runs); runs.append(gt.q0)
+                run_of_gate[g] = open_run[gt.q0]
+        # runs are consumed per qubit in order: the k-th run of qubit a is the k-th time a appears in the passes
+        seen, run_pass, counters = {}, {}, {}
+        for ip, blk in enumerate(passes3):
+            for a in blk:
+                counters[a] = counters.get(a, 0) + 1
+                seen[(a, counters[a])] = ip
+        occ = {}
+        for r, a in enumerate(runs):
+            occ[a] = occ.get(a, 0) + 1
+            run_pass[r] = seen[(a, occ[a])]
+        cost3 = [len(blk) for blk in passes3]
+        total = 2.0 * sum(cost3)
+        for g, gt in enumerate(gates3):
+            if gt.pidx >= 0:
+                total += sum(cost3[run_pass[run_of_gate[g]]:])
     assert lib.dqgp_circuit_shifted_u2_applications(ec.handle) == int(total + 0.5)
 
 
@@ -183,3 +212,55 @@ def test_use_parameter_shift_selects_the_reference_branch(d):
     assert a.gradient == "analytic"
     a = mk(use_parameter_shift=False, kernel_type="fidelity", gradient="central_difference", training_ignores_outer_kernel=True)
     assert a.gradient == "central_difference" and a.training_ignores_outer_kernel is True
+
+
+def _python_cx_free_plan(enc, q, dd, layers):
+    """Independent port of the CX-free planner (csrc/circuit.cu: build_plan3): list scheduling over fused 1-qubit runs and CX gates,
+    a ready CX is absorbed into the index map at once (control's mask ^= target's mask), a pass takes the earliest <= 3 ready runs."""
+    from oracle import circuits
+    gates = circuits.build_circuit(enc, q, dd, layers)
+    events, open_run = [], {}
+    for gt in gates:
+        if gt.name == "crz":
+            return None
+        if gt.name == "cx":
+            open_run.pop(gt.q0, None); open_run.pop(gt.q1, None)
+            events.append(("cx", gt.q0, gt.q1))
+        elif gt.q0 not in open_run:
+            open_run[gt.q0] = len(events)
+            events.append(("u2", gt.q0, -1))
+    done, mask, passes = [False] * len(events), [1 << k for k in range(q)], []
+    qubits = lambda e: {events[e][1]} | ({events[e][2]} if events[e][0] == "cx" else set())
+    ready = lambda e: all(done[f] or not (qubits(e) & qubits(f)) for f in range(e))
+    while not all(done):
+        progress = True
+        while progress:
+            progress = False
+            for e, ev in enumerate(events):
+                if not done[e] and ev[0] == "cx" and ready(e):
+                    mask[ev[1]] ^= mask[ev[2]]; done[e] = True; progress = True
+        blk = [e for e, ev in enumerate(events) if not done[e] and ev[0] == "u2" and ready(e)][:3]
+        if not blk:
+            break
+        for e in blk:
+            done[e] = True
+        passes.append([events[e][1] for e in blk])
+    return passes, mask
+
+
+@pytest.mark.parametrize("enc,q,dd,layers,expect", [("kyriienko", 10, 6, 4, 14), ("yz_cx", 8, 4, 3, 8), ("yz_cx", 11, 5, 1, 4),
+                                                   ("kyriienko", 12, 6, 4, 16), ("chebyshev", 4, 2, 3, 0), ("hubregtsen", 5, 2, 2, 0)])
+def test_cx_free_plan_pass_count(d, enc, q, dd, layers, expect):
+    ec = d.EncodingCircuit(enc, q, dd, layers)
+    got = d.load().dqgp_circuit_num_passes_cx_free(ec.handle)
+    assert got == expect
+    ref = _python_cx_free_plan(enc, q, dd, layers)
+    assert got == (0 if ref is None else len(ref[0]))
+    if ref is not None:
+        # the final index map is a bijection: its column masks are linearly independent over GF(2)
+        basis = []
+        for m in ref[1]:
+            for b in basis:
+                m = min(m, m ^ b)
+            assert m != 0
+            basis.append(m)
