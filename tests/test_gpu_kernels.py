@@ -53,7 +53,10 @@ def test_features_and_states_match_oracle(d, enc, q, dd, layers):
 
 @pytest.mark.parametrize("enc,q,dd,layers", [("chebyshev", 3, 2, 1), ("chebyshev", 4, 2, 3), ("hubregtsen", 5, 2, 2), ("yz_cx", 8, 4, 3),
                                             ("yz_cx", 1, 1, 2), ("kyriienko", 10, 6, 2), ("hubregtsen", 9, 3, 1), ("yz_cx", 6, 3, 2),
-                                            ("yz_cx", 12, 4, 1), ("kyriienko", 12, 6, 4)])
+                                            ("yz_cx", 12, 4, 1), ("kyriienko", 12, 6, 4),
+                                            # every qubit count of the CX-free lc2 kernel (team = 1 .. 32 lanes, then a CTA)
+                                            ("yz_cx", 3, 2, 2), ("kyriienko", 4, 3, 2), ("yz_cx", 5, 2, 3), ("kyriienko", 7, 4, 2),
+                                            ("yz_cx", 9, 3, 2), ("kyriienko", 11, 5, 1)])
 def test_shared_prefix_simulation_matches_per_set_kernels(d, enc, q, dd, layers, monkeypatch):
     """dqgp_features_shifted / dqgp_states_shifted over the 2P+1 central-difference sets against the per-set kernels:
     the two-fork prefix-sharing kernel bit for bit; the linear-combination kernel (one fork per rotation parameter, both
