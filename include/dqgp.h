@@ -64,7 +64,8 @@ int dqgp_circuit_num_passes_cx_free(const dqgp_circuit* c); /* passes of the CX-
                                                               0 when the circuit has CRZ gates or a parameter feeding several gates */
 int dqgp_circuit_num_fused_ops(const dqgp_circuit* c); /* ops after fusing runs of 1-qubit gates (2x2 unitaries + CX/CRZ) */
 /* executed simulator work per SAMPLE of dqgp_features_shifted / dqgp_states_shifted, in fused 2x2-unitary applications
- * (16 * 2^(q-1) flops each): bench.py's statevector roofline */
+ * (16 FMA = 32 flops per amplitude pair, 2^(q-1) pairs): bench.py's statevector roofline.  Follows the CX-free plan
+ * when the circuit has one (dqgp_circuit_num_passes_cx_free > 0), the CX-executing plan otherwise. */
 long long dqgp_circuit_shifted_u2_applications(const dqgp_circuit* c);
 int dqgp_circuit_describe(const dqgp_circuit* c, dqgp_gate* h_out, int capacity); /* host copy of the program */
 
@@ -76,7 +77,9 @@ int dqgp_states(const dqgp_circuit* c, const double* d_X, int n, const double* d
 
 /* Same outputs for the 2P+1 central-difference sets of dqgp_shift_parameter_sets (d_Pm (2P+1,P): row 0 the base
  * set, rows 1+2i / 2+2i differing from it in parameter i only), computed with prefix sharing: the part of the circuit
- * that precedes the shifted gate is simulated once per sample.  Bit-identical to dqgp_features / dqgp_states. */
+ * that precedes the shifted gate is simulated once per sample.  Equal to dqgp_features / dqgp_states to rounding (2e-14): both
+ * shifted sets of a rotation parameter are linear combinations of the base state and ONE forked state; features of circuits without
+ * CRZ gates (yz_cx, kyriienko) run the CX-free plan (CX gates absorbed into a logical -> physical index map). */
 int dqgp_features_shifted(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int P, double* d_F, void* stream);
 int dqgp_states_shifted(const dqgp_circuit* c, const double* d_X, int n, const double* d_Pm, int P, double* d_Psi, void* stream);
 
@@ -95,8 +98,12 @@ int dqgp_gram_fidelity(const double* d_Psi1, int n1, const double* d_Psi2, int n
 /* ---- fp64 Cholesky / solve / inverse (agent_riemannian.py:410-418, :442): for the SPD matrix
  *      A = K + sigma^2 I held in the solver (dqgp_solver_matrix, leading dimension dqgp_solver_ld):
  *      factor, alpha = A^-1 y, A^-1 (full symmetric, dqgp_solver_inverse), logdet(A).
- *      *d_info = 0 ok, j>0 = first non-positive pivot (1-based) so the host can mirror the
- *      reference's LU -> pinv ladder (agent_riemannian.py:419-428) or raise. */
+ *      *d_info = 0 ok, j>0 = first non-positive pivot (1-based): the host then walks the reference's ladder
+ *      (agent_riemannian.py:419-428) with dqgp_lu_solve_inv below.
+ *      NOT computed here: the reference's `condition_number = np.linalg.cond(C)` (agent_riemannian.py:411), a 2-norm SVD of the
+ *      UN-noised Gram used only in prints (main.py:2629-2642).  These Grams are numerically singular (cond ~ 1e17..1e19 in the
+ *      golden files), so its value is rounding noise of that particular SVD; an estimate from this factorisation of C + sigma^2 I
+ *      would be a different noise.  The Python layer returns NaN and offers a library SVD as a diagnostic opt-in. */
 int dqgp_solver_create(int n, dqgp_solver** out);
 /* outer_blocks: width of the outer Cholesky panel in 128-column blocks. 4 (default, = 0) gives rank-512 trailing
  * updates (best throughput when several agents share a GPU); < 0 = width 4 while more than 28 block columns remain and 2
