@@ -508,3 +508,17 @@ def test_agent_step_on_a_second_device_after_the_first(d):
                 g = eng.d_grad.cpu().numpy()
             assert np.max(np.abs(g - ref.grad)) < 1e-8 * max(1.0, np.abs(ref.grad).max()), (kt, dev)
     torch.cuda.set_device(0)
+
+
+def test_predict_propagates_nan_like_numpy(d):
+    """A chebyshev test point outside [-1, 1] gives a NaN row of K(test, train); np.maximum (main.py:1466) propagates the NaN into
+    the predictive variance, and so must the device epilogue (CUDA's fmax alone would return the 1e-10 floor instead)."""
+    g = load_golden("agent_step_cheb_proj_matern_q3.npz")
+    xt = g["X_test"].copy()
+    xt[3, 0] = 1.5                                   # arccos(1.5) = NaN
+    mean, var, *_ = d.predict_quantum_gp(g["X"], g["Y"], xt, np.mod(g["z"], np.pi), int(g["q"]), int(g["layers"]), 0.1, True,
+                                         str(g["encoding"]), str(g["kernel_type"]), "XYZ", str(g["outer_kernel"]))
+    assert np.isnan(mean[3]) and np.isnan(var[3])
+    ok = np.arange(len(mean)) != 3
+    assert np.max(np.abs(mean[ok] - g["pred_mean"][ok])) < 1e-8 * max(1.0, np.abs(g["pred_mean"]).max())
+    assert np.max(np.abs(var[ok] - g["pred_var"][ok])) < 1e-8
