@@ -1278,8 +1278,14 @@ __device__ __forceinline__ void lc2_pass(const double2* src0, const double2* src
 // PAIR = false: one fork at a time and three state copies (no second scratch): the variant for one-state-per-warp teams (q <= 8)
 // MAPPED = true: the CX-free plan (SvPass3 passes; CX gates absorbed into the logical -> physical index map, Pauli features read
 // through the final map)
+// Resident CTAs the register allocation must allow: lane-group teams (q <= 8) 4 x 128 threads; CTA-per-state teams up to q = 10 three
+// CTAs with pairing (four state copies, 73 KB), four without (three copies and the plan read from global memory: 56 KB per CTA at
+// q = 10 - measured 37.3 ms against 36.3 ms for the paired variant at config 5, so pairing stays the default; DQGP_SV_UNPAIRED for A/B).
+// Without the bound the paired q = 10 kernel takes 174 registers and drops to two CTAs per SM (39.8 ms).
+template <int Q, bool PAIR>
+struct Lc2Bounds { static constexpr int MIN_BLOCKS = !SvTeam<Q>::BLOCK ? (PAIR ? 3 : 0) : (Q > 10 ? 0 : (PAIR ? 3 : 4)); };   // 0 = unspecified
 template <int Q, bool PAIR, bool MAPPED>
-__global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
+__global__ void __launch_bounds__(SvTeam<Q>::THREADS, Lc2Bounds<Q, PAIR>::MIN_BLOCKS) statevec_lc2_kernel(
     const dqgp_gate* __restrict__ g_gates, int n_gates, const typename std::conditional<MAPPED, SvPass3, SvPass>::type* __restrict__ g_passes,
     int n_passes, const SvOp* __restrict__ g_ops,
     const SvMat* __restrict__ g_mats, int n_mats, const int* __restrict__ g_mat_gates, const int* __restrict__ g_share, int d, int P,
@@ -1294,11 +1300,22 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
     const int* pass_par_begin = g_share + 2 * P;
     const int* pass_params = g_share + 2 * P + n_passes + 1;
     // per CTA: the op list and the pass table (read in every pass; the rest of the gate program stays in global memory)
-    const size_t op_bytes = (sizeof(SvOp) * n_gates + 15) & ~size_t(15), pass_bytes = (sizeof(PassT) * (n_passes + N_EPI) + 15) & ~size_t(15);
-    SvOp* s_ops = reinterpret_cast<SvOp*>(smem_raw);
-    PassT* s_passes = reinterpret_cast<PassT*>(smem_raw + op_bytes);
-    for (int i = threadIdx.x; i < n_gates; i += blockDim.x) s_ops[i] = g_ops[i];        // #ops <= #gates
-    for (int i = threadIdx.x; i < n_passes + N_EPI; i += blockDim.x) s_passes[i] = g_passes[i];
+    constexpr bool STAGE_PLAN = !(T::BLOCK && !PAIR);      // the unpaired CTA-per-state variant spends its shared memory on a fourth CTA
+    const size_t op_bytes = STAGE_PLAN ? ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) : 0;
+    const size_t pass_bytes = STAGE_PLAN ? ((sizeof(PassT) * (n_passes + N_EPI) + 15) & ~size_t(15)) : 0;
+    const SvOp* s_ops;
+    const PassT* s_passes;
+    if constexpr (STAGE_PLAN) {          // (if constexpr: one address space per instantiation, so the staged reads stay LDS)
+        SvOp* so = reinterpret_cast<SvOp*>(smem_raw);
+        PassT* sp = reinterpret_cast<PassT*>(smem_raw + op_bytes);
+        for (int i = threadIdx.x; i < n_gates; i += blockDim.x) so[i] = g_ops[i];        // #ops <= #gates
+        for (int i = threadIdx.x; i < n_passes + N_EPI; i += blockDim.x) sp[i] = g_passes[i];
+        s_ops = so;
+        s_passes = sp;
+    } else {
+        s_ops = g_ops;
+        s_passes = g_passes;
+    }
     const SvPass3* epi = reinterpret_cast<const SvPass3*>(s_passes + n_passes);        // MAPPED only
     __syncthreads();
     // per-team storage: base | scratch 0 | scratch 1 | final base state | cos/sin table | fused matrices | 2 fork matrices | acos | red | A
@@ -1413,17 +1430,16 @@ __global__ void __launch_bounds__(SvTeam<Q>::THREADS) statevec_lc2_kernel(
     }
 }
 
-template <int Q, bool MAPPED>
-static int launch_sv_lc2(const dqgp_circuit* c, const double* X, int n, const double* Pm, double* out, cudaStream_t st) {
+template <int Q, bool MAPPED, bool PAIR>
+static int launch_sv_lc2_impl(const dqgp_circuit* c, const double* X, int n, const double* Pm, double* out, cudaStream_t st) {
     using T = SvTeam<Q>;
     using PassT = typename std::conditional<MAPPED, SvPass3, SvPass>::type;
     const int n_gates = (int)c->gates.size();
     const int n_passes = MAPPED ? c->n_passes3 : (int)c->passes.size(), n_mats = (int)(MAPPED ? c->mats3.size() : c->mats.size());
     const int n_epi = MAPPED ? (Q + 2) / 3 : 0;
     constexpr int M3 = 3 * Q, M3P = (M3 + 1) & ~1, NW = T::BLOCK ? T::SIZE / 32 : 1;
-    constexpr bool PAIR = T::BLOCK;
     const size_t team_bytes = sizeof(double2) * ((PAIR ? 4 : 3) * T::DIM + n_gates + 4 * n_mats + 8) + sizeof(double) * (((c->d + 1) & ~1) + 2 * M3 * NW + M3P + 8);
-    const size_t fixed = ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(PassT) * (n_passes + n_epi) + 15) & ~size_t(15));
+    const size_t fixed = (T::BLOCK && !PAIR) ? 0 : ((sizeof(SvOp) * n_gates + 15) & ~size_t(15)) + ((sizeof(PassT) * (n_passes + n_epi) + 15) & ~size_t(15));
     int warps = T::BLOCK ? T::SIZE / 32 : 4;
     if (!T::BLOCK) {
         // CTA size that keeps the most warps resident under the shared-memory limit (four state copies per team)
@@ -1455,6 +1471,18 @@ static int launch_sv_lc2(const dqgp_circuit* c, const double* X, int n, const do
                                                         c->d_share, c->d, c->P, c->uses_acos ? 1 : 0, pair_forks, X, n, Pm, out);
     DQGP_LAUNCH_CHECK("statevec_lc2_kernel");
     return 0;
+}
+
+template <int Q, bool MAPPED>
+static int launch_sv_lc2(const dqgp_circuit* c, const double* X, int n, const double* Pm, double* out, cudaStream_t st) {
+    if constexpr (SvTeam<Q>::BLOCK) {
+        // CTA per state: two forks per pass and three CTAs per SM, or (DQGP_SV_UNPAIRED, A/B) one fork and four CTAs per SM
+        if (getenv("DQGP_SV_UNPAIRED") != nullptr) return launch_sv_lc2_impl<Q, MAPPED, false>(c, X, n, Pm, out, st);
+        return launch_sv_lc2_impl<Q, MAPPED, true>(c, X, n, Pm, out, st);
+    } else {
+        if (getenv("DQGP_SV_PAIRED_SMALL") != nullptr) return launch_sv_lc2_impl<Q, MAPPED, true>(c, X, n, Pm, out, st);   // A/B only
+        return launch_sv_lc2_impl<Q, MAPPED, false>(c, X, n, Pm, out, st);
+    }
 }
 
 template <int Q, bool WANT_STATES>
