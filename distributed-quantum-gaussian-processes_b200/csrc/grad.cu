@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
         if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_init(&s_bar[2], 1); mbar_fence_init(); }
         __syncthreads();
     }
-    const double gam = (OUTER == DQGP_OUTER_GAUSSIAN) ? hyp.a : 1.0;
+    const double gam = (OUTER == DQGP_OUTER_GAUSSIAN) ? hyp.a * DQGP_EXP_S32 : 1.0;      // Gaussian: argument in units of ln2/32
     const double a_scale = 2.0 * gam;
     const double tab = exp_table_entry();
 
@@ -233,11 +233,11 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
         const double* nr = buf + 2 * PW_TILE * PITCH;
         double c[2][4][2];
         {
-            const double n0 = -gam * nr[wr * 16 + g], n1 = -gam * nr[wr * 16 + 8 + g];
+            const double n0 = nr[wr * 16 + g], n1 = nr[wr * 16 + 8 + g];            // already -gamma_eff |f|^2
 #pragma unroll
             for (int cb = 0; cb < 4; ++cb) {
                 const double2 nc = *reinterpret_cast<const double2*>(&nr[PW_TILE + wc * 32 + cb * 8 + 2 * t]);
-                const double m0 = -gam * nc.x, m1 = -gam * nc.y;
+                const double m0 = nc.x, m1 = nc.y;
                 c[0][cb][0] = n0 + m0; c[0][cb][1] = n0 + m1;
                 c[1][cb][0] = n1 + m0; c[1][cb][1] = n1 + m1;
             }
@@ -283,13 +283,13 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
 }
 
 // squared norms of every feature row: Nrm[s*n + j] = sum_k F[s][j][k]^2 (one warp per 4 rows)
-__global__ void feature_norms_kernel(const double* __restrict__ F, long long rows, int m, double* __restrict__ Nrm) {
+__global__ void feature_norms_kernel(const double* __restrict__ F, long long rows, int m, double scale, double* __restrict__ Nrm) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     const double* f = F + row * m;
     double acc = 0.0;
     for (int k = 0; k < m; ++k) acc = fma(f[k], f[k], acc);
-    Nrm[row] = acc;
+    Nrm[row] = scale * acc;
 }
 
 constexpr int FID_KC_G = 16;
@@ -537,7 +537,10 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
         }
     } else {
         const long long rows = (long long)(2 * P + 1) * n;
-        feature_norms_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d_F, rows, m, norms);
+        // the norms arrive pre-multiplied by -gamma_eff (and, Gaussian, by 32/ln2: the exponent's argument then leaves the DMMA in the
+        // units its range reduction wants): the kernel only adds them
+        const double gam_eff = (outer == DQGP_OUTER_GAUSSIAN) ? hyp.a * DQGP_EXP_S32 : 1.0;
+        feature_norms_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(d_F, rows, m, -gam_eff, norms);
         // Pauli features lie in [-1, 1]: gamma d^2 <= 4 m gamma, so the exponent guard is only needed for large gamma
         // the exponent's argument is bounded below by -gamma 4m (Gaussian), -sqrt(3) 2 sqrt(m) / l (Matern), -2 / l^2 (ExpSineSquared)
         const double worst = outer == DQGP_OUTER_GAUSSIAN ? 4.0 * m * hyp.a

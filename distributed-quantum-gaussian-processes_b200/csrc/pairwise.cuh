@@ -136,7 +136,8 @@ __device__ __forceinline__ double fast_sqrt_guarded(double x) {
 template <int OUTER, bool CLAMP>
 __device__ __forceinline__ double outer_grad_from_neg_gd2(double v, const OuterHyp& h, double tab) {
     if (OUTER == DQGP_OUTER_GAUSSIAN) {
-        return fast_exp_tab5(CLAMP ? fmax(v, -700.0) : v, tab);
+        // v arrives in units of ln2/32 (the kernel folds 32/ln2 into the DMMA operands): exact two-add range reduction
+        return fast_exp_tab5_scaled(CLAMP ? fmax(v, -700.0 * DQGP_EXP_S32) : v, tab);
     } else if (OUTER == DQGP_OUTER_MATERN15) {
         const double nk = fast_sqrt_guarded(-v) * (-1.7320508075688772 * h.a);      // -sqrt(3) d / l
         const double e = fast_exp_tab5(CLAMP ? fmax(nk, -700.0) : nk, tab);
