@@ -451,7 +451,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--also", default="cfg5,cfg3", help="other BASELINE workloads measured after the headline one (compact entries "
+    ap.add_argument("--also", default="cfg5,cfg3,cfg2,cfg1", help="other BASELINE workloads measured after the headline one (compact entries "
                                                         "under other_workloads); '' to skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
