@@ -378,7 +378,6 @@ def cpu_reference_sample(w, n_i, P, jobs=None):
     cores, bounded: `jobs` of the S = 2P+1 Gram jobs of ONE agent through a process pool of all cores (as
     agent_riemannian.py:261-262), plus the LAPACK sequence of agent_riemannian.py:410-418,442 (without the
     np.linalg.cond SVD) at a reduced n with n^3 extrapolation when n_i is large."""
-    from concurrent.futures import ProcessPoolExecutor
     from oracle import agent_step, driver
     cores = os.cpu_count() or 1
     S = 2 * P + 1
@@ -388,10 +387,10 @@ def cpu_reference_sample(w, n_i, P, jobs=None):
     cfg = agent_step.KernelConfig(w["encoding"], w["kernel"], w["q"], w["layers"], w["outer"], training_ignores_outer_kernel=not w["honour_outer"])
     z = np.round(np.random.RandomState(42).rand(P), 4)
     sets = agent_step.shifted_parameter_sets(z, H)[:jobs]
-    t0 = time.perf_counter()
-    with ProcessPoolExecutor(max_workers=cores) as pool:
+    with agent_step.process_pool(cores) as pool:
+        t0 = time.perf_counter()
         grams = list(pool.map(agent_step._gram_job, [(cfg, x, s) for s in sets]))
-    t_gram = time.perf_counter() - t0
+        t_gram = time.perf_counter() - t0
     n_la = min(n_i, 3072)
     c = grams[0][:n_la, :n_la]
     dk = np.zeros((1, n_la, n_la))

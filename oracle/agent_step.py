@@ -58,6 +58,21 @@ def _gram_job(args):
     return k.evaluate(x, x)
 
 
+def _noop(_):
+    return None
+
+
+def process_pool(workers: Optional[int]):
+    """The reference's process pool of shifted-kernel workers (agent_riemannian.py:261), started with "spawn" instead of the
+    platform's fork: with OpenBLAS 0.3.30 a threaded LAPACK call in the PARENT after a fork pool can deadlock (seen with
+    np.linalg.solve at n = 113).  The workers are started before the pool is returned, so a timed region around the map
+    excludes the interpreter start-up that fork would not pay."""
+    import multiprocessing
+    pool = ProcessPoolExecutor(max_workers=workers, mp_context=multiprocessing.get_context("spawn"))
+    list(pool.map(_noop, range(pool._max_workers)))
+    return pool
+
+
 def kernel_and_derivatives(cfg: KernelConfig, x, p, h, workers: Optional[int] = 1, subset=None):
     """K (n,n) and dK (P,n,n) by central differences, dK_i = (K(p+h e_i) - K(p-h e_i)) / (2h)
     (agent_riemannian.py:270-275, Q3).  ``workers`` > 1 mirrors the reference's nested process pool."""
@@ -68,7 +83,7 @@ def kernel_and_derivatives(cfg: KernelConfig, x, p, h, workers: Optional[int] = 
     if workers is not None and workers == 1:
         grams = [_gram_job(j) for j in jobs]
     else:
-        with ProcessPoolExecutor(max_workers=workers) as pool:
+        with process_pool(workers) as pool:
             grams = list(pool.map(_gram_job, jobs))
     if subset is not None:
         return grams

@@ -127,6 +127,16 @@ CFG2_ARGS = ("--input-dim 2 --n-dataset 1000 --encoding chebyshev --kernel-type 
              "--num-qubits 4 --outer-kernel matern --rho 100 --L 100 --n-agents 4")
 
 
+# configs[2], [3], [4] at sizes the reference's CPU path finishes in minutes: the other circuits and the fidelity kernel through the whole
+# of main.main() (data generation, partitioning, ADMM loop with per-iteration CV, best-CV consensus)
+CFG3S_ARGS = ("--input-dim 2 --n-dataset 1000 --encoding hubregtsen --kernel-type fidelity --num-layers 2 --num-qubits 5 "
+              "--rho 100 --L 100 --n-agents 8")
+CFG4S_ARGS = ("--input-dim 4 --n-dataset 1000 --encoding yz_cx --kernel-type projected --num-layers 2 --num-qubits 6 "
+              "--outer-kernel gaussian --rho 100 --L 100 --n-agents 8")
+CFG5S_ARGS = ("--input-dim 6 --n-dataset 1000 --encoding kyriienko --kernel-type projected --num-layers 2 --num-qubits 4 "
+              "--outer-kernel matern --rho 100 --L 100 --n-agents 4 --data-range -0.95 0.95")
+
+
 def trajectory_golden(max_iter=30, name="trajectory_cfg1", args=CFG1_ARGS):
     """BASELINE.json configs[0] (or a configs[1]-shaped run) through the real main.main(), recording what crosses its
     process pool."""
@@ -209,3 +219,7 @@ if __name__ == "__main__":
     if not only or "cfg2" in only:
         with open("/tmp/main_cfg2.log", "w") as f:
             f.write(trajectory_golden(10, "trajectory_cfg2", CFG2_ARGS))
+    for key, iters, cfg_args in (("cfg3s", 8, CFG3S_ARGS), ("cfg4s", 6, CFG4S_ARGS), ("cfg5s", 6, CFG5S_ARGS)):
+        if not only or key in only:
+            with open(f"/tmp/main_{key}.log", "w") as f:
+                f.write(trajectory_golden(iters, f"trajectory_{key}", cfg_args))

@@ -40,7 +40,9 @@ def test_library_is_sm100a_dmma_code(d):
     sass = subprocess.run(["cuobjdump", "-sass", d._lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
     assert "DMMA.8x8x4" in sass            # fp64 tensor path in the factorisation
-    assert "LDGSTS" in sass                # async global->shared staging
+    assert "LDGSTS" in sass                # async global->shared staging (GEMM operand ring)
+    assert "UBLKCP" in sass                # bulk-copy (TMA engine) staging of the gradient's / fidelity kernel's feature tiles
+    assert "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass      # ... completed on mbarriers
 
 
 @pytest.mark.parametrize("enc,q,dd,layers", [("chebyshev", 3, 2, 1), ("chebyshev", 4, 2, 3), ("chebyshev", 2, 1, 2),

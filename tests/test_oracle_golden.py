@@ -75,11 +75,13 @@ def test_first_iteration_of_reference_main_trajectory():
     assert np.array_equal(z2, np.array(rec["iterations"][1]["z"]))
 
 
-@pytest.mark.parametrize("name,q,layers,late", [("trajectory_cfg1", 3, 1, 29), ("trajectory_cfg2", 4, 3, 9)])
-def test_whole_reference_main_trajectory_consensus_chain(name, q, layers, late):
-    """Every z of the recorded main.main() runs (30 iterations of configs[0]; 10 of the configs[1]-shaped run) follows bit for
-    bit from the previous iteration's recorded theta / psi (main.py:2523), and the oracle's agent step reproduces a LATE
-    iteration's outputs of the smallest shard exactly (the state has left the initial random grid points by then)."""
+@pytest.mark.parametrize("name,late", [("trajectory_cfg1", 29), ("trajectory_cfg2", 9), ("trajectory_cfg3s", 7), ("trajectory_cfg4s", 5),
+                                       ("trajectory_cfg5s", 5)])
+def test_whole_reference_main_trajectory_consensus_chain(name, late):
+    """Every z of the recorded main.main() runs (30 iterations of configs[0]; 10 of the configs[1]-shaped run; 8 / 6 / 6 of the
+    reduced configs[2], [3], [4]) follows bit for bit from the previous iteration's recorded theta / psi (main.py:2523), and the
+    oracle's agent step reproduces a LATE iteration's outputs of the last shard exactly (the state has left the initial random
+    grid points by then)."""
     with open(os.path.join(GOLDEN, f"{name}.json")) as f:
         rec = json.load(f)
     its = rec["iterations"]
@@ -89,8 +91,11 @@ def test_whole_reference_main_trajectory_consensus_chain(name, q, layers, late):
         assert np.array_equal(z, np.array(its[k]["z"])), k
         assert its[k]["psi_in"] == its[k - 1]["psi_out"]
     data = load_golden(f"{name}_data.npz")
-    it, a = its[late], 3
-    cfg = agent_step.KernelConfig("chebyshev", "projected", q, layers, "matern")
+    it, a = its[late], rec["n_agents"] - 1
+    argv = rec["argv"].split()
+    get = lambda flag, default=None: argv[argv.index(flag) + 1] if flag in argv else default
+    cfg = agent_step.KernelConfig(get("--encoding"), get("--kernel-type"), int(get("--num-qubits")), int(get("--num-layers")),
+                                  get("--outer-kernel", "gaussian"))
     r = agent_step.train_and_update(cfg, data[f"X_{a}"], data[f"Y_{a}"], np.array(it["z"]), np.array(it["psi_in"][a]), 0.1,
                                     100.0, 100.0, workers=None, want_cond=False)
     assert np.array_equal(r.theta, np.array(it["theta_out"][a])) and np.array_equal(r.psi, np.array(it["psi_out"][a]))
