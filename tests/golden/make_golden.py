@@ -137,7 +137,46 @@ CFG5S_ARGS = ("--input-dim 6 --n-dataset 1000 --encoding kyriienko --kernel-type
               "--outer-kernel matern --rho 100 --L 100 --n-agents 4 --data-range -0.95 0.95")
 
 
-def trajectory_golden(max_iter=30, name="trajectory_cfg1", args=CFG1_ARGS):
+# configs[1] itself: the SRTM branch of main.py on a SYNTHETIC 1201 x 1201 tile (make_data_golden.synthetic_tile; the real tile
+# is not in the reference tree).  main.py:2137 seeds the subsampling and the train/test split from the wall clock; the
+# clock main.py sees is frozen for the run so that the seed is reproducible, and the seed is recorded.
+CFG2_SRTM_ARGS = ("--real-world-dataset srtm --srtm-region maharashtra --dataset-max-samples 1000 --dataset-normalize "
+                  "--input-dim 2 --encoding chebyshev --kernel-type projected --num-layers 3 --num-qubits 4 --outer-kernel matern "
+                  "--rho 100 --L 100 --n-agents 4")
+FROZEN_CLOCK = 1_760_000_123.456
+
+
+class FrozenClock:
+    """Stands in for the ``time`` module inside main.py only."""
+
+    def __getattr__(self, name):
+        import time
+        return getattr(time, name)
+
+    @staticmethod
+    def time():
+        return FROZEN_CLOCK
+
+
+@contextlib.contextmanager
+def srtm_sandbox():
+    import tempfile
+    import real_world_datasets as RW
+    import make_data_golden
+    cwd, real_time, real_plot = os.getcwd(), M.time, RW.plot_real_world_dataset
+    with tempfile.TemporaryDirectory() as tmp:
+        make_data_golden.write_tiles(tmp)
+        os.chdir(tmp)
+        M.time = FrozenClock()
+        RW.plot_real_world_dataset = lambda *a, **k: None
+        try:
+            yield
+        finally:
+            os.chdir(cwd)
+            M.time, RW.plot_real_world_dataset = real_time, real_plot
+
+
+def trajectory_golden(max_iter=30, name="trajectory_cfg1", args=CFG1_ARGS, sandbox=contextlib.nullcontext):
     """BASELINE.json configs[0] (or a configs[1]-shaped run) through the real main.main(), recording what crosses its
     process pool."""
     record = {"iterations": []}
@@ -182,7 +221,7 @@ def trajectory_golden(max_iter=30, name="trajectory_cfg1", args=CFG1_ARGS):
     sys.argv = argv
     log = io.StringIO()
     try:
-        with contextlib.redirect_stdout(log):
+        with contextlib.redirect_stdout(log), sandbox():
             M.main()
     except Exception as e:  # post-training reporting may trip over the matplotlib stub; ADMM is recorded by then
         print("main() stopped after the ADMM loop with:", repr(e)[:200])
@@ -199,6 +238,8 @@ def trajectory_golden(max_iter=30, name="trajectory_cfg1", args=CFG1_ARGS):
     np.savez_compressed(os.path.join(HERE, f"{name}_data.npz"), **arrays)
     record["argv"] = " ".join(argv)
     record["n_agents"] = len(shards)
+    if sandbox is srtm_sandbox:
+        record["srtm_data_seed"] = int(FROZEN_CLOCK * 1000) % 2 ** 32
     with open(os.path.join(HERE, f"{name}.json"), "w") as f:
         json.dump(record, f, indent=1)
     print("trajectory golden:", len(record["iterations"]), "iterations; shard sizes", [s[0].shape[0] for s in shards])
@@ -219,6 +260,10 @@ if __name__ == "__main__":
     if not only or "cfg2" in only:
         with open("/tmp/main_cfg2.log", "w") as f:
             f.write(trajectory_golden(10, "trajectory_cfg2", CFG2_ARGS))
+    if not only or "cfg2srtm" in only:
+        sys.path.insert(0, HERE)
+        with open("/tmp/main_cfg2srtm.log", "w") as f:
+            f.write(trajectory_golden(8, "trajectory_cfg2_srtm", CFG2_SRTM_ARGS, srtm_sandbox))
     for key, iters, cfg_args in (("cfg3s", 8, CFG3S_ARGS), ("cfg4s", 6, CFG4S_ARGS), ("cfg5s", 6, CFG5S_ARGS)):
         if not only or key in only:
             with open(f"/tmp/main_{key}.log", "w") as f:

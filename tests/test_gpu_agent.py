@@ -119,7 +119,7 @@ def test_wrong_parameter_count_raises(d):
         d.create_quantum_kernel(3, 2, 1, True, "yz_cx", "no_such_kernel")
 
 
-TRAJECTORIES = ["trajectory_cfg1", "trajectory_cfg2", "trajectory_cfg3s", "trajectory_cfg4s", "trajectory_cfg5s"]
+TRAJECTORIES = ["trajectory_cfg1", "trajectory_cfg2", "trajectory_cfg2_srtm", "trajectory_cfg3s", "trajectory_cfg4s", "trajectory_cfg5s"]
 
 
 def _trajectory_config(rec):
@@ -133,7 +133,8 @@ def _trajectory_config(rec):
 @pytest.mark.parametrize("name", TRAJECTORIES)
 def test_trajectory_matches_reference_main(d, name):
     """BASELINE.json configs[0] (30 iterations), a configs[1]-shaped run (chebyshev q=4, 3 layers, P = 32, 10 iterations; the SRTM
-    tile is absent, so main.py's synthetic branch) and reduced-size runs of configs[2], [3], [4] (hubregtsen fidelity q=5, 8 agents;
+    tile is absent, so main.py's synthetic branch), configs[1] itself on main.py's SRTM branch over a synthetic tile (8 iterations;
+    tests/test_data_plumbing.py rebuilds its shards from the tile) and reduced-size runs of configs[2], [3], [4] (hubregtsen fidelity q=5, 8 agents;
     yz_cx projected-Gaussian q=6, 8 agents; kyriienko projected-Matern q=4, 4 agents): replay the ADMM trajectory the real
     main.main() produced (regional partitions of unequal size, matern flag -> Gaussian training Grams (Q1), rho = L = 100) through
     AdmmEngine on the device - every iteration's z, theta on the same 1e-4 grid point, psi, per-agent NLL to 1e-8."""

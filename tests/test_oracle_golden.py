@@ -75,7 +75,7 @@ def test_first_iteration_of_reference_main_trajectory():
     assert np.array_equal(z2, np.array(rec["iterations"][1]["z"]))
 
 
-@pytest.mark.parametrize("name,late", [("trajectory_cfg1", 29), ("trajectory_cfg2", 9), ("trajectory_cfg3s", 7), ("trajectory_cfg4s", 5),
+@pytest.mark.parametrize("name,late", [("trajectory_cfg1", 29), ("trajectory_cfg2", 9), ("trajectory_cfg2_srtm", 7), ("trajectory_cfg3s", 7), ("trajectory_cfg4s", 5),
                                        ("trajectory_cfg5s", 5)])
 def test_whole_reference_main_trajectory_consensus_chain(name, late):
     """Every z of the recorded main.main() runs (30 iterations of configs[0]; 10 of the configs[1]-shaped run; 8 / 6 / 6 of the
