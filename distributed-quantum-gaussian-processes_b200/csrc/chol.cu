@@ -646,7 +646,10 @@ static int solver_create_impl(int n, int outer_blocks, int lean, dqgp_solver** o
     DQGP_REQUIRE(n >= 1 && n <= (1 << 17), "dqgp_solver_create: n = %d outside [1, 131072]", n);
     dqgp_solver* s = new dqgp_solver();
     s->n = n;
-    s->ob = outer_blocks > 0 ? (outer_blocks > 16 ? 16 : outer_blocks) : 4;      // widest panel
+    // widest panel.  Default (0): rank-128 panels up to n = 6144, where a factorisation is bound by its leaf chain and every extra
+    // panel-boundary dependency costs (potrf at n = 2048: 0.88 / 0.94 / 1.02 ms with 1 / 2 / 4 blocks; 4096: 2.1 / 2.3 / 2.5;
+    // 6144: 4.28 / 4.33 / 4.69), rank-512 above (throughput of several concurrent factorisations; 8192: 8.4 / 8.1 / 8.3 alone)
+    s->ob = outer_blocks > 0 ? (outer_blocks > 16 ? 16 : outer_blocks) : (outer_blocks == 0 && !lean && n <= 6144 ? 1 : 4);
     s->nblk = (n + NB - 1) / NB;
     {
         // outer_blocks < 0: rank-512 panels while more than 28 block columns remain (there the rank-k trailing updates bound

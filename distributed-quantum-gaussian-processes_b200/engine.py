@@ -332,8 +332,10 @@ class AdmmEngine:
         self.rho = float(rho)
         lips = L if np.ndim(L) else [L] * self.A_total
         # one agent per GPU: latency matters -> rank-256 outer panels (measured best of 1, 2, 4, 6, 8 and of the 4-then-2
-        # schedule, outer_blocks = -1, which ties with 2); several agents: throughput -> rank-512
-        agent_kw.setdefault("cholesky_outer_blocks", 2 if self.A_local == 1 else 4)
+        # schedule, outer_blocks = -1, which ties with 2); several agents: throughput -> rank-512.  Shards up to 6144 samples are
+        # bound by the leaf chain either way: the solver's size-aware default (rank-128 panels) is best for them.
+        n_max = max(len(y) for _, y in shards)
+        agent_kw.setdefault("cholesky_outer_blocks", 0 if n_max <= 6144 else (2 if self.A_local == 1 else 4))
         self.agents = [AgentEngine(x, y, rho=rho, L=lips[self.first + i], **agent_kw) for i, (x, y) in enumerate(shards)]
         if any(a.P != self.P for a in self.agents):
             raise ValueError("theta0 does not match the circuit's parameter count")

@@ -105,8 +105,8 @@ int dqgp_gram_fidelity(const double* d_Psi1, int n1, const double* d_Psi2, int n
  *      golden files), so its value is rounding noise of that particular SVD; an estimate from this factorisation of C + sigma^2 I
  *      would be a different noise.  The Python layer returns NaN and offers a library SVD as a diagnostic opt-in. */
 int dqgp_solver_create(int n, dqgp_solver** out);
-/* outer_blocks: width of the outer Cholesky panel in 128-column blocks. 4 (default, = 0) gives rank-512 trailing
- * updates (best throughput when several agents share a GPU); < 0 = width 4 while more than 28 block columns remain and 2
+/* outer_blocks: width of the outer Cholesky panel in 128-column blocks.  0 = default: 1 up to n = 6144 (bound by the leaf chain),
+ * 4 above (rank-512 trailing updates: best throughput when several agents share a GPU); < 0 = width 4 while more than 28 block columns remain and 2
  * afterwards (one agent per GPU: wide while the trailing updates bound the factorisation, narrow once the leaf chain does). */
 int dqgp_solver_create_ex(int n, int outer_blocks, dqgp_solver** out);
 /* Lean solver for prediction / CV at full-train scale (main.py:1364-1596): ONE padded square (A, factored
