@@ -80,7 +80,13 @@ constexpr size_t LEAF_SMEM_V2 = sizeof(double) * (NB * LP + 2 * NB + 8 * NB);
 // Four interleaved accumulators per tile keep the dependent DMMA chain j0/16 long; the B fragment is shared by the tiles.
 template <int NT>
 __device__ __forceinline__ void leaf_panel_update(const double* __restrict__ M, double* __restrict__ s_pan, int j0, int r0, int r1, int g,
-                                                  int t, const double2 (&av)[2]) {
+                                                  int t, const double2 (&av)[2], long long* tq = nullptr) {
+#ifdef DQGP_LEAF_TIMING
+    long long q0 = clock64();
+#define LEAF_Q(slot) do { const long long n__ = clock64(); tq[slot] += n__ - q0; q0 = n__; } while (0)
+#else
+#define LEAF_Q(slot) do { } while (0)
+#endif
     double acc[NT][4][2];
 #pragma unroll
     for (int x = 0; x < NT; ++x)
@@ -97,6 +103,7 @@ __device__ __forceinline__ void leaf_panel_update(const double* __restrict__ M, 
             for (int x = 0; x < NT; ++x) dmma884(acc[x][u][0], acc[x][u][1], ma[x][(k0 + 4 * u) * LP], b);
         }
     }
+    LEAF_Q(0);
     if (j0 & 8) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -105,12 +112,21 @@ __device__ __forceinline__ void leaf_panel_update(const double* __restrict__ M, 
             for (int x = 0; x < NT; ++x) dmma884(acc[x][u][0], acc[x][u][1], ma[x][(full + 4 * u) * LP], b);
         }
     }
+#ifdef DQGP_LEAF_TIMING
+    if (acc[0][0][0] + acc[0][1][0] + acc[0][2][0] + acc[0][3][0] == 1.2345e300) tq[3] += 1;      // wait for the DMMAs here
+#endif
+    LEAF_Q(1);
+#ifdef DQGP_LEAF_TIMING
+    if (av[0].x == 1.2345e300) tq[3] += 1;                                                       // wait for the prefetched A here
+#endif
+    LEAF_Q(2);
 #pragma unroll
     for (int x = 0; x < NT; ++x) {
         const int r = (x == 0 ? r0 : r1) + g;
         s_pan[(2 * t) * NB + r] = av[x].x - ((acc[x][0][0] + acc[x][1][0]) + (acc[x][2][0] + acc[x][3][0]));
         s_pan[(2 * t + 1) * NB + r] = av[x].y - ((acc[x][0][1] + acc[x][1][1]) + (acc[x][2][1] + acc[x][3][1]));
     }
+    LEAF_Q(4);
 }
 
 // One level of the triangular inverse inside the leaf: every pair of inverted BxB diagonal blocks (W11, W22) of the
@@ -206,7 +222,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
         av[x] = *reinterpret_cast<const double2*>(Ablk + (size_t)(8 * ti + g) * ld + 2 * t);
     }
 #ifdef DQGP_LEAF_TIMING
-    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ta[16], tw = 0, t_prev = clock64(), t_begin = t_prev;
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ta[16], tw = 0, t_prev = clock64(), t_begin = t_prev, tq[5] = {0, 0, 0, 0, 0}, tr[2] = {0, 0};
 #define LEAF_TICK(slot) do { const long long now__ = clock64(); tk[slot] += now__ - t_prev; t_prev = now__; } while (0)
 #else
 #define LEAF_TICK(slot) do { } while (0)
@@ -219,8 +235,16 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
             const bool has0 = ti0 < NB / 8, has1 = ti1 < NB / 8;     // warp-uniform
             // no predicated mma.sync inside the loops: a predicate makes the compiler fence every DMMA with WARPSYNC
             // (measured: 180 cycles per DMMA instead of 16), so the one- and two-tile cases are separate instantiations
+#ifdef DQGP_LEAF_TIMING
+            const long long c_pre = clock64();
+            if (has1) leaf_panel_update<2>(M, s_pan, j0, 8 * ti0, 8 * ti1, g, t, av, tq);
+            else if (has0) leaf_panel_update<1>(M, s_pan, j0, 8 * ti0, 8 * ti0, g, t, av, tq);
+            const long long c_post = clock64();
+            tr[0] += c_pre - t_prev; tr[1] += c_post - c_pre;
+#else
             if (has1) leaf_panel_update<2>(M, s_pan, j0, 8 * ti0, 8 * ti1, g, t, av);
             else if (has0) leaf_panel_update<1>(M, s_pan, j0, 8 * ti0, 8 * ti0, g, t, av);
+#endif
             if (j0 + 8 < NB) {                                      // prefetch this warp's tiles of the next panel
                 if (ti0 + 1 < NB / 8) av[0] = *reinterpret_cast<const double2*>(Ablk + (size_t)(8 * (ti0 + 1) + g) * ld + j0 + 8 + 2 * t);
                 if (ti1 + 1 < NB / 8) av[1] = *reinterpret_cast<const double2*>(Ablk + (size_t)(8 * (ti1 + 1) + g) * ld + j0 + 8 + 2 * t);
@@ -246,18 +270,26 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
             if (l[7][7] == 1.2345e300) tk[7] += 1;     // force the loads to complete here
             LEAF_TICK(2);
 #endif
+            // The thread's own row rides along as a ninth row of the block (column-oriented substitution: as soon as x_c is known it
+            // is removed from all later columns): its independent instructions fill the latency of the rsqrt chain.  The rows of
+            // the diagonal block take the same path (no divergence in their warp): the recurrence reproduces their row of L
+            // operation by operation, and what it leaves right of the diagonal is never stored.
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const double piv = l[c][c];
                 if (!(piv > 0.0) && i == j0 && s_bad == 0) s_bad = j0 + c + 1;
                 rd[c] = rsqrt(piv);
                 l[c][c] = piv * rd[c];
+                const double x = a[c] * rd[c];
+                a[c] = x;
 #pragma unroll
                 for (int r = c + 1; r < 8; ++r) l[r][c] *= rd[c];
 #pragma unroll
-                for (int c2 = c + 1; c2 < 8; ++c2)
+                for (int c2 = c + 1; c2 < 8; ++c2) {
 #pragma unroll
                     for (int r = c2; r < 8; ++r) l[r][c2] = fma(-l[r][c], l[c2][c], l[r][c2]);
+                    a[c2] = fma(-x, l[c2][c], a[c2]);
+                }
             }
 #ifdef DQGP_LEAF_TIMING
             if (l[7][7] == 1.2345e300) tk[7] += 1;
@@ -265,23 +297,12 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
 #endif
             if (i < j0 + 8) {
                 const int r0 = i - j0;
+                double dv = a[0], rv = rd[0];
 #pragma unroll
-                for (int r = 0; r < 8; ++r)
-                    if (r == r0) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) a[c] = (c <= r) ? l[r][c] : 0.0;
-                        s_diag[i] = l[r][r];
-                        s_rdiag[i] = rd[r];
-                    }
-            } else {
-                // column-oriented substitution: as soon as x_k is known it is removed from all later columns
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const double x = a[c] * rd[c];
-                    a[c] = x;
-#pragma unroll
-                    for (int c2 = c + 1; c2 < 8; ++c2) a[c2] = fma(-x, l[c2][c], a[c2]);
-                }
+                for (int r = 1; r < 8; ++r)
+                    if (r == r0) { dv = a[r]; rv = rd[r]; }
+                s_diag[i] = dv;
+                s_rdiag[i] = rv;
             }
 #ifdef DQGP_LEAF_TIMING
             if (a[7] == 1.2345e300) tk[7] += 1;
@@ -360,6 +381,10 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
     if (tid == NB - 1 && blk == 1)
         printf("panel update cycles per panel: %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", ta[0], ta[1], ta[2],
                ta[3], ta[4], ta[5], ta[6], ta[7], ta[8], ta[9], ta[10], ta[11], ta[12], ta[13], ta[14], ta[15]);
+    if (tid == NB - 1 && blk == 1)
+        printf("panel update split (thread 127, all panels): zero + full rounds %lld | half round + DMMA drain %lld | wait for prefetched A %lld | s_pan stores %lld\n",
+               tq[0], tq[1], tq[2], tq[4]);
+    if (tid == NB - 1 && blk == 1) printf("   before the call %lld | inside the call %lld | (rest of 'dmma update': the prefetch loads of the next panel)\n", tr[0], tr[1]);
     if (tid == NB - 1 && blk == 1)
         printf("leaf cycles (thread 127): dmma update %lld | sync wait %lld | loads %lld | 8x8 factor %lld | substitution %lld | stores %lld | "
                "end sync %lld | (a: dmma loops %lld, wait for prefetched A %lld) || phase1 %lld  logdet+phase2 %lld  W store %lld\n", tk[0], tk[1], tk[2], tk[3], tk[4], tk[5], tk[6], tk[7], tw,

@@ -51,6 +51,46 @@ __global__ void rsqrt_chain(double* out, long long* cycles, int iters) {
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// Cold-start cost of the DMMA unit: a burst of 8 independent DMMAs after the warp spent `gap` cycles without issuing one
+// (GAP_KIND 0: spinning on clock64; 1: a dependent DFMA chain, i.e. the FP64 pipe stays busy; 2: a dependent FFMA chain).
+template <int GAP_KIND>
+__global__ void dmma_after_gap(double* out, long long* cycles, int gap, int reps) {
+    double c[8][2];
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    double f = a; float ff = (float)a;
+    long long burst = 0;
+    for (int r = 0; r < reps; ++r) {
+        const long long g0 = clock64();
+        if (GAP_KIND == 0) { while (clock64() - g0 < gap) { } }
+        else if (GAP_KIND == 1) { while (clock64() - g0 < gap) { f = fma(f, b, a); } }
+        else { while (clock64() - g0 < gap) { ff = fmaf(ff, 0.999f, 1.0f); } }
+        __syncwarp();
+        const long long t0 = clock64();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma(c[i][0], c[i][1], a, b);
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += c[i][0];
+        if (s == 1.2345e300) f += 1.0;         // consume: the clock read below waits for the last DMMA
+        const long long t1 = clock64();
+        if (r > 0) burst += t1 - t0;
+    }
+    out[threadIdx.x] = c[0][0] + c[7][1] + f + ff;
+    if (threadIdx.x == 0) cycles[0] = burst / (reps - 1);
+}
+
+template <int GAP_KIND>
+static void run_gap(const char* what) {
+    double* out; long long* cyc; cudaMalloc(&out, 8 * 1024); cudaMalloc(&cyc, 32);
+    for (int gap : {0, 100, 300, 1000, 2000, 5000, 20000}) {
+        dmma_after_gap<GAP_KIND><<<1, 32>>>(out, cyc, gap, 50);
+        long long h = 0; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+        printf("burst of 8 DMMA after a %5d-cycle gap (%s): %lld cycles\n", gap, what, h);
+    }
+    cudaFree(out); cudaFree(cyc);
+}
+
 template <typename K>
 static void run(const char* name, K kern, int chains, int threads) {
     double* out; long long* cyc;
@@ -79,5 +119,8 @@ int main() {
         long long h = 0; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
         printf("rsqrt(double)+add dependent chain: %.1f cycles per step\n", double(h) / 2000);
     }
+    run_gap<0>("idle warp");
+    run_gap<1>("DFMA chain in the gap");
+    run_gap<2>("FFMA chain in the gap");
     return 0;
 }
