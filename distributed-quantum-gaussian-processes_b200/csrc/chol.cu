@@ -323,18 +323,11 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
 #ifdef DQGP_LEAF_TIMING
     const long long t_phase1 = clock64();
 #endif
-    {
-        double v = (tid < NB) ? log(s_diag[tid]) : 0.0;
-        v = warp_sum(v);
+    // logdet: the helper warps (idle in level 0 of phase 2) take the logarithms; the read-modify-write of the global accumulator
+    // (a round trip to L2) waits until the end of the kernel, off the path of the barriers below
+    if (helper) {
+        double v = warp_sum(log(s_diag[tid - NB]));
         if (lane == 0) s_red[warp] = v;
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-#pragma unroll
-            for (int w = 0; w < LEAF_THREADS / 32; ++w) tot += s_red[w];
-            *logdet += 2.0 * tot;
-            if (s_bad && *info == 0 && blk * NB + s_bad <= n_real) *info = blk * NB + s_bad;
-        }
     }
 
     // ---------------- phase 2: W = L^-1 by recursive doubling on the DMMA pipe ----------------
@@ -369,6 +362,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
     const long long t_phase2 = clock64();
 #endif
     // lower triangle only: the strict upper triangle of W's diagonal blocks is zeroed once, at solver creation
+#pragma unroll 4
     for (int e = tid; e < NB * NB / 2; e += LEAF_THREADS) {
         const int r = e >> 6, c = (e & 63) * 2;
         if (c > r) continue;
@@ -376,6 +370,13 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) potrf_leaf_kernel(double* __r
         v.x = (c < r) ? M[r * LP + c] : s_rdiag[r];
         v.y = (c + 1 < r) ? M[r * LP + c + 1] : (c + 1 == r ? s_rdiag[r] : 0.0);
         *reinterpret_cast<double2*>(Wblk + (size_t)r * ldw + c) = v;
+    }
+    if (tid == LEAF_THREADS - 1) {      // s_red[4..7] were written before the barriers of phase 2
+        double tot = 0.0;
+#pragma unroll
+        for (int w = NB / 32; w < LEAF_THREADS / 32; ++w) tot += s_red[w];
+        *logdet += 2.0 * tot;
+        if (s_bad && *info == 0 && blk * NB + s_bad <= n_real) *info = blk * NB + s_bad;
     }
 #ifdef DQGP_LEAF_TIMING
     if (tid == NB - 1 && blk == 1)
