@@ -8,6 +8,8 @@
 // fixed order, so the result is bit-reproducible run to run (the reference rounds it to 4 decimals).
 // Bound: FP64 pipe (3m + outer-kernel flops per entry); HBM traffic is one read of A^-1.
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>
 #include "pairwise.cuh"
 
 namespace dqgp {
@@ -143,19 +145,37 @@ __device__ __forceinline__ void g2_stage_bulk(double* buf, const double* __restr
     else if (threadIdx.x < 2 * PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(col0 + threadIdx.x - PW_TILE, n - 1)]);
 }
 
+// Same tile as TWO boxes of a 3-D tensor map over F = [set][sample][feature] (TMA proper, SASS UTMALDG), issued by one thread: box =
+// 64 samples x PITCH features, so the features beyond m - outside the tensor - arrive as the zero padding of the fragment layout, and
+// samples beyond n as zero rows (their bracket weights are zero).  Replaces 128 per-row copies per parameter set.
+template <int PITCH>
+__device__ __forceinline__ void g2_stage_tmap(double* buf, const void* tmap, int set, const double* __restrict__ Ns, int row0, int col0, int n,
+                                              unsigned long long* bar) {
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, 2u * PW_TILE * PITCH * sizeof(double));
+        tensor_copy_3d_g2s(buf, tmap, 0, row0, set, bar);
+        tensor_copy_3d_g2s(buf + PW_TILE * PITCH, tmap, 0, col0, set, bar);
+    }
+    double* nr = buf + 2 * PW_TILE * PITCH;
+    if (threadIdx.x < PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(row0 + threadIdx.x, n - 1)]);
+    else if (threadIdx.x < 2 * PW_TILE) cp_async8(&nr[threadIdx.x], &Ns[min(col0 + threadIdx.x - PW_TILE, n - 1)]);
+}
+
 // CLAMP: guard the exponent against arguments below -700 (only reachable when gamma * 4m > 700; features lie in [-1, 1])
 // BULK: stage the feature tiles with cp.async.bulk + mbarrier instead of per-thread cp.async (needs VEC == 2)
 // PITCH: doubles per staged sample row, = 4 (mod 8) so the DMMA fragment loads are bank-conflict-free, >= m.  With PITCH = 28 (m <= 28:
 // up to 9 qubits) a stage is 29.7 KB and THREE stages fit beside a second CTA, so a tile's copy is issued two sets ahead.
-template <int OUTER, int VEC, bool CLAMP = true, bool BULK = false, int PITCH = G2_PITCH>
+// TMAP: the feature tiles of a parameter set arrive as two boxes of the tensor map `tmap` (needs BULK's mbarriers)
+template <int OUTER, int VEC, bool CLAMP = true, bool BULK = false, int PITCH = G2_PITCH, bool TMAP = false>
 __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(const double* __restrict__ Ainv, int ld,
                                                                            const double* __restrict__ alpha,
                                                                            const double* __restrict__ F,
                                                                            const double* __restrict__ Nrm, int n, int m, int P,
-                                                                           OuterHyp hyp, double* __restrict__ partial) {
+                                                                           OuterHyp hyp, double* __restrict__ partial,
+                                                                           const __grid_constant__ CUtensorMap tmap) {
     constexpr int STAGES = (BULK && PITCH <= 28) ? 3 : 2;
     constexpr int G2_STAGE_DOUBLES = 2 * PW_TILE * PITCH + 2 * PW_TILE;
-    extern __shared__ __align__(16) double g2_smem[];
+    extern __shared__ __align__(128) double g2_smem[];
     __shared__ double s_red[2][PW_THREADS / 32];
     __shared__ __align__(8) unsigned long long s_bar[3];
     int bi, bj;
@@ -172,8 +192,8 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
     const double a_scale = 2.0 * gam;
     const double tab = exp_table_entry();
 
-    // zero the k-padding columns of both stages once (cp.async never writes them)
-    for (int e = threadIdx.x; e < STAGES * 2 * PW_TILE * (PITCH - m); e += PW_THREADS) {
+    // zero the k-padding columns of both stages once (cp.async never writes them; the tensor map's boxes bring their own zeros)
+    for (int e = threadIdx.x; !TMAP && e < STAGES * 2 * PW_TILE * (PITCH - m); e += PW_THREADS) {
         const int per = PITCH - m;
         const int row = e / per, k = m + (e - row * per);          // row in [0, 4*64): stage x operand x sample
         const int stage = row / (2 * PW_TILE), rr = row - stage * 2 * PW_TILE;
@@ -198,7 +218,8 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
 
     const size_t set_stride = (size_t)n * m;
     const int T = 2 * P;
-    if (BULK) g2_stage_bulk<PITCH>(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m, &s_bar[0]);
+    if (TMAP) g2_stage_tmap<PITCH>(g2_smem, &tmap, 1, Nrm + n, row0, col0, n, &s_bar[0]);
+    else if (BULK) g2_stage_bulk<PITCH>(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m, &s_bar[0]);
     else g2_stage<VEC, PITCH>(g2_smem, F + set_stride, Nrm + n, row0, col0, n, m);
     cp_async_commit();
     if (STAGES == 3) {
@@ -222,7 +243,8 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
             const int nx = tt + STAGES - 1;          // the set whose copy is issued now; its stage was last read at iteration tt - 1
             if (nx < T) {
                 const int ns = nx % STAGES;
-                if (BULK) g2_stage_bulk<PITCH>(g2_smem + ns * G2_STAGE_DOUBLES, F + (size_t)(nx + 1) * set_stride, Nrm + (size_t)(nx + 1) * n, row0, col0, n, m, &s_bar[ns]);
+                if (TMAP) g2_stage_tmap<PITCH>(g2_smem + ns * G2_STAGE_DOUBLES, &tmap, nx + 1, Nrm + (size_t)(nx + 1) * n, row0, col0, n, &s_bar[ns]);
+                else if (BULK) g2_stage_bulk<PITCH>(g2_smem + ns * G2_STAGE_DOUBLES, F + (size_t)(nx + 1) * set_stride, Nrm + (size_t)(nx + 1) * n, row0, col0, n, m, &s_bar[ns]);
                 else g2_stage<VEC, PITCH>(g2_smem + ns * G2_STAGE_DOUBLES, F + (size_t)(nx + 1) * set_stride, Nrm + (size_t)(nx + 1) * n, row0, col0, n, m);
             }
         }
@@ -280,6 +302,30 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
         for (int w = 0; w < PW_THREADS / 32; ++w) s += s_red[i & 1][w];
         partial[(size_t)blockIdx.x * P + i] = s;
     }
+}
+
+// F = [sets][n][m] doubles as a 3-D tensor map with a (1, 64, G2_PITCH) box.  false when the driver entry point is missing or refuses.
+static bool make_feature_tensor_map(CUtensorMap* out, const double* d_F, int n, int m, int sets) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+        else
+            cudaGetLastError();
+    }
+    if (!encode) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)m, (cuuint64_t)n, (cuuint64_t)sets};
+    const cuuint64_t strides[2] = {(cuuint64_t)m * sizeof(double), (cuuint64_t)n * m * sizeof(double)};      // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)G2_PITCH, (cuuint32_t)PW_TILE, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(d_F), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // squared norms of every feature row: Nrm[s*n + j] = sum_k F[s][j][k]^2 (one warp per 4 rows)
@@ -551,6 +597,12 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
         // pitch 28 + three stages (copy issued two sets ahead) measured 1% SLOWER than pitch 36 + two stages at config 4 (8.74 against
         // 8.63 ms): the copy is already hidden one set ahead; kept as an opt-in for A/B runs
         const bool use_p28 = getenv("DQGP_GRAD_P28") != nullptr;
+        // ... and as two boxes of a 3-D tensor map per parameter set (one thread issues them) unless DQGP_GRAD_NO_TMAP is set or the
+        // driver refuses the map (then the per-row bulk copies above)
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
+        const bool have_tmap = use_bulk && !use_p28 && getenv("DQGP_GRAD_NO_TMAP") == nullptr && (m & 1) == 0 && m <= G2_PITCH &&
+                               (reinterpret_cast<uintptr_t>(d_F) & 15) == 0 && make_feature_tensor_map(&tmap, d_F, n, m, 2 * P + 1);
 #define DQGP_G2(OUT)                                                                                                         \
     do {                                                                                                                     \
         static bool attr_done_dev[64] = {false};        /* the attribute is per DEVICE (as gemm_init's flags) */            \
@@ -564,17 +616,22 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, false, true, 28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM_P28)); \
+            DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, false, true, G2_PITCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
+            DQGP_CUDA(cudaFuncSetAttribute(grad_projected_dmma_kernel<OUT, 2, true, true, G2_PITCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM)); \
             attr_done = true;                                                                                                \
         }                                                                                                                    \
         if ((m & 1) == 0 && (reinterpret_cast<uintptr_t>(d_F) & 15) == 0) {                                                  \
-            if (use_bulk) {                                                                                                  \
-                if (no_clamp && m <= 28 && use_p28) grad_projected_dmma_kernel<OUT, 2, false, true, 28><<<tiles, PW_THREADS, G2_SMEM_P28, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
-                else if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
-                else grad_projected_dmma_kernel<OUT, 2, true, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
-            } else if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
-            else grad_projected_dmma_kernel<OUT, 2><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+            if (use_bulk && have_tmap) {                                                                                     \
+                if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false, true, G2_PITCH, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial, tmap); \
+                else grad_projected_dmma_kernel<OUT, 2, true, true, G2_PITCH, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial, tmap); \
+            } else if (use_bulk) {                                                                                           \
+                if (no_clamp && m <= 28 && use_p28) grad_projected_dmma_kernel<OUT, 2, false, true, 28><<<tiles, PW_THREADS, G2_SMEM_P28, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial, tmap); \
+                else if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial, tmap); \
+                else grad_projected_dmma_kernel<OUT, 2, true, true><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial, tmap); \
+            } else if (no_clamp) grad_projected_dmma_kernel<OUT, 2, false><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial, tmap); \
+            else grad_projected_dmma_kernel<OUT, 2><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial, tmap); \
         } else                                                                                                               \
-            grad_projected_dmma_kernel<OUT, 1><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial); \
+            grad_projected_dmma_kernel<OUT, 1><<<tiles, PW_THREADS, G2_SMEM, st>>>(d_Ainv, ld, d_alpha, d_F, norms, n, m, P, hyp, partial, tmap); \
     } while (0)
         switch (outer) {
             case DQGP_OUTER_GAUSSIAN: DQGP_G2(DQGP_OUTER_GAUSSIAN); break;
