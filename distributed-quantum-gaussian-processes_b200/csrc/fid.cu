@@ -8,7 +8,9 @@
 // alpha^T in registers, deterministic two-stage reduction.  Operand chunks of 32 doubles stream through a
 // double-buffered cp.async ring.  Replaces the SIMT kernels of gram.cu / grad.cu (kept behind DQGP_FID_SIMT).
 #include <cstdlib>
+#include <cstring>
 #include "pairwise.cuh"
+#include "tensormap.cuh"
 
 namespace dqgp {
 
@@ -41,14 +43,27 @@ __device__ __forceinline__ void fd_stage_bulk(double* buf, const double* __restr
     }
 }
 
-template <int MODE, bool BULK = true>
+// ... and as two boxes of a 3-D tensor map over Psi = [set][state][2 * 2^q doubles] (TMA proper, SASS UTMALDG), issued by one thread: box =
+// 64 states x FD_PITCH doubles starting at the chunk; the four doubles beyond the chunk land in the padding of the fragment layout (never
+// read), states beyond n arrive as zero rows (their bracket weights are zero).
+__device__ __forceinline__ void fd_stage_tmap(double* buf, const void* tmap, int set, int row0, int col0, int k0, unsigned long long* bar) {
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, 2u * PW_TILE * FD_PITCH * sizeof(double));
+        tensor_copy_3d_g2s(buf, tmap, k0, row0, set, bar);
+        tensor_copy_3d_g2s(buf + PW_TILE * FD_PITCH, tmap, k0, col0, set, bar);
+    }
+}
+
+// TMAP (MODE 1 only: one state array): stage through the tensor map `tmap`
+template <int MODE, bool BULK = true, bool TMAP = false>
 __global__ void __launch_bounds__(PW_THREADS, 1) fidelity_dmma_kernel(const double* __restrict__ Psi1, int n1,
                                                                       const double* __restrict__ Psi2, int n2, int d2, int n_sets,
                                                                       double* __restrict__ K, int ldk,
                                                                       const double* __restrict__ Ainv, int ld,
                                                                       const double* __restrict__ alpha, int P,
-                                                                      double* __restrict__ partial) {
-    extern __shared__ __align__(16) double fd_smem[];
+                                                                      double* __restrict__ partial,
+                                                                      const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) double fd_smem[];
     __shared__ double s_red[2][PW_THREADS / 32];
     __shared__ __align__(8) unsigned long long s_bar[2];
     if (BULK) {
@@ -91,7 +106,8 @@ __global__ void __launch_bounds__(PW_THREADS, 1) fidelity_dmma_kernel(const doub
     const size_t set_stride1 = (size_t)n1 * d2, set_stride2 = (size_t)n2 * d2;
     const int first_set = (MODE == 1) ? 1 : 0;
     const int total = n_sets * n_chunks;
-    if (BULK) fd_stage_bulk(fd_smem, Psi1 + first_set * set_stride1, Psi2 + first_set * set_stride2, row0, col0, n1, n2, d2, 0, kc, &s_bar[0]);
+    if (TMAP) fd_stage_tmap(fd_smem, &tmap, first_set, row0, col0, 0, &s_bar[0]);
+    else if (BULK) fd_stage_bulk(fd_smem, Psi1 + first_set * set_stride1, Psi2 + first_set * set_stride2, row0, col0, n1, n2, d2, 0, kc, &s_bar[0]);
     else fd_stage(fd_smem, Psi1 + first_set * set_stride1, Psi2 + first_set * set_stride2, row0, col0, n1, n2, d2, 0, kc);
     cp_async_commit();
     double re[2][4][2], im[2][4][2];
@@ -110,7 +126,9 @@ __global__ void __launch_bounds__(PW_THREADS, 1) fidelity_dmma_kernel(const doub
         }
         if (it + 1 < total) {
             const int ns = (it + 1) / n_chunks, nch = (it + 1) - ns * n_chunks;
-            if (BULK)
+            if (TMAP)
+                fd_stage_tmap(fd_smem + ((it + 1) & 1) * FD_STAGE, &tmap, first_set + ns, row0, col0, nch * kc, &s_bar[(it + 1) & 1]);
+            else if (BULK)
                 fd_stage_bulk(fd_smem + ((it + 1) & 1) * FD_STAGE, Psi1 + (size_t)(first_set + ns) * set_stride1,
                               Psi2 + (size_t)(first_set + ns) * set_stride2, row0, col0, n1, n2, d2, nch * kc, kc, &s_bar[(it + 1) & 1]);
             else
@@ -195,6 +213,7 @@ static int fd_attr() {
         DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
         DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
         DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
+        DQGP_CUDA(cudaFuncSetAttribute(fidelity_dmma_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FD_SMEM));
         done = true;
     }
     return 0;
@@ -205,8 +224,10 @@ int fidelity_gram_dmma(const double* Psi1, int n1, const double* Psi2, int n2, i
     if (rc) return rc;
     dim3 grid((n2 + PW_TILE - 1) / PW_TILE, (n1 + PW_TILE - 1) / PW_TILE);
     static const bool no_bulk = getenv("DQGP_FID_NO_BULK") != nullptr;      // A/B: per-thread cp.async staging
-    if (no_bulk) fidelity_dmma_kernel<0, false><<<grid, PW_THREADS, FD_SMEM, st>>>(Psi1, n1, Psi2, n2, 2 * dim, 1, K, ldk, nullptr, 0, nullptr, 0, nullptr);
-    else fidelity_dmma_kernel<0><<<grid, PW_THREADS, FD_SMEM, st>>>(Psi1, n1, Psi2, n2, 2 * dim, 1, K, ldk, nullptr, 0, nullptr, 0, nullptr);
+    CUtensorMap tmap;                                                       // unused by the Gram (two state arrays): per-row bulk copies
+    memset(&tmap, 0, sizeof(tmap));
+    if (no_bulk) fidelity_dmma_kernel<0, false><<<grid, PW_THREADS, FD_SMEM, st>>>(Psi1, n1, Psi2, n2, 2 * dim, 1, K, ldk, nullptr, 0, nullptr, 0, nullptr, tmap);
+    else fidelity_dmma_kernel<0><<<grid, PW_THREADS, FD_SMEM, st>>>(Psi1, n1, Psi2, n2, 2 * dim, 1, K, ldk, nullptr, 0, nullptr, 0, nullptr, tmap);
     DQGP_LAUNCH_CHECK("fidelity_dmma_kernel<0>");
     return 0;
 }
@@ -216,8 +237,14 @@ int fidelity_grad_dmma(const double* Ainv, int ld, const double* alpha, const do
     int rc = fd_attr();
     if (rc) return rc;
     static const bool no_bulk = getenv("DQGP_FID_NO_BULK") != nullptr;
-    if (no_bulk) fidelity_dmma_kernel<1, false><<<tiles, PW_THREADS, FD_SMEM, st>>>(Psi, n, Psi, n, 2 * dim, 2 * P, nullptr, 0, Ainv, ld, alpha, P, partial);
-    else fidelity_dmma_kernel<1><<<tiles, PW_THREADS, FD_SMEM, st>>>(Psi, n, Psi, n, 2 * dim, 2 * P, nullptr, 0, Ainv, ld, alpha, P, partial);
+    // the state tiles of a parameter set as two boxes of a 3-D tensor map (one issuing thread) unless DQGP_FID_NO_TMAP is set or the
+    // driver refuses the map
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const bool have_tmap = !no_bulk && getenv("DQGP_FID_NO_TMAP") == nullptr && make_rows_tensor_map(&tmap, Psi, 2 * dim, n, 2 * P + 1, FD_PITCH, PW_TILE);
+    if (no_bulk) fidelity_dmma_kernel<1, false><<<tiles, PW_THREADS, FD_SMEM, st>>>(Psi, n, Psi, n, 2 * dim, 2 * P, nullptr, 0, Ainv, ld, alpha, P, partial, tmap);
+    else if (have_tmap) fidelity_dmma_kernel<1, true, true><<<tiles, PW_THREADS, FD_SMEM, st>>>(Psi, n, Psi, n, 2 * dim, 2 * P, nullptr, 0, Ainv, ld, alpha, P, partial, tmap);
+    else fidelity_dmma_kernel<1><<<tiles, PW_THREADS, FD_SMEM, st>>>(Psi, n, Psi, n, 2 * dim, 2 * P, nullptr, 0, Ainv, ld, alpha, P, partial, tmap);
     DQGP_LAUNCH_CHECK("fidelity_dmma_kernel<1>");
     return 0;
 }

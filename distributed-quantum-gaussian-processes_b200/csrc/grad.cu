@@ -9,8 +9,8 @@
 // Bound: FP64 pipe (3m + outer-kernel flops per entry); HBM traffic is one read of A^-1.
 #include <cstdlib>
 #include <cstring>
-#include <cuda.h>
 #include "pairwise.cuh"
+#include "tensormap.cuh"
 
 namespace dqgp {
 
@@ -304,30 +304,6 @@ __global__ void __launch_bounds__(PW_THREADS, 2) grad_projected_dmma_kernel(cons
     }
 }
 
-// F = [sets][n][m] doubles as a 3-D tensor map with a (1, 64, G2_PITCH) box.  false when the driver entry point is missing or refuses.
-static bool make_feature_tensor_map(CUtensorMap* out, const double* d_F, int n, int m, int sets) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    static bool looked = false;
-    if (!looked) {
-        looked = true;
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-            encode = reinterpret_cast<EncodeFn>(fn);
-        else
-            cudaGetLastError();
-    }
-    if (!encode) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)m, (cuuint64_t)n, (cuuint64_t)sets};
-    const cuuint64_t strides[2] = {(cuuint64_t)m * sizeof(double), (cuuint64_t)n * m * sizeof(double)};      // bytes, dimensions 1 and 2
-    const cuuint32_t box[3] = {(cuuint32_t)G2_PITCH, (cuuint32_t)PW_TILE, 1u};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(d_F), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // squared norms of every feature row: Nrm[s*n + j] = sum_k F[s][j][k]^2 (one warp per 4 rows)
 __global__ void feature_norms_kernel(const double* __restrict__ F, long long rows, int m, double scale, double* __restrict__ Nrm) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -602,7 +578,7 @@ int dqgp_grad_projected(int outer, const double* h_hyp, const double* d_Ainv, in
         CUtensorMap tmap;
         memset(&tmap, 0, sizeof(tmap));
         const bool have_tmap = use_bulk && !use_p28 && getenv("DQGP_GRAD_NO_TMAP") == nullptr && (m & 1) == 0 && m <= G2_PITCH &&
-                               (reinterpret_cast<uintptr_t>(d_F) & 15) == 0 && make_feature_tensor_map(&tmap, d_F, n, m, 2 * P + 1);
+                               (reinterpret_cast<uintptr_t>(d_F) & 15) == 0 && make_rows_tensor_map(&tmap, d_F, m, n, 2 * P + 1, G2_PITCH, PW_TILE);
 #define DQGP_G2(OUT)                                                                                                         \
     do {                                                                                                                     \
         static bool attr_done_dev[64] = {false};        /* the attribute is per DEVICE (as gemm_init's flags) */            \
