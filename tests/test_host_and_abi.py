@@ -41,7 +41,8 @@ def test_library_is_sm100a_dmma_code(d):
     assert "sm_100a" in sass
     assert "DMMA.8x8x4" in sass            # fp64 tensor path in the factorisation
     assert "LDGSTS" in sass                # async global->shared staging (GEMM operand ring)
-    assert "UBLKCP" in sass                # bulk-copy (TMA engine) staging of the gradient's / fidelity kernel's feature tiles
+    assert "UTMALDG.3D" in sass            # tensor-map (TMA) staging of the fused gradients' feature / state tiles
+    assert "UBLKCP" in sass                # per-row bulk copies: their fallback, and the Gram kernels' staging
     assert "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass      # ... completed on mbarriers
 
 
