@@ -443,6 +443,38 @@ def test_fused_gradient_honoured_outer_kernels_match_oracle(d, outer, enc, q, dd
             assert abs(float(eng.d_nll[3].item()) - comp["total"]) < 1e-8 * max(1.0, abs(comp["total"]))
 
 
+@pytest.mark.parametrize("enc,ktype,q,dd,layers,n,outer", [("yz_cx", "projected", 8, 4, 3, 333, "gaussian"), ("kyriienko", "projected", 10, 6, 2, 200, "matern"),
+                                                          ("yz_cx", "projected", 5, 3, 2, 64, "expsinesquared"), ("hubregtsen", "fidelity", 5, 2, 2, 333, "gaussian"),
+                                                          ("chebyshev", "fidelity", 2, 2, 1, 97, "gaussian")])
+def test_gradient_staging_paths_agree_bit_for_bit(d, monkeypatch, enc, ktype, q, dd, layers, n, outer):
+    """The fused gradients stage their tiles through a 3-D tensor map (TMA, the default), through one bulk copy per row
+    (DQGP_*_NO_TMAP) or through per-thread cp.async (DQGP_GRAD_NO_BULK): same arithmetic on the same operands, so the gradients must
+    be identical to the last bit - at ragged n, where the tensor map zero-fills the rows past n and the other paths clamp them."""
+    x, y = d.synthetic_dataset(n, dd, enc, seed=3)
+    eng = d.AgentEngine(x, y, encoding_type=enc, kernel_type=ktype, num_qubits=q, num_layers=layers, noise_std=0.1, rho=100.0, L=100.0,
+                        outer_kernel=outer, training_ignores_outer_kernel=False)
+    z = d.kernels.dev_f64(np.round(np.random.RandomState(1).rand(eng.P) * np.pi, 4))
+    eng.simulate(z); eng.gram(full=True)
+    rs = np.random.RandomState(2)                       # any symmetric "inverse" and alpha will do: the contraction is what is compared
+    b = rs.randn(n, n)
+    eng.solver.inverse()[:n, :n].copy_(torch.from_numpy(b + b.T).cuda())
+    eng.d_alpha.copy_(torch.from_numpy(rs.randn(n)).cuda())
+    grads = {}
+    for name, env in (("tensor map", {}), ("bulk rows", {"DQGP_GRAD_NO_TMAP": "1", "DQGP_FID_NO_TMAP": "1"}),
+                      ("cp.async", {"DQGP_GRAD_NO_TMAP": "1", "DQGP_FID_NO_TMAP": "1", "DQGP_GRAD_NO_BULK": "1"})):
+        for k in ("DQGP_GRAD_NO_TMAP", "DQGP_FID_NO_TMAP", "DQGP_GRAD_NO_BULK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng.d_grad.zero_()
+        eng.gradient()
+        torch.cuda.synchronize()
+        grads[name] = eng.d_grad.cpu().numpy().copy()
+    assert np.all(np.isfinite(grads["tensor map"])) and np.abs(grads["tensor map"]).max() > 0
+    assert np.array_equal(grads["tensor map"], grads["bulk rows"])
+    assert np.array_equal(grads["tensor map"], grads["cp.async"])
+
+
 @pytest.mark.parametrize("n", [1, 5, 33, 64, 100, 257, 700])
 @pytest.mark.parametrize("kind", ["indefinite", "general"])
 def test_lu_solve_inv_matches_lapack(d, n, kind):
