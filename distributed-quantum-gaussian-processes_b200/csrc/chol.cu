@@ -797,6 +797,7 @@ static int solver_create_impl(int n, int outer_blocks, int lean, dqgp_solver** o
 
     e = cudaMalloc(&s->d_tasks, sizeof(GemmTask) * tasks.size());
     if (e == cudaSuccess) e = cudaMemcpy(s->d_tasks, tasks.data(), sizeof(GemmTask) * tasks.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) gemm_register_maps(s->d_tasks, tasks.data(), (int)tasks.size());      // tensor maps of the operands (DQGP_GEMM_NO_TMAP: none)
     if (e == cudaSuccess) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -842,6 +843,7 @@ void dqgp_solver_destroy(dqgp_solver* s) {
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->helper) cudaStreamDestroy(s->helper);
+    dqgp::gemm_unregister_maps(s->d_tasks);
     cudaFree(s->A); cudaFree(s->W); cudaFree(s->T); cudaFree(s->y_pad); cudaFree(s->w); cudaFree(s->partial); cudaFree(s->strip); cudaFree(s->V); cudaFree(s->d_tasks); cudaFree(s->d_dyn); cudaFree(s->tmp);
     delete s;
 }

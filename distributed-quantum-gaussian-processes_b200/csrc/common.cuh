@@ -81,6 +81,12 @@ __device__ __forceinline__ void tensor_copy_3d_g2s(void* smem, const void* tmap,
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
                  ::"r"(d), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(b) : "memory");
 }
+__device__ __forceinline__ void tensor_copy_2d_g2s(void* smem, const void* tmap, int c0, int c1, unsigned long long* bar) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    const unsigned b = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 ::"r"(d), "l"(tmap), "r"(c0), "r"(c1), "r"(b) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 

@@ -1,13 +1,17 @@
 // Grouped fp64 GEMM, 128x64 tile per CTA, 8 warps (4x2) each owning 32x32 = 4x4 DMMA 8x8 blocks, two CTAs per SM
 // so one CTA's prologue / C read-modify-write overlaps the other's DMMA stream (v1 was 128x128, one CTA per SM:
 // 60% DMMA-pipe utilisation on the K=128 trailing updates, 83% on long K; ncu profiles/r01_v1_syrk0, _lauum).
-// Operands stream HBM/L2 -> shared memory through a 3-stage cp.async (LDGSTS) ring, 16-byte copies;
+// Operands stream HBM/L2 -> shared memory through a 3-stage ring: two tensor-map boxes per 16-deep k-chunk issued by one thread
+// (TMA, gemm_group_tmap_kernel, the default) or per-thread 16-byte cp.async (LDGSTS; the small-tile kernel and the fallback);
 // shared-memory pitches (20 / 132 doubles) make every DMMA fragment load bank-conflict-free.
 // A launch covers a *group* of independent tasks (device-resident table) so the many small products of
 // the recursive triangular inverse fill the machine in one launch.  Roofline: FP64 pipe (DMMA and DFMA
 // share it on B200: 37.1 TFLOP/s measured, profiles/r01_fp64_peak.json).
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 #include "gemm64.cuh"
+#include "tensormap.cuh"
 
 namespace dqgp {
 
@@ -47,8 +51,8 @@ __device__ __forceinline__ void gm_load_operand_bulk(double* sm, const double* _
     }
 }
 
-template <typename S, int AK, int BK, bool BULK>
-__device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* gm_smem);
+template <typename S, int AK, int BK, bool BULK, bool TMAP = false>
+__device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* gm_smem, const CUtensorMap* tmaps = nullptr);
 
 __device__ __forceinline__ int gm_find_task(const GemmTask* __restrict__ tasks, int n_tasks, int tile) {
     int lo = 0, hi = n_tasks - 1;
@@ -59,16 +63,18 @@ __device__ __forceinline__ int gm_find_task(const GemmTask* __restrict__ tasks, 
     return lo;
 }
 
-template <typename S, bool BULK>
-__device__ __forceinline__ void gm_dispatch(const GemmTask* __restrict__ tasks, int n_tasks, double* gm_smem) {
+template <typename S, bool BULK, bool TMAP = false>
+__device__ __forceinline__ void gm_dispatch(const GemmTask* __restrict__ tasks, int n_tasks, double* gm_smem, const CUtensorMap* maps = nullptr) {
     // locate the task that owns this tile (tables are short: <= a few hundred entries)
-    const GemmTask T = tasks[gm_find_task(tasks, n_tasks, blockIdx.x)];
+    const int ti = gm_find_task(tasks, n_tasks, blockIdx.x);
+    const GemmTask T = tasks[ti];
     const int local = blockIdx.x - T.tile_begin;
+    const CUtensorMap* tm = TMAP ? maps + 2 * ti : nullptr;      // this task's A and B operand maps
     // operand layouts are compile-time inside the tile routine (no predicated duplicate fragment loads)
     if (T.a_k_contig) {
-        if (T.b_k_contig) gemm_tile<S, 1, 1, BULK>(T, local, gm_smem); else gemm_tile<S, 1, 0, BULK>(T, local, gm_smem);
+        if (T.b_k_contig) gemm_tile<S, 1, 1, BULK, TMAP>(T, local, gm_smem, tm); else gemm_tile<S, 1, 0, BULK, TMAP>(T, local, gm_smem, tm);
     } else {
-        if (T.b_k_contig) gemm_tile<S, 0, 1, BULK>(T, local, gm_smem); else gemm_tile<S, 0, 0, BULK>(T, local, gm_smem);
+        if (T.b_k_contig) gemm_tile<S, 0, 1, BULK, TMAP>(T, local, gm_smem, tm); else gemm_tile<S, 0, 0, BULK, TMAP>(T, local, gm_smem, tm);
     }
 }
 
@@ -95,9 +101,21 @@ __global__ void __launch_bounds__(GemmSmall::THREADS, 4) gemm_small_bulk_kernel(
     extern __shared__ __align__(16) double gm_smem[];
     gm_dispatch<GemmSmall, true>(tasks, n_tasks, gm_smem);
 }
+// Operand tiles as TWO tensor-map boxes per k-chunk (TMA proper, SASS UTMALDG.2D), issued by one thread: the box is as wide as the padded
+// shared-memory pitch (20 for k-contiguous operands: the 4 doubles beyond the chunk are the next chunk's, never read; BM + 4 / BN + 4
+// otherwise), so the fragment layout stays bank-conflict-free without a swizzle.  The DEFAULT for every registered task table
+// (DQGP_GEMM_NO_TMAP=1 restores the cp.async ring): same box, one issuing thread instead of 768 LDGSTS per chunk - measured on one
+// B200, alternating runs: lauum 5.73 -> 5.31 ms (32.0 -> 34.5 TF = 0.93 of the FP64 peak), triangular inverse 6.15 -> 5.80 ms, potrf
+// 8.13 -> 7.79 ms, a lone n = 8192 factorisation 20.02 -> 18.89 ms, the N = 1 iteration of config 4 227.9 -> 219.2 ms; bit-identical
+// results.  (The per-row bulk copies above lost; what they lacked was the single issuing thread.)
+__global__ void __launch_bounds__(GemmBig::THREADS, 2) gemm_group_tmap_kernel(const GemmTask* __restrict__ tasks, int n_tasks,
+                                                                              const CUtensorMap* __restrict__ maps) {
+    extern __shared__ __align__(128) double gm_smem_t[];
+    gm_dispatch<GemmBig, true, true>(tasks, n_tasks, gm_smem_t, maps);
+}
 
-template <typename S, int AK, int BK, bool BULK>
-__device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* gm_smem) {
+template <typename S, int AK, int BK, bool BULK, bool TMAP>
+__device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* gm_smem, const CUtensorMap* tmaps) {
     __shared__ __align__(8) unsigned long long gm_bar[GM_STAGES];
     if (BULK) {
         if (threadIdx.x == 0) {
@@ -157,8 +175,16 @@ __device__ __forceinline__ void gemm_tile(const GemmTask& T, int local, double* 
     constexpr unsigned STAGE_BYTES = (GM_BM + GM_BN) * GM_KC * sizeof(double);
     constexpr int B_T0 = AK ? GM_BM : GM_KC;          // first thread that copies the B operand (after the A operand's copies)
     static_assert(GM_BM + GM_BN <= S::THREADS, "one bulk copy per thread");
+    constexpr unsigned TM_BYTES = ((AK ? GM_BM * GM_PITCH_K : GM_KC * GM_PITCH_M) + (BK ? GM_BN * GM_PITCH_K : GM_KC * GM_PITCH_N)) * sizeof(double);
     auto fill = [&](int s, int c) {
-        if (BULK) {
+        if (TMAP) {
+            if (threadIdx.x == 0) {
+                const int k = kb + c * GM_KC;
+                mbar_arrive_expect_tx(&gm_bar[s], TM_BYTES);
+                if (AK) tensor_copy_2d_g2s(stage_a(s), tmaps, k, m0, &gm_bar[s]); else tensor_copy_2d_g2s(stage_a(s), tmaps, m0, k, &gm_bar[s]);
+                if (BK) tensor_copy_2d_g2s(stage_b(s), tmaps + 1, k, n0, &gm_bar[s]); else tensor_copy_2d_g2s(stage_b(s), tmaps + 1, n0, k, &gm_bar[s]);
+            }
+        } else if (BULK) {
             if (threadIdx.x == 0) mbar_arrive_expect_tx(&gm_bar[s], STAGE_BYTES);
             gm_load_operand_bulk<GM_BM, GM_PITCH_M>(stage_a(s), T.A, T.lda, m0, kb + c * GM_KC, AK, 0, &gm_bar[s]);
             gm_load_operand_bulk<GM_BN, GM_PITCH_N>(stage_b(s), T.B, T.ldb, n0, kb + c * GM_KC, BK, B_T0, &gm_bar[s]);
@@ -236,14 +262,53 @@ int gemm_init() {
     DQGP_CUDA(cudaFuncSetAttribute(gemm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmall::SMEM_BYTES));
     DQGP_CUDA(cudaFuncSetAttribute(gemm_group_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmBig::SMEM_BYTES));
     DQGP_CUDA(cudaFuncSetAttribute(gemm_small_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmSmall::SMEM_BYTES));
+    DQGP_CUDA(cudaFuncSetAttribute(gemm_group_tmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmBig::SMEM_BYTES + 128));
     if (dev >= 0 && dev < 64) done[dev] = true;
     return 0;
+}
+
+// ---- tensor maps: registered task tables -> device arrays of (A map, B map) per task -----------------------------------------
+struct GemmMapTable { const GemmTask* d_tasks; int n; CUtensorMap* d_maps; };
+static std::vector<GemmMapTable>& gemm_map_tables() { static std::vector<GemmMapTable> t; return t; }
+static bool gemm_use_tmap() { static const bool on = getenv("DQGP_GEMM_NO_TMAP") == nullptr; return on; }
+
+void gemm_register_maps(const GemmTask* d_tasks, const GemmTask* h_tasks, int n_tasks) {
+    if (!gemm_use_tmap() || n_tasks <= 0) return;
+    std::vector<CUtensorMap> maps(2 * (size_t)n_tasks);
+    memset(maps.data(), 0, sizeof(CUtensorMap) * maps.size());
+    for (int i = 0; i < n_tasks; ++i) {
+        const GemmTask& t = h_tasks[i];
+        // k-contiguous: rows of K values, box = (tile rows) x (chunk + padding); otherwise rows of M (N) values, box = (chunk) x (tile + padding)
+        const bool oka = t.a_k_contig ? make_matrix_tensor_map(&maps[2 * i], t.A, t.K, t.M, t.lda, GM_PITCH_K, GM_BM)
+                                      : make_matrix_tensor_map(&maps[2 * i], t.A, t.M, t.K, t.lda, GM_PITCH_M, GM_KC);
+        const bool okb = t.b_k_contig ? make_matrix_tensor_map(&maps[2 * i + 1], t.B, t.K, t.N, t.ldb, GM_PITCH_K, GM_BN)
+                                      : make_matrix_tensor_map(&maps[2 * i + 1], t.B, t.N, t.K, t.ldb, GM_PITCH_N, GM_KC);
+        if (!oka || !okb) return;                  // the driver refused a map: this table stays on the cp.async ring
+    }
+    CUtensorMap* d_maps = nullptr;
+    if (cudaMalloc(&d_maps, sizeof(CUtensorMap) * maps.size()) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaMemcpy(d_maps, maps.data(), sizeof(CUtensorMap) * maps.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(d_maps); return; }
+    gemm_map_tables().push_back({d_tasks, n_tasks, d_maps});
+}
+
+void gemm_unregister_maps(const GemmTask* d_tasks) {
+    auto& tabs = gemm_map_tables();
+    for (size_t i = 0; i < tabs.size(); ++i)
+        if (tabs[i].d_tasks == d_tasks) { cudaFree(tabs[i].d_maps); tabs.erase(tabs.begin() + i); return; }
 }
 
 int launch_gemm_group(const GemmTask* d_tasks, int n_tasks, int total_tiles, cudaStream_t st) {
     if (n_tasks <= 0 || total_tiles <= 0) return 0;
     int rc = gemm_init();
     if (rc) return rc;
+    if (gemm_use_tmap()) {
+        for (const GemmMapTable& tab : gemm_map_tables())
+            if (d_tasks >= tab.d_tasks && d_tasks + n_tasks <= tab.d_tasks + tab.n) {
+                gemm_group_tmap_kernel<<<total_tiles, GemmBig::THREADS, GemmBig::SMEM_BYTES + 128, st>>>(d_tasks, n_tasks, tab.d_maps + 2 * (d_tasks - tab.d_tasks));
+                DQGP_LAUNCH_CHECK("gemm_group_tmap_kernel");
+                return 0;
+            }
+    }
     static const bool use_bulk = getenv("DQGP_GEMM_BULK") != nullptr;
     if (use_bulk) gemm_group_bulk_kernel<<<total_tiles, GemmBig::THREADS, GemmBig::SMEM_BYTES, st>>>(d_tasks, n_tasks);
     else gemm_group_kernel<<<total_tiles, GemmBig::THREADS, GemmBig::SMEM_BYTES, st>>>(d_tasks, n_tasks);

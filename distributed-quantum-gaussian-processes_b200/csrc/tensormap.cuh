@@ -31,4 +31,29 @@ static inline bool make_rows_tensor_map(CUtensorMap* out, const double* base, in
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// A row-major matrix view [outer][inner] doubles with row stride ld (doubles, even) as a 2-D tensor map with a (box_outer, box_inner) box.
+static inline bool make_matrix_tensor_map(CUtensorMap* out, const double* base, long long inner, long long outer, long long ld, int box_inner,
+                                          int box_outer) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+        else
+            cudaGetLastError();
+    }
+    if (!encode || (ld & 1) || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace dqgp

@@ -40,8 +40,9 @@ def test_library_is_sm100a_dmma_code(d):
     sass = subprocess.run(["cuobjdump", "-sass", d._lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
     assert "DMMA.8x8x4" in sass            # fp64 tensor path in the factorisation
-    assert "LDGSTS" in sass                # async global->shared staging (GEMM operand ring)
+    assert "LDGSTS" in sass                # per-thread async staging (the GEMM's fallback ring, small-tile kernel)
     assert "UTMALDG.3D" in sass            # tensor-map (TMA) staging of the fused gradients' feature / state tiles
+    assert "UTMALDG.2D" in sass            # ... and of the GEMM's operand tiles
     assert "UBLKCP" in sass                # per-row bulk copies: their fallback, and the Gram kernels' staging
     assert "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass      # ... completed on mbarriers
 
