@@ -281,9 +281,10 @@ def measure(args, w, workload_name, pg, world, rank, local_rank, full):
     if "executed" in primary:            # the headline fraction is the one that cannot exceed 1
         primary["achieved_algorithmic"], primary["achieved"] = primary["achieved"], primary["executed"]
         primary["frac"] = primary["frac_executed"]
-    traffic = load_json(os.path.join(ROOT, "profiles", "r01_traffic.json"), {})
+    traffic_file = "r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01_traffic.json"
+    traffic = load_json(os.path.join(ROOT, "profiles", traffic_file), {})
     primary.update({"kernel": {"gradient": "grad_projected_dmma_kernel" if w["kernel"] == "projected" else "fidelity_dmma_kernel<1>",
-                               "factor": "gemm_group_kernel", "gram": "gram_projected_dmma_kernel",
+                               "factor": "gemm_group_kernel" if os.environ.get("DQGP_GEMM_NO_TMAP") else "gemm_group_tmap_kernel", "gram": "gram_projected_dmma_kernel",
                                "statevector": ("statevec_lc2_kernel<%d>" if w["encoding"] in ("yz_cx", "kyriienko") else "statevec_lc_kernel<%d>") % w["q"]}[dominant], "phase": dominant,
                     "traffic": None, "peak_source": "profiles/r01_fp64_peak.json (measured on this pool: pure DMMA/DFMA issue loops)"
                     if primary["bound"] != "hbm" else "MEASURED_PEAKS.json"})
@@ -291,7 +292,7 @@ def measure(args, w, workload_name, pg, world, rank, local_rank, full):
     tk = traffic.get(primary["kernel"].replace("grad_projected_kernel", "grad_projected_dmma_kernel"), {})
     if tk.get("dram_bytes"):
         primary["traffic"] = tk["dram_bytes"]
-        primary["traffic_note"] = ("dram__bytes_read+write of one launch under ncu (profiles/r01_traffic.json): " + tk.get("launch", tk.get("note", "")))
+        primary["traffic_note"] = (f"dram__bytes_read+write of one launch under ncu (profiles/{traffic_file}): " + tk.get("launch", tk.get("note", "")))
 
     # ---- e2e: host buffers through RiemannianAgent.train_and_update + host consensus ------------------------------
     e2e = None if (args.skip_e2e or not full) else run_e2e(args, w, d, torch, dist, world, rank, shards, theta0, psi0, n_i, P, entries_per_iter)
