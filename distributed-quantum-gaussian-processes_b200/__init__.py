@@ -14,8 +14,9 @@ from .kernels import (EncodingCircuit, Executor, FidelityKernel, ProjectedQuantu
 from .agent import RiemannianAgent, process_agent_training, train_agents  # noqa: F401
 from .engine import AgentEngine, AdmmEngine, agent_block, exchange_rows, synthetic_dataset  # noqa: F401
 from .datagen import generate_quantum_gp_data  # noqa: F401
-from .data import (get_tile_for_region, load_srtm_elevation_dataset, prepare_training_data, read_hgt_file,  # noqa: F401
-                   sample_agent_data_percentage, split_data_numpy, split_indices)
+from .data import (evaluate_predictions, generate_data_numpy, get_tile_for_region, load_srtm_elevation_dataset,  # noqa: F401
+                   prepare_training_data, read_hgt_file, sample_agent_data_percentage, save_quantum_dataset, split_data_numpy,
+                   split_indices)
 from .driver import run_admm  # noqa: F401
 from .predict import k_fold_cross_validation_consensus, nlpd, predict_quantum_gp  # noqa: F401
 

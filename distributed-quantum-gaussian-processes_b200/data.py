@@ -2,6 +2,9 @@
 ``real_world_datasets.py:238-572`` and the agent partitioning of ``main.py:524-682`` (regular grid / k-d bisection / random /
 sequential, optional per-agent subsampling), with the reference's names, argument meaning and error behaviour.
 
+Also here, on the output side: ``evaluate_predictions`` (the metric dictionary of main.py:1598-1736, NLPD included), and the small
+dataset helpers ``generate_data_numpy`` (main.py:457-522, the "classical dataset" mode) and ``save_quantum_dataset`` (main.py:433-455).
+
 This is index and byte work on a few thousand rows; it stays in NumPy by design (the shards reach the GPU once, through the
 engine's persistent pinned staging buffers).  Every function here selects exactly the rows the reference selects on the same
 inputs - ``tests/test_data_plumbing.py`` compares with outputs of the real reference functions (``tests/golden/data_plumbing.npz``).
@@ -174,3 +177,80 @@ def prepare_training_data(X_full, Y_full, n_agents, partition_method="regional",
     x_tr, x_te, y_tr, y_te = train_test_split(X_full, Y_full, test_size=test_split, shuffle=True,
                                               random_state=seed if split_seed is None else split_seed)
     return split_data_numpy(x_tr, y_tr, n_agents, partition_method, data_percentage, seed), (x_tr, y_tr), (x_te, y_te)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def generate_data_numpy(num_samples, input_dim=1, noise_std=0.1, data_seed=None):
+    """main.py:457-522, the ``--classical-dataset`` mode: inputs from ``np.random.seed(data_seed)`` + ``uniform``, a closed-form test
+    function (1-D: the GRBCM paper's function on [0,1]; 2-D: normalised Goldstein-Price on [-2,2]^2; 3-D: negated Hartmann-3 on
+    [0,1]^3) plus ``normal(0, noise_std)`` from the same stream.  ``data_seed=None`` = wall-clock seed, as in the reference."""
+    if data_seed is None:
+        import time
+        data_seed = int(time.time() * 1000) % 2 ** 32
+    np.random.seed(data_seed)
+    if input_dim == 1:
+        X = np.random.uniform(0, 1, size=(num_samples, 1))
+        x = X[:, 0]
+        Y = 5 * x ** 2 * np.sin(12 * x) + (x ** 3 - 0.5) * np.sin(3 * x - 0.5) + 4 * np.cos(2 * x)
+    elif input_dim == 2:
+        X = np.random.uniform(-2.0, 2.0, size=(num_samples, 2))
+        u, v = X[:, 0], X[:, 1]
+        first = 1 + (u + v + 1) ** 2 * (19 - 14 * u + 3 * u ** 2 - 14 * v + 6 * u * v + 3 * v ** 2)
+        second = 30 + (2 * u - 3 * v) ** 2 * (18 - 32 * u + 12 * u ** 2 + 48 * v - 36 * u * v + 27 * v ** 2)
+        Y = (np.log(first * second) - 8.693) / 2.427
+    elif input_dim == 3:
+        X = np.random.uniform(0.0, 1.0, size=(num_samples, 3))
+        weights = np.array([1.0, 1.2, 3.0, 3.2])
+        widths = np.array([[3.0, 10.0, 30.0], [0.1, 10.0, 35.0], [3.0, 10.0, 30.0], [0.1, 10.0, 35.0]])
+        centres = 1e-4 * np.array([[3689.0, 1170.0, 2673.0], [4699.0, 4387.0, 7470.0], [1091.0, 8732.0, 5547.0], [381.0, 5743.0, 8828.0]])
+        Y = np.zeros(num_samples)
+        for w, a, c in zip(weights, widths, centres):
+            Y += w * np.exp(-np.sum(a * (X - c) ** 2, axis=1))
+        Y = -Y
+    else:
+        raise ValueError(f"Unsupported input dimension: {input_dim}")
+    Y += np.random.normal(0, noise_std, num_samples)
+    return X, Y
+
+
+def save_quantum_dataset(X, Y, dataset_name, output_dir="quantum_datasets"):
+    """main.py:433-455: one CSV ``<name>_<d>d_<n>.csv`` with the header ``X1,...,Xd,Y``; returns its path."""
+    os.makedirs(output_dir, exist_ok=True)
+    path = os.path.join(output_dir, f"{dataset_name}_{X.shape[1]}d_{X.shape[0]}.csv")
+    header = ",".join([f"X{i + 1}" for i in range(X.shape[1])] + ["Y"])
+    np.savetxt(path, np.column_stack((X, Y)), delimiter=",", header=header, comments="")
+    return path
+
+
+def _grade(value, cuts, labels):
+    for cut, label in zip(cuts, labels):
+        if value > cut:
+            return label
+    return labels[-1]
+
+
+def evaluate_predictions(Y_true, Y_pred, Y_pred_var=None, dataset_type="Test"):
+    """main.py:1598-1736 without the printing: mse, rmse, mae, r2, max_error, mean / std of the residuals, range-normalised rmse and
+    the verbal grade; with variances also mean predictive std, 1-sigma / 2-sigma coverage, the uncertainty-normalised rmse, the mean NLPD
+    (variance floored at 1e-10, main.py:1657-1662) and the calibration grade.  ``dataset_type`` only labelled the printout."""
+    y, p = np.asarray(Y_true, dtype=np.float64), np.asarray(Y_pred, dtype=np.float64)
+    res = y - p
+    mse = float(np.mean(res ** 2))
+    rmse = float(np.sqrt(mse))
+    spread = float(np.sum((y - np.mean(y)) ** 2))
+    r2 = 1.0 - float(np.sum(res ** 2)) / spread if spread > 0 else (1.0 if np.sum(res ** 2) == 0 else 0.0)
+    y_range = y.max() - y.min()
+    out = {"mse": mse, "rmse": rmse, "mae": float(np.mean(np.abs(res))), "r2": r2, "max_error": np.max(np.abs(res)),
+           "mean_residual": np.mean(res), "std_residual": np.std(res),
+           "normalized_rmse_range": rmse / y_range if y_range > 0 else float("inf"),
+           "performance": _grade(r2, (0.9, 0.7, 0.5), ("Excellent", "Good", "Fair", "Poor"))}
+    if Y_pred_var is not None:
+        var = np.asarray(Y_pred_var, dtype=np.float64)
+        std = np.sqrt(var)
+        one, two = np.mean(np.abs(res) <= std), np.mean(np.abs(res) <= 2 * std)
+        safe = np.maximum(var, 1e-10)
+        nlpd = np.mean(0.5 * np.log(2 * np.pi) + 0.5 * np.log(safe) + 0.5 * (res ** 2 / safe))
+        quality = "Good" if one > 0.5 and two > 0.8 else ("Fair" if one > 0.4 and two > 0.7 else "Poor")
+        out.update({"mean_uncertainty": np.mean(std), "within_1sigma": one, "within_2sigma": two,
+                    "normalized_rmse_uncertainty": np.sqrt(np.mean((res / std) ** 2)), "nlpd": nlpd, "uncertainty_quality": quality})
+    return out

@@ -117,3 +117,41 @@ def test_srtm_loader_errors(tile_dir):
     with pytest.raises(FileNotFoundError, match="Preprocessed file not found"):
         d.load_srtm_elevation_dataset(region="maharashtra", use_preprocessed=True, preprocessed_dir=tile_dir)
     assert d.get_tile_for_region("oregon_coast") == "N45W123" and d.get_tile_for_region("N00E000") == "N00E000"
+
+
+@pytest.mark.parametrize("dim,n,noise,seed", [(1, 57, 0.1, 3), (2, 64, 0.05, 11), (3, 41, 0.2, 2024)])
+def test_generate_data_numpy_equals_reference(dim, n, noise, seed):
+    """The --classical-dataset generator (main.py:457-522): the inputs bit for bit (same random stream), the targets to rounding."""
+    gold = load_golden("data_plumbing.npz")
+    x, y = d.generate_data_numpy(n, dim, noise, seed)
+    assert np.array_equal(x, gold[f"classical_{dim}d_X"])
+    assert np.max(np.abs(y - gold[f"classical_{dim}d_Y"])) < 1e-13
+    with pytest.raises(ValueError, match="Unsupported input dimension: 4"):
+        d.generate_data_numpy(5, 4, 0.1, 1)
+
+
+@pytest.mark.parametrize("tag", ["novar", "var"])
+def test_evaluate_predictions_equals_reference(tag):
+    """The metric dictionary of main.py:1598-1736 (scikit-learn's mse / mae / r2 there, plain NumPy here): same keys, numbers to
+    1e-12, same verbal grades; three predicted variances are zero (NLPD floor 1e-10, infinite calibration rmse as in the reference)."""
+    gold = load_golden("data_plumbing.npz")
+    y_true, y_pred, y_var = G.prediction_case()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        got = d.evaluate_predictions(y_true, y_pred, None if tag == "novar" else y_var)
+    want = {k[len(f"metrics_{tag}_"):]: gold[k] for k in gold.files if k.startswith(f"metrics_{tag}_")}
+    assert set(got) == set(want)
+    for k, v in want.items():
+        if v.dtype.kind in "US":
+            assert got[k] == str(v), k
+        elif np.isfinite(v):
+            assert abs(got[k] - float(v)) <= 1e-12 * max(1.0, abs(float(v))), k
+        else:
+            assert not np.isfinite(got[k]) and np.isnan(got[k]) == np.isnan(v), k
+
+
+def test_save_quantum_dataset_writes_the_reference_csv(tmp_path):
+    gold = load_golden("data_plumbing.npz")
+    x, y = CASES["grid_2d_4"][:2]
+    path = d.save_quantum_dataset(x[:5], y[:5], "golden", output_dir=str(tmp_path / "out"))
+    assert os.path.basename(path) == str(gold["csv_name"]) == "golden_2d_5.csv"
+    assert open(path).read() == str(gold["csv_text"])
